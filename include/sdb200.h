@@ -1,0 +1,158 @@
+/* libsdb200 -- C ABI of the B200-native SlotDiffusion hot path.
+ *
+ * The reference (Wuziyi616/SlotDiffusion) is pure Python/PyTorch and has no FFI; every entry
+ * point below replaces the ATen/cuDNN/cuBLAS call sequence that the cited reference lines
+ * issue from eager PyTorch.  The Python host (slotdiffusion_b200/*.py)
+ * binds these with ctypes and mirrors the reference nn.Module interfaces on top.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch allocates; the library never
+ *     allocates or frees device memory and keeps no pointer after the call returns);
+ *   - `stream` is a cudaStream_t; calls only enqueue work (no sync, no host read-back), so a
+ *     sequence of calls is CUDA-graph capturable;
+ *   - return 0 on success, SDB_ERR_* otherwise; sdb_last_error() gives the message (thread-local);
+ *   - fp32 tensors are row-major contiguous unless a leading dimension is passed;
+ *   - "packed" = GEMM operand format: fp16 [2][rows][K], plane 0 = hi = fp16(x), plane 1 = lo =
+ *     fp16(x - hi).  hi*hi + hi*lo + lo*hi on the fp16 tensor pipe with fp32 accumulation
+ *     reproduces an fp32 product to ~2^-22 (DESIGN.md "precision").
+ */
+#ifndef SDB200_H_
+#define SDB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDB_OK 0
+#define SDB_ERR_INVALID 1 /* bad shape / alignment / argument */
+#define SDB_ERR_CUDA 2    /* a CUDA runtime/driver call failed */
+#define SDB_ERR_UNSUPPORTED 3
+
+int sdb_version(void);
+const char* sdb_last_error(void);
+/* number of kernels this library has launched in this process (bench.py "gpu_launches") */
+int64_t sdb_launch_count(void);
+
+/* ------------------------------------------------------------------ GEMM (tcgen05 / TMEM / TMA)
+ * C[M,N] = A[M,K] * W[N,K]^T (+ bias[N]) (+ rowvec[m / rows_per_group, N]) (+ residual[M,N])
+ * A and W are packed operands.  Replaces nn.Linear / nn.Conv2d(1x1, 3x3) calls:
+ *   unet.py:222,249,258 (ResBlock convs), :408 (input conv), :161-168 (Downsample), :111-112
+ *   (Upsample conv), attention.py:175-180,278-295 (to_q/k/v/out, proj_in/out), :44,60 (GEGLU FF),
+ *   unet.py:400-403,240 (time_embed, emb_layers), slot_attention.py:41,43-44,47,50-52.
+ * mode SDB_A_PLAIN : A is [M,K] row-major.
+ * mode SDB_A_CONV3 : A is an NHWC activation [B,H,W,C]; implicit im2col, 3x3, pad 1, stride 1;
+ *                    M = B*H*W, K = 9*C with k = (ky*3+kx)*C + c  (W packed by sdb_pack_weight_conv3).
+ * mode SDB_A_CONV3S2: A is a phase-split NHWC activation [B,4,H,W,C] (phase = (iy&1)*2 + (ix&1),
+ *                    H,W = OUTPUT size = input/2) produced by sdb_pack_nhwc(..., SDB_PACK_PHASE2);
+ *                    3x3, pad 1, stride 2.
+ */
+#define SDB_A_PLAIN 0
+#define SDB_A_CONV3 1
+#define SDB_A_CONV3S2 2
+
+typedef struct SdbGemm {
+  const void* a;         /* packed A, planes are a_plane_stride halves apart */
+  const void* w;         /* packed W [2][N][K] */
+  float* c;              /* [M, ldc] */
+  const float* bias;     /* [N] or NULL */
+  const float* rowvec;   /* [M / rows_per_group, ldv] or NULL (ResBlock timestep-embedding add, unet.py:280-283) */
+  const float* residual; /* [M, ldr] or NULL */
+  int64_t a_plane_stride; /* halves between the hi and lo plane of A */
+  int64_t ldc, ldv, ldr;
+  int32_t M, N, K;
+  int32_t mode;
+  int32_t B, H, W, C;     /* conv geometry (modes 1,2) */
+  int32_t rows_per_group; /* H*W for rowvec */
+  int32_t passes;         /* 3 = hi*hi + lo*hi + hi*lo (fp32-faithful), 1 = hi*hi only */
+  int32_t relu;           /* apply max(.,0) to the result (slot-attention MLP, slot_attention.py:51) */
+} SdbGemm;
+
+int sdb_gemm(const SdbGemm* p, void* stream);
+
+/* ------------------------------------------------------------------ operand producers */
+/* W [N,K] fp32 (nn.Linear / 1x1 conv weight) -> packed [2][N][K] */
+int sdb_pack_weight(const float* w, void* out, int64_t N, int64_t K, void* stream);
+/* W [Cout,Cin,3,3] -> packed [2][Cout][9*Cin], k = (ky*3+kx)*Cin + c */
+int sdb_pack_weight_conv3(const float* w, void* out, int64_t Cout, int64_t Cin, void* stream);
+
+/* rows x [M,K] (ldx) -> packed [2][M][K]; act: 0 none, 1 SiLU (unet.py:237-238), 2 ReLU */
+int sdb_pack_rows(const float* x, int64_t ldx, void* out, int64_t M, int64_t K, int act, void* stream);
+
+/* LayerNorm over the last dim (eps, affine) then pack: nn.LayerNorm at attention.py:232-234,
+ * slot_attention.py:36,40,49.  y (optional, may be NULL) also receives the fp32 result. */
+int sdb_layernorm_pack(const float* x, const float* gamma, const float* beta, float eps, void* out, float* y,
+                       int64_t M, int64_t C, void* stream);
+
+/* GroupNorm statistics of an NHWC activation that is the channel-concatenation of x1 [B,HW,C1] and
+ * x2 [B,HW,C2] (x2 may be NULL, C2 = 0): stats[b][g] = (mean, rstd); groups of (C1+C2)/G channels.
+ * GroupNorm32 (unet/utils.py:136-139, eps 1e-5) and Normalize (attention.py:77-79, eps 1e-6). */
+int sdb_groupnorm_stats(const float* x1, int64_t C1, const float* x2, int64_t C2, float* stats, int64_t B,
+                        int64_t HW, int G, float eps, void* stream);
+/* apply GN (+ optional SiLU) and pack: out = packed [2][B*HW][C1+C2] */
+int sdb_groupnorm_apply_pack(const float* x1, int64_t C1, const float* x2, int64_t C2, const float* stats,
+                             const float* gamma, const float* beta, void* out, int64_t B, int64_t HW, int G,
+                             int silu, void* stream);
+
+/* raw NHWC -> packed, with layout transform.  x1 [B,H,W,C1] (+ x2 [B,H,W,C2] concatenated on C).
+ *  SDB_PACK_PLAIN : out [2][B*H*W][C]                      (skip_connection 1x1 conv input, unet.py:256-259)
+ *  SDB_PACK_UP2   : nearest x2 upsample, out [2][B*2H*2W][C]   (Upsample, unet.py:118)
+ *  SDB_PACK_PHASE2: out [2][B][4][H/2][W/2][C], phase = (y&1)*2+(x&1)   (Downsample stride-2 conv, unet.py:161-168)
+ *  y_cat (optional): also write the fp32 concatenation [B,H,W,C1+C2] (th.cat at unet.py:572). */
+#define SDB_PACK_PLAIN 0
+#define SDB_PACK_UP2 1
+#define SDB_PACK_PHASE2 2
+int sdb_pack_nhwc(const float* x1, int64_t C1, const float* x2, int64_t C2, void* out, float* y_cat, int64_t B,
+                  int64_t H, int64_t W, int mode, void* stream);
+
+/* GEGLU: u [M, 2F] -> packed [2][M][F] of u[:, :F] * gelu_erf(u[:, F:])   (attention.py:46-48) */
+int sdb_geglu_pack(const float* u, void* out, int64_t M, int64_t F, void* stream);
+
+/* sinusoidal timestep embedding, [cos | sin] order, fp32 freqs (unet/utils.py:79-86) -> packed [2][B][dim] */
+int sdb_timestep_embedding_pack(const float* t, void* out, int64_t B, int dim, void* stream);
+
+/* ------------------------------------------------------------------ attention core (attention.py:188-205)
+ * out[b, i, h*d:(h+1)*d] = softmax_j(scale * q[b,i,h,:] . k[b,j,h,:]) v[b,j,h,:],   d = head dim (32)
+ * q [B,Lq,*] with row stride ldq, k/v [B,Lk,*] with row strides ldk/ldv (views into fused projections).
+ * out: packed [2][B*Lq][heads*d] (feeds to_out) */
+int sdb_attention_pack(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                       void* out, int64_t B, int64_t Lq, int64_t Lk, int heads, int d, float scale, void* stream);
+
+/* ------------------------------------------------------------------ small-channel convolutions
+ * input conv (unet.py:408): x NCHW [B,Cin,H,W] (Cin small, e.g. 3) -> NHWC fp32 [B,H,W,Cout], 3x3 pad 1 */
+int sdb_conv3_in(const float* x, const float* w, const float* bias, float* y, int64_t B, int64_t Cin, int64_t H,
+                 int64_t W, int64_t Cout, void* stream);
+/* output head (unet.py:537-542): y NCHW [B,Cout,H,W] = conv3x3(SiLU(GN(h))) for NHWC h [B,H,W,C], Cout small */
+int sdb_conv3_out(const float* h, const float* stats, const float* gamma, const float* beta, const float* w,
+                  const float* bias, float* y, int64_t B, int64_t H, int64_t W, int64_t C, int G, int64_t Cout,
+                  void* stream);
+
+/* ------------------------------------------------------------------ Slot Attention (slot_attention.py:55-104,
+ * sa_diffusion.py:15-70).  One attention iteration over the tokens of every sample, fused:
+ *   logits = scale * k q^T ; attn = softmax over slots ; (optional) seg_mask[b,s,n] = attn ;
+ *   a = attn + eps ; updates[b,s,:] = sum_n a[n,s] v[n,:] / sum_n a[n,s]
+ * kv [B,N,2D] (k | v fused projection of LayerNorm(inputs)), q [B,S,D].
+ * updates: packed [2][B*S][D] (feeds the GRU input GEMM) and fp32 upd32 (optional, may be NULL).
+ * work: fp32 scratch of sdb_slot_attend_workspace(B,N,S,D) bytes. */
+int64_t sdb_slot_attend_workspace(int64_t B, int64_t N, int64_t S, int64_t D);
+int sdb_slot_attend(const float* kv, const float* q, float* seg_mask, void* upd_packed, float* upd32, float* work,
+                    int64_t B, int64_t N, int64_t S, int64_t D, float scale, float eps, void* stream);
+/* GRUCell pointwise part (PyTorch gate order r,z,n; slot_attention.py:97-100): gi = x W_ih^T + b_ih and
+ * gh = h W_hh^T + b_hh come from sdb_gemm; h_new = (1-z) n + z h.  All [R, 3D] / [R, D]. */
+int sdb_gru_gates(const float* gi, const float* gh, const float* h, float* h_new, int64_t R, int64_t D,
+                  void* stream);
+
+/* ------------------------------------------------------------------ DPM-Solver++ glue (dpm_solver.py:523-534,
+ * :804-831; quantize.py:84-94).  Latents are NCHW fp32 [B,C,HW]. */
+/* x0 = (x - sigma*eps)/alpha ; if codebook != NULL: x0 = nearest codebook row (squared distance, first min) */
+int sdb_dpm_x0(const float* x, const float* eps, float alpha, float sigma, const float* codebook, int64_t ncodes,
+               float* x0, int32_t* idx /*optional*/, int64_t B, int64_t C, int64_t HW, void* stream);
+/* out = a*x + b*m0 + c*(m1 - m0)   (m1 may be NULL -> c ignored) */
+int sdb_lincomb(float* out, const float* x, const float* m0, const float* m1, float a, float b, float c,
+                int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDB200_H_ */

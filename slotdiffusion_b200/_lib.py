@@ -1,0 +1,86 @@
+"""ctypes binding of libsdb200.so (the C ABI declared in include/sdb200.h).
+
+There is NO fallback: if the shared library is missing or a call fails, a RuntimeError is raised.
+"""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libsdb200.so')
+
+SDB_A_PLAIN, SDB_A_CONV3, SDB_A_CONV3S2 = 0, 1, 2
+SDB_PACK_PLAIN, SDB_PACK_UP2, SDB_PACK_PHASE2 = 0, 1, 2
+
+
+class SdbGemm(Structure):
+    _fields_ = [
+        ('a', c_void_p), ('w', c_void_p), ('c', c_void_p), ('bias', c_void_p), ('rowvec', c_void_p),
+        ('residual', c_void_p), ('a_plane_stride', c_int64), ('ldc', c_int64), ('ldv', c_int64), ('ldr', c_int64),
+        ('M', c_int32), ('N', c_int32), ('K', c_int32), ('mode', c_int32), ('B', c_int32), ('H', c_int32),
+        ('W', c_int32), ('C', c_int32), ('rows_per_group', c_int32), ('passes', c_int32), ('relu', c_int32),
+    ]
+
+
+# name -> (restype, argtypes); must list every symbol declared in include/sdb200.h
+SIGNATURES = {
+    'sdb_version': (c_int, []),
+    'sdb_last_error': (c_char_p, []),
+    'sdb_launch_count': (c_int64, []),
+    'sdb_gemm': (c_int, [POINTER(SdbGemm), c_void_p]),
+    'sdb_pack_weight': (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
+    'sdb_pack_weight_conv3': (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
+    'sdb_pack_rows': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_void_p]),
+    'sdb_layernorm_pack': (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int64, c_int64,
+                                   c_void_p]),
+    'sdb_groupnorm_stats': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int,
+                                    c_float, c_void_p]),
+    'sdb_groupnorm_apply_pack': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
+                                         c_void_p, c_int64, c_int64, c_int, c_int, c_void_p]),
+    'sdb_pack_nhwc': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int64,
+                              c_int, c_void_p]),
+    'sdb_geglu_pack': (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
+    'sdb_timestep_embedding_pack': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    'sdb_attention_pack': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,
+                                   c_int64, c_int64, c_int, c_int, c_float, c_void_p]),
+    'sdb_conv3_in': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64,
+                             c_void_p]),
+    'sdb_conv3_out': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                              c_int64, c_int64, c_int64, c_int, c_int64, c_void_p]),
+    'sdb_slot_attend_workspace': (c_int64, [c_int64, c_int64, c_int64, c_int64]),
+    'sdb_slot_attend': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
+                                c_int64, c_int64, c_float, c_float, c_void_p]),
+    'sdb_gru_gates': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
+    'sdb_dpm_x0': (c_int, [c_void_p, c_void_p, c_float, c_float, c_void_p, c_int64, c_void_p, c_void_p, c_int64,
+                           c_int64, c_int64, c_void_p]),
+    'sdb_lincomb': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_int64, c_void_p]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load libsdb200.so (once).  Raises RuntimeError if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f'{LIB_PATH} not found: build it with `python -m slotdiffusion_b200.build` '
+                '(there is no CPU / PyTorch fallback for the hot path)')
+        l = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)          # AttributeError if the symbol is missing
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().sdb_last_error().decode(errors='replace')
+        raise RuntimeError(f'{what} failed (code {rc}): {msg}')
+
+
+def launch_count():
+    return int(lib().sdb_launch_count())

@@ -1,0 +1,44 @@
+// Error plumbing, device queries and bookkeeping shared by every entry point of libsdb200.
+#include <stdarg.h>
+#include <string.h>
+
+#include <atomic>
+
+#include "common.cuh"
+
+namespace sdb {
+
+static thread_local char g_err[1024] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) {
+    g_launches.fetch_add(strstr(what, "cudaGetLastError") ? 1 : 0, std::memory_order_relaxed);
+    return 0;
+  }
+  set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+  return SDB_ERR_CUDA;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+}  // namespace sdb
+
+extern "C" int sdb_version(void) { return 1; }
+extern "C" const char* sdb_last_error(void) { return sdb::g_err; }
+extern "C" int64_t sdb_launch_count(void) { return sdb::g_launches.load(); }

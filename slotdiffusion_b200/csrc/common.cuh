@@ -1,0 +1,58 @@
+// Shared host/device helpers for libsdb200.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/sdb200.h"
+
+namespace sdb {
+
+// ---- error plumbing (no C++ exceptions cross the ABI) ----
+void set_error(const char* fmt, ...);
+int check_cuda(cudaError_t e, const char* what);
+#define SDB_CHECK(expr)                                   \
+  do {                                                    \
+    int _rc = ::sdb::check_cuda((expr), #expr);           \
+    if (_rc) return _rc;                                  \
+  } while (0)
+#define SDB_REQUIRE(cond, ...)                            \
+  do {                                                    \
+    if (!(cond)) {                                        \
+      ::sdb::set_error(__VA_ARGS__);                      \
+      return SDB_ERR_INVALID;                             \
+    }                                                     \
+  } while (0)
+#define SDB_LAUNCH_CHECK() SDB_CHECK(cudaGetLastError())
+
+int num_sms();
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- fp32 -> (fp16 hi, fp16 lo) split: x ~= hi + lo with ~22 mantissa bits ----
+__device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
+  // saturate instead of producing inf for |x| > 65504 (never reached by normalised activations)
+  x = fminf(fmaxf(x, -65504.f), 65504.f);
+  hi = __float2half_rn(x);
+  lo = __float2half_rn(x - __half2float(hi));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + __expf(-x)); }
+__device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+
+}  // namespace sdb

@@ -1,0 +1,574 @@
+// Memory-bound producers of GEMM operands and the small fused pointwise kernels of the hot path.
+// All are HBM/L2-bandwidth kernels: coalesced 128-bit accesses, grid sized from the element count.
+#include "common.cuh"
+
+namespace sdb {
+
+static inline int grid_for(int64_t work_items, int threads, int max_waves = 8) {
+  int64_t blocks = cdiv(work_items, threads);
+  int64_t cap = (int64_t)num_sms() * max_waves;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+__device__ __forceinline__ void store_split4(__half* hi, __half* lo, int64_t idx, float4 v) {
+  __half h0, h1, h2, h3, l0, l1, l2, l3;
+  split_f16(v.x, h0, l0);
+  split_f16(v.y, h1, l1);
+  split_f16(v.z, h2, l2);
+  split_f16(v.w, h3, l3);
+  __half2 a = __halves2half2(h0, h1), b = __halves2half2(h2, h3);
+  __half2 c = __halves2half2(l0, l1), d = __halves2half2(l2, l3);
+  uint2 ph, pl;
+  ph.x = *reinterpret_cast<uint32_t*>(&a);
+  ph.y = *reinterpret_cast<uint32_t*>(&b);
+  pl.x = *reinterpret_cast<uint32_t*>(&c);
+  pl.y = *reinterpret_cast<uint32_t*>(&d);
+  *reinterpret_cast<uint2*>(hi + idx) = ph;
+  *reinterpret_cast<uint2*>(lo + idx) = pl;
+}
+
+// ------------------------------------------------------------------ weights
+__global__ void pack_weight_kernel(const float* __restrict__ w, __half* __restrict__ out, int64_t n4, int64_t plane) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = reinterpret_cast<const float4*>(w)[i];
+    store_split4(out, out + plane, i * 4, v);
+  }
+}
+
+// [Cout][Cin][3][3] -> [Cout][tap][Cin]
+__global__ void pack_weight_conv3_kernel(const float* __restrict__ w, __half* __restrict__ out, int64_t Cout,
+                                         int64_t Cin) {
+  const int64_t total = Cout * 9 * Cin;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t c = i % Cin;
+    const int64_t tap = (i / Cin) % 9;
+    const int64_t o = i / (9 * Cin);
+    const float v = w[(o * Cin + c) * 9 + tap];
+    __half h, l;
+    split_f16(v, h, l);
+    out[i] = h;
+    out[total + i] = l;
+  }
+}
+
+// ------------------------------------------------------------------ rows
+__global__ void pack_rows_kernel(const float* __restrict__ x, int64_t ldx, __half* __restrict__ out, int64_t M,
+                                 int64_t K, int act) {
+  const int64_t k4 = K / 4;
+  const int64_t total = M * k4;
+  const int64_t plane = M * K;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / k4, j = i % k4;
+    float4 v = *reinterpret_cast<const float4*>(x + m * ldx + j * 4);
+    if (act == 1) {
+      v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w);
+    } else if (act == 2) {
+      v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+    }
+    store_split4(out, out + plane, m * K + j * 4, v);
+  }
+}
+
+// ------------------------------------------------------------------ LayerNorm (one warp per row)
+__global__ void layernorm_pack_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                      const float* __restrict__ beta, float eps, __half* __restrict__ out,
+                                      float* __restrict__ y, int64_t M, int C) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const int64_t plane = M * (int64_t)C;
+  for (int64_t row = blockIdx.x * (int64_t)warps_per_block + (threadIdx.x >> 5); row < M;
+       row += (int64_t)gridDim.x * warps_per_block) {
+    const float4* xr = reinterpret_cast<const float4*>(x + row * C);
+    const int c4 = C / 4;
+    float4 v[4];   // C <= 512
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int idx = lane + j * 32;
+      if (idx < c4) {
+        v[j] = xr[idx];
+        s += v[j].x + v[j].y + v[j].z + v[j].w;
+      }
+    }
+    const float mean = warp_sum(s) / C;
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int idx = lane + j * 32;
+      if (idx < c4) {
+        const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+        ss += a * a + b * b + c * c + d * d;
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(ss) / C + eps);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int idx = lane + j * 32;
+      if (idx < c4) {
+        const float4 gm = reinterpret_cast<const float4*>(gamma)[idx];
+        const float4 bt = reinterpret_cast<const float4*>(beta)[idx];
+        float4 o;
+        o.x = (v[j].x - mean) * rstd * gm.x + bt.x;
+        o.y = (v[j].y - mean) * rstd * gm.y + bt.y;
+        o.z = (v[j].z - mean) * rstd * gm.z + bt.z;
+        o.w = (v[j].w - mean) * rstd * gm.w + bt.w;
+        if (out) store_split4(out, out + plane, row * C + idx * 4, o);
+        if (y) reinterpret_cast<float4*>(y + row * C)[idx] = o;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ GroupNorm
+// stats: one CTA per (b, group); two-pass in registers is not possible (HW*cpg up to 32K elements), so use
+// a shifted single pass (Welford-free: subtract the first element as pivot) followed by an exact second pass
+// from L2 for the variance -- the activation of one sample-group (<= 128 KB) stays L2/L1 resident.
+__global__ void groupnorm_stats_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2, int C2,
+                                       float* __restrict__ stats, int64_t HW, int G, float eps) {
+  const int b = blockIdx.x / G, g = blockIdx.x % G;
+  const int C = C1 + C2;
+  const int cpg = C / G;
+  const int c_begin = g * cpg;
+  const int64_t n = HW * cpg;
+  __shared__ float red[32];
+  __shared__ float s_mean;
+  auto load = [&](int64_t i) -> float {
+    const int64_t p = i / cpg;
+    const int c = c_begin + int(i % cpg);
+    return (c < C1) ? x1[(b * HW + p) * C1 + c] : x2[(b * HW + p) * C2 + (c - C1)];
+  };
+  float s = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += load(i);
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) s_mean = t / n;
+  }
+  __syncthreads();
+  const float mean = s_mean;
+  float ss = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const float d = load(i) - mean;
+    ss += d * d;
+  }
+  ss = warp_sum(ss);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) {
+      stats[(b * G + g) * 2 + 0] = mean;
+      stats[(b * G + g) * 2 + 1] = rsqrtf(t / n + eps);
+    }
+  }
+}
+
+__global__ void groupnorm_apply_pack_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2,
+                                            int C2, const float* __restrict__ stats,
+                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                            __half* __restrict__ out, int64_t B, int64_t HW, int G, int silu) {
+  const int C = C1 + C2;
+  const int c4n = C / 4;
+  const int cpg = C / G;
+  const int64_t total = B * HW * c4n;
+  const int64_t plane = B * HW * (int64_t)C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = int(i % c4n) * 4;
+    const int64_t row = i / c4n;   // b*HW + p
+    const int64_t b = row / HW;
+    float4 v = (c < C1) ? *reinterpret_cast<const float4*>(x1 + row * C1 + c)
+                        : *reinterpret_cast<const float4*>(x2 + row * C2 + (c - C1));
+    const float4 gm = *reinterpret_cast<const float4*>(gamma + c);
+    const float4 bt = *reinterpret_cast<const float4*>(beta + c);
+    float r[4] = {v.x, v.y, v.z, v.w};
+    const float gmv[4] = {gm.x, gm.y, gm.z, gm.w};
+    const float btv[4] = {bt.x, bt.y, bt.z, bt.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int g = (c + j) / cpg;   // cpg may not be a multiple of 4 (e.g. 28)
+      const float mean = stats[(b * G + g) * 2], rstd = stats[(b * G + g) * 2 + 1];
+      float o = (r[j] - mean) * rstd * gmv[j] + btv[j];
+      r[j] = silu ? silu_f(o) : o;
+    }
+    store_split4(out, out + plane, row * C + c, make_float4(r[0], r[1], r[2], r[3]));
+  }
+}
+
+// ------------------------------------------------------------------ raw NHWC packing with layout transforms
+__global__ void pack_nhwc_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2, int C2,
+                                 __half* __restrict__ out, float* __restrict__ ycat, int64_t B, int H, int W,
+                                 int mode) {
+  const int C = C1 + C2;
+  const int c4n = C / 4;
+  const int Ho = (mode == SDB_PACK_UP2) ? 2 * H : H;
+  const int Wo = (mode == SDB_PACK_UP2) ? 2 * W : W;
+  const int64_t total = B * Ho * Wo * c4n;     // iterate over OUTPUT elements
+  const int64_t plane = B * (int64_t)Ho * Wo * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = int(i % c4n) * 4;
+    int64_t p = i / c4n;
+    const int xo = int(p % Wo);
+    p /= Wo;
+    const int yo = int(p % Ho);
+    const int64_t b = p / Ho;
+    int yi = yo, xi = xo;
+    if (mode == SDB_PACK_UP2) { yi = yo >> 1; xi = xo >> 1; }
+    const int64_t src = (b * H + yi) * W + xi;
+    float4 v = (c < C1) ? *reinterpret_cast<const float4*>(x1 + src * C1 + c)
+                        : *reinterpret_cast<const float4*>(x2 + src * C2 + (c - C1));
+    int64_t dst;
+    if (mode == SDB_PACK_PHASE2) {
+      const int ph = (yo & 1) * 2 + (xo & 1);
+      dst = (((b * 4 + ph) * (H / 2) + (yo >> 1)) * (W / 2) + (xo >> 1)) * C + c;
+    } else {
+      dst = ((b * Ho + yo) * Wo + xo) * C + c;
+    }
+    store_split4(out, out + plane, dst, v);
+    if (ycat) *reinterpret_cast<float4*>(ycat + src * C + c) = v;
+  }
+}
+
+// ------------------------------------------------------------------ GEGLU
+__global__ void geglu_pack_kernel(const float* __restrict__ u, __half* __restrict__ out, int64_t M, int64_t F) {
+  const int64_t f4 = F / 4;
+  const int64_t total = M * f4;
+  const int64_t plane = M * F;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / f4, j = (i % f4) * 4;
+    const float4 a = *reinterpret_cast<const float4*>(u + m * 2 * F + j);
+    const float4 g = *reinterpret_cast<const float4*>(u + m * 2 * F + F + j);
+    float4 o;
+    o.x = a.x * gelu_erf_f(g.x);
+    o.y = a.y * gelu_erf_f(g.y);
+    o.z = a.z * gelu_erf_f(g.z);
+    o.w = a.w * gelu_erf_f(g.w);
+    store_split4(out, out + plane, m * F + j, o);
+  }
+}
+
+// ------------------------------------------------------------------ timestep embedding
+__global__ void timestep_embedding_pack_kernel(const float* __restrict__ t, __half* __restrict__ out, int64_t B,
+                                               int dim) {
+  const int half = dim / 2;
+  const int64_t total = B * dim;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / dim;
+    const int j = int(i % dim);
+    const int f = j < half ? j : j - half;
+    // freqs = exp(-ln(1e4) * f / half) in fp32 (unet/utils.py:81-84)
+    const float freq = expf(-9.210340371976184f * (float)f / (float)half);
+    const float arg = t[b] * freq;
+    const float v = j < half ? cosf(arg) : sinf(arg);
+    __half h, l;
+    split_f16(v, h, l);
+    out[i] = h;
+    out[total + i] = l;
+  }
+}
+
+// ------------------------------------------------------------------ GRU gates
+__global__ void gru_gates_kernel(const float* __restrict__ gi, const float* __restrict__ gh,
+                                 const float* __restrict__ h, float* __restrict__ hn, int64_t R, int64_t D) {
+  const int64_t total = R * D;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / D, d = i % D;
+    const float* a = gi + r * 3 * D;
+    const float* b = gh + r * 3 * D;
+    const float rg = 1.f / (1.f + expf(-(a[d] + b[d])));
+    const float zg = 1.f / (1.f + expf(-(a[D + d] + b[D + d])));
+    const float ng = tanhf(a[2 * D + d] + rg * b[2 * D + d]);
+    hn[i] = (1.f - zg) * ng + zg * h[i];
+  }
+}
+
+// ------------------------------------------------------------------ small-channel convs
+// input conv: x NCHW [B,Cin,H,W] -> y NHWC [B,H,W,Cout]; one thread per (pixel, 4 output channels)
+__global__ void conv3_in_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                const float* __restrict__ bias, float* __restrict__ y, int64_t B, int Cin, int H,
+                                int W, int Cout) {
+  extern __shared__ float sw[];   // [Cin*9][Cout]
+  for (int i = threadIdx.x; i < Cin * 9 * Cout; i += blockDim.x) {
+    const int o = i % Cout, r = i / Cout;    // r = c*9 + tap
+    sw[i] = w[o * Cin * 9 + r];
+  }
+  __syncthreads();
+  const int o4n = Cout / 4;
+  const int64_t total = B * H * W * o4n;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int o = int(i % o4n) * 4;
+    int64_t p = i / o4n;
+    const int xo = int(p % W);
+    p /= W;
+    const int yo = int(p % H);
+    const int64_t b = p / H;
+    float4 acc = *reinterpret_cast<const float4*>(bias + o);
+    for (int c = 0; c < Cin; ++c) {
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int yi = yo + tap / 3 - 1, xi = xo + tap % 3 - 1;
+        if (yi < 0 || yi >= H || xi < 0 || xi >= W) continue;
+        const float v = x[((b * Cin + c) * H + yi) * W + xi];
+        const float4 ww = *reinterpret_cast<const float4*>(sw + (c * 9 + tap) * Cout + o);
+        acc.x += v * ww.x; acc.y += v * ww.y; acc.z += v * ww.z; acc.w += v * ww.w;
+      }
+    }
+    *reinterpret_cast<float4*>(y + ((b * H + yo) * W + xo) * Cout + o) = acc;
+  }
+}
+
+// output head: y NCHW [B,Cout,H,W] = conv3x3(SiLU(GN(h))), h NHWC [B,H,W,C]; one warp per output pixel,
+// lanes split the C channels, Cout (<= 4) accumulators per lane, warp-shuffle reduction.
+template <int COUT_MAX>
+__global__ void conv3_out_kernel(const float* __restrict__ h, const float* __restrict__ stats,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta,
+                                 const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ y,
+                                 int64_t B, int H, int W, int C, int G, int Cout) {
+  extern __shared__ float sw[];   // [Cout][9][C]
+  for (int i = threadIdx.x; i < Cout * 9 * C; i += blockDim.x) {
+    const int c = i % C, tap = (i / C) % 9, o = i / (9 * C);
+    sw[i] = w[(o * C + c) * 9 + tap];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int cpg = C / G;
+  const int64_t total = B * H * W;
+  for (int64_t p = blockIdx.x * (int64_t)wpb + (threadIdx.x >> 5); p < total; p += (int64_t)gridDim.x * wpb) {
+    const int xo = int(p % W), yo = int((p / W) % H);
+    const int64_t b = p / ((int64_t)H * W);
+    float acc[COUT_MAX];
+#pragma unroll
+    for (int o = 0; o < COUT_MAX; ++o) acc[o] = 0.f;
+    for (int tap = 0; tap < 9; ++tap) {
+      const int yi = yo + tap / 3 - 1, xi = xo + tap % 3 - 1;
+      if (yi < 0 || yi >= H || xi < 0 || xi >= W) continue;
+      const float* hp = h + ((b * H + yi) * W + xi) * C;
+      for (int c = lane; c < C; c += 32) {
+        const int g = c / cpg;
+        const float mean = stats[(b * G + g) * 2], rstd = stats[(b * G + g) * 2 + 1];
+        const float a = silu_f((hp[c] - mean) * rstd * gamma[c] + beta[c]);
+#pragma unroll
+        for (int o = 0; o < COUT_MAX; ++o)
+          if (o < Cout) acc[o] += a * sw[(o * 9 + tap) * C + c];
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < COUT_MAX; ++o) {
+      if (o < Cout) {
+        const float s = warp_sum(acc[o]);
+        if (lane == 0) y[((b * Cout + o) * H + yo) * W + xo] = s + bias[o];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ DPM-Solver glue
+// x0 = (x - sigma*eps)/alpha, then nearest codebook row.  One thread per latent pixel; codebook in smem.
+__global__ void dpm_x0_kernel(const float* __restrict__ x, const float* __restrict__ eps, float alpha, float sigma,
+                              const float* __restrict__ codebook, int ncodes, float* __restrict__ x0,
+                              int* __restrict__ idx, int64_t B, int C, int64_t HW) {
+  extern __shared__ float scb[];   // [ncodes][C] + [ncodes] squared norms
+  float* snorm = scb + (size_t)ncodes * C;
+  if (codebook) {
+    for (int i = threadIdx.x; i < ncodes * C; i += blockDim.x) scb[i] = codebook[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < ncodes; i += blockDim.x) {
+      float s = 0.f;
+      for (int c = 0; c < C; ++c) s += scb[i * C + c] * scb[i * C + c];
+      snorm[i] = s;
+    }
+    __syncthreads();
+  }
+  const int64_t total = B * HW;
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = p / HW, q = p % HW;
+    float z[8];
+    float zz = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const int64_t o = (b * C + c) * HW + q;
+      z[c] = (x[o] - sigma * eps[o]) / alpha;
+      zz += z[c] * z[c];
+    }
+    if (codebook) {
+      // d = |z|^2 + |e|^2 - 2 z.e  (the reference's expanded form, quantize.py:89-91); first minimum wins
+      float best = INFINITY;
+      int bi = 0;
+      for (int j = 0; j < ncodes; ++j) {
+        float dot = 0.f;
+        for (int c = 0; c < C; ++c) dot += z[c] * scb[j * C + c];
+        const float d = zz + snorm[j] - 2.f * dot;
+        if (d < best) { best = d; bi = j; }
+      }
+      for (int c = 0; c < C; ++c) z[c] = scb[bi * C + c];
+      if (idx) idx[p] = bi;
+    }
+    for (int c = 0; c < C; ++c) x0[(b * C + c) * HW + q] = z[c];
+  }
+}
+
+__global__ void lincomb_kernel(float* __restrict__ out, const float* __restrict__ x, const float* __restrict__ m0,
+                               const float* __restrict__ m1, float a, float b, float c, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = a * x[i] + b * m0[i];
+    if (m1) v += c * (m1[i] - m0[i]);
+    out[i] = v;
+  }
+}
+
+}  // namespace sdb
+
+using namespace sdb;
+
+extern "C" int sdb_pack_weight(const float* w, void* out, int64_t N, int64_t K, void* stream) {
+  SDB_REQUIRE(w && out && N > 0 && K > 0 && K % 4 == 0, "sdb_pack_weight: bad args N=%lld K=%lld", (long long)N,
+              (long long)K);
+  const int64_t n4 = N * K / 4;
+  pack_weight_kernel<<<grid_for(n4, 256), 256, 0, as_stream(stream)>>>(w, (__half*)out, n4, N * K);
+  SDB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sdb_pack_weight_conv3(const float* w, void* out, int64_t Cout, int64_t Cin, void* stream) {
+  SDB_REQUIRE(w && out && Cout > 0 && Cin > 0, "sdb_pack_weight_conv3: bad args");
+  pack_weight_conv3_kernel<<<grid_for(Cout * 9 * Cin, 256), 256, 0, as_stream(stream)>>>(w, (__half*)out, Cout, Cin);
+  SDB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sdb_pack_rows(const float* x, int64_t ldx, void* out, int64_t M, int64_t K, int act, void* stream) {
+  SDB_REQUIRE(x && out && M > 0 && K > 0 && K % 4 == 0 && ldx % 4 == 0, "sdb_pack_rows: bad args M=%lld K=%lld ldx=%lld",
+              (long long)M, (long long)K, (long long)ldx);
+  pack_rows_kernel<<<grid_for(M * K / 4, 256), 256, 0, as_stream(stream)>>>(x, ldx, (__half*)out, M, K, act);
+  SDB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sdb_layernorm_pack(const float* x, const float* gamma, const float* beta, float eps, void* out,
+                                  float* y, int64_t M, int64_t C, void* stream) {
+  SDB_REQUIRE(x && gamma && beta && (out || y) && M > 0, "sdb_layernorm_pack: null argument");
+  SDB_REQUIRE(C % 4 == 0 && C <= 512, "sdb_layernorm_pack: C=%lld must be a multiple of 4 and <= 512", (long long)C);
+  const int threads = 256;
+  layernorm_pack_kernel<<<grid_for(M, threads / 32), threads, 0, as_stream(stream)>>>(x, gamma, beta, eps,
+                                                                                      (__half*)out, y, M, (int)C);
+  SDB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sdb_groupnorm_stats(const float* x1, int64_t C1, const float* x2, int64_t C2, float* stats, int64_t B,
+                                   int64_t HW, int G, float eps, void* stream) {
+  SDB_REQUIRE(x1 && stats && B > 0 && HW > 0 && G > 0, "sdb_groupnorm_stats: bad args");
+  SDB_REQUIRE((C1 + C2) % G == 0 && (C2 == 0 || x2), "sdb_groupnorm_stats: C=%lld not divisible by G=%d",
+              (long long)(C1 + C2), G);
+  groupnorm_stats_kernel<<<(int)(B * G), 256, 0, as_stream(stream)>>>(x1, (int)C1, x2, (int)C2, stats, HW, G, eps);
+  SDB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sdb_groupnorm_apply_pack(const float* x1, int64_t C1, const float* x2, int64_t C2, const float* stats,
+                                        const float* gamma, const float* beta, void* out, int64_t B, int64_t HW,
+                                        int G, int silu, void* stream) {
+  SDB_REQUIRE(x1 && stats && gamma && beta && out, "sdb_groupnorm_apply_pack: null argument");
+  SDB_REQUIRE(C1 % 4 == 0 && C2 % 4 == 0 && (C1 + C2) % G == 0, "sdb_groupnorm_apply_pack: bad channels");
+  groupnorm_apply_pack_kernel<<<grid_for(B * HW * (C1 + C2) / 4, 256), 256, 0, as_stream(stream)>>>(
+      x1, (int)C1, x2, (int)C2, stats, gamma, beta, (__half*)out, B, HW, G, silu);
+  SDB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sdb_pack_nhwc(const float* x1, int64_t C1, const float* x2, int64_t C2, void* out, float* y_cat,
+                             int64_t B, int64_t H, int64_t W, int mode, void* stream) {
+  SDB_REQUIRE(x1 && out && B > 0 && H > 0 && W > 0, "sdb_pack_nhwc: bad args");
+  SDB_REQUIRE(C1 % 4 == 0 && C2 % 4 == 0 && (C2 == 0 || x2), "sdb_pack_nhwc: channels must be multiples of 4");
+  SDB_REQUIRE(mode == SDB_PACK_PLAIN || mode == SDB_PACK_UP2 || mode == SDB_PACK_PHASE2, "sdb_pack_nhwc: bad mode");
+  SDB_REQUIRE(mode != SDB_PACK_PHASE2 || (H % 2 == 0 && W % 2 == 0), "sdb_pack_nhwc: phase split needs even H, W");
+  SDB_REQUIRE(!y_cat || mode != SDB_PACK_UP2, "sdb_pack_nhwc: y_cat unsupported with upsample");
+  const int64_t mult = mode == SDB_PACK_UP2 ? 4 : 1;
+  pack_nhwc_kernel<<<grid_for(B * H * W * mult * (C1 + C2) / 4, 256), 256, 0, as_stream(stream)>>>(
+      x1, (int)C1, x2, (int)C2, (__half*)out, y_cat, B, (int)H, (int)W, mode);
+  SDB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sdb_geglu_pack(const float* u, void* out, int64_t M, int64_t F, void* stream) {
+  SDB_REQUIRE(u && out && M > 0 && F > 0 && F % 4 == 0, "sdb_geglu_pack: bad args");
+  geglu_pack_kernel<<<grid_for(M * F / 4, 256), 256, 0, as_stream(stream)>>>(u, (__half*)out, M, F);
+  SDB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sdb_timestep_embedding_pack(const float* t, void* out, int64_t B, int dim, void* stream) {
+  SDB_REQUIRE(t && out && B > 0 && dim > 0 && dim % 2 == 0, "sdb_timestep_embedding_pack: bad args");
+  timestep_embedding_pack_kernel<<<grid_for(B * dim, 128), 128, 0, as_stream(stream)>>>(t, (__half*)out, B, dim);
+  SDB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sdb_gru_gates(const float* gi, const float* gh, const float* h, float* h_new, int64_t R, int64_t D,
+                             void* stream) {
+  SDB_REQUIRE(gi && gh && h && h_new && R > 0 && D > 0, "sdb_gru_gates: bad args");
+  gru_gates_kernel<<<grid_for(R * D, 256), 256, 0, as_stream(stream)>>>(gi, gh, h, h_new, R, D);
+  SDB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sdb_conv3_in(const float* x, const float* w, const float* bias, float* y, int64_t B, int64_t Cin,
+                            int64_t H, int64_t W, int64_t Cout, void* stream) {
+  SDB_REQUIRE(x && w && bias && y && B > 0, "sdb_conv3_in: null argument");
+  SDB_REQUIRE(Cout % 4 == 0 && Cin * 9 * Cout * 4 <= 96 * 1024, "sdb_conv3_in: Cin=%lld Cout=%lld unsupported",
+              (long long)Cin, (long long)Cout);
+  const size_t smem = (size_t)Cin * 9 * Cout * 4;
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    SDB_CHECK(cudaFuncSetAttribute(conv3_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  conv3_in_kernel<<<grid_for(B * H * W * Cout / 4, 256, 4), 256, smem, as_stream(stream)>>>(x, w, bias, y, B, (int)Cin,
+                                                                                          (int)H, (int)W, (int)Cout);
+  SDB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sdb_conv3_out(const float* h, const float* stats, const float* gamma, const float* beta,
+                             const float* w, const float* bias, float* y, int64_t B, int64_t H, int64_t W, int64_t C,
+                             int G, int64_t Cout, void* stream) {
+  SDB_REQUIRE(h && stats && gamma && beta && w && bias && y, "sdb_conv3_out: null argument");
+  SDB_REQUIRE(Cout >= 1 && Cout <= 4 && C % G == 0, "sdb_conv3_out: Cout=%lld must be in 1..4", (long long)Cout);
+  const size_t smem = (size_t)Cout * 9 * C * 4;
+  SDB_REQUIRE(smem <= 48 * 1024, "sdb_conv3_out: C=%lld too large", (long long)C);
+  conv3_out_kernel<4><<<grid_for(B * H * W, 8, 4), 256, smem, as_stream(stream)>>>(h, stats, gamma, beta, w, bias, y, B,
+                                                                                  (int)H, (int)W, (int)C, G, (int)Cout);
+  SDB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sdb_dpm_x0(const float* x, const float* eps, float alpha, float sigma, const float* codebook,
+                          int64_t ncodes, float* x0, int32_t* idx, int64_t B, int64_t C, int64_t HW, void* stream) {
+  SDB_REQUIRE(x && eps && x0 && B > 0 && C > 0 && C <= 8 && HW > 0, "sdb_dpm_x0: bad args (C <= 8)");
+  size_t smem = codebook ? (size_t)ncodes * (C + 1) * 4 : 0;
+  SDB_REQUIRE(smem <= 200 * 1024, "sdb_dpm_x0: codebook too large for shared memory");
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    SDB_CHECK(cudaFuncSetAttribute(dpm_x0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  const int threads = 128;
+  dpm_x0_kernel<<<grid_for(B * HW, threads, 1), threads, smem, as_stream(stream)>>>(x, eps, alpha, sigma, codebook,
+                                                                                    (int)ncodes, x0, idx, B, (int)C, HW);
+  SDB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sdb_lincomb(float* out, const float* x, const float* m0, const float* m1, float a, float b, float c,
+                           int64_t n, void* stream) {
+  SDB_REQUIRE(out && x && m0 && n > 0, "sdb_lincomb: bad args");
+  lincomb_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(out, x, m0, m1, a, b, c, n);
+  SDB_LAUNCH_CHECK();
+  return 0;
+}

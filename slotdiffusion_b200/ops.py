@@ -1,0 +1,279 @@
+"""Tensor-level wrappers over the C ABI (include/sdb200.h).
+
+PyTorch is used only as the owner of device memory and streams: every function takes CUDA tensors,
+allocates outputs with torch.empty and enqueues hand-written kernels from libsdb200.so on
+torch.cuda.current_stream().  No function here computes anything with torch ops.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import (SDB_A_CONV3, SDB_A_CONV3S2, SDB_A_PLAIN, SDB_PACK_PHASE2, SDB_PACK_PLAIN, SDB_PACK_UP2,
+                   SdbGemm, check, lib)
+
+_PASSES = 3   # 3: hi*hi + lo*hi + hi*lo (fp32-faithful, default); 1: single fp16 pass
+
+
+def set_precision(mode):
+    """'fp32' (default): 3-pass split-fp16 tensor-core products, ~2^-22 relative product error.
+    'fp16': single pass (hi planes only), ~2^-11 -- the accuracy class of the reference under TF32/AMP."""
+    global _PASSES
+    if mode not in ('fp32', 'fp16'):
+        raise ValueError(mode)
+    _PASSES = 3 if mode == 'fp32' else 1
+
+
+def get_passes():
+    return _PASSES
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _f32(t, name='tensor'):
+    if t.dtype != torch.float32 or not t.is_cuda:
+        raise RuntimeError(f'{name}: expected a CUDA float32 tensor, got {t.dtype} on {t.device}')
+    return t
+
+
+class Packed:
+    """GEMM operand: fp16 [2][rows][K] (hi plane, lo plane)."""
+    __slots__ = ('t', 'rows', 'K')
+
+    def __init__(self, t, rows, K):
+        self.t, self.rows, self.K = t, rows, K
+
+    @staticmethod
+    def empty(rows, K, device):
+        return Packed(torch.empty(2 * rows * K, dtype=torch.float16, device=device), rows, K)
+
+    def unpack(self):
+        """fp32 value of the operand (tests only)."""
+        t = self.t.view(2, self.rows, self.K).float()
+        return t[0] + t[1]
+
+
+# ---------------------------------------------------------------- weights (cached per parameter version)
+class WeightCache:
+    """Packed copies of parameters, re-packed when the parameter storage or version changes
+    (an optimizer step bumps `_version`)."""
+
+    def __init__(self):
+        self._c = {}
+
+    def _get(self, key, tensors, fn):
+        sig = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in tensors)
+        hit = self._c.get(key)
+        if hit is not None and hit[0] == sig:
+            return hit[1]
+        val = fn()
+        self._c[key] = (sig, val)
+        return val
+
+    def linear(self, key, *ws):
+        """Row-concatenation of nn.Linear / 1x1-conv weights [N_i, K] -> Packed [sum N_i, K]."""
+        def make():
+            w2 = [w.detach().reshape(w.shape[0], -1) for w in ws]
+            w = w2[0] if len(w2) == 1 else torch.cat(w2, 0)
+            return pack_weight(w.contiguous())
+        return self._get(key, ws, make)
+
+    def conv3(self, key, w):
+        return self._get(key, (w,), lambda: pack_weight_conv3(w.detach().contiguous()))
+
+    def cat(self, key, *vs):
+        """Concatenation of fp32 vectors (fused biases)."""
+        return self._get(key, vs, lambda: torch.cat([v.detach().reshape(-1) for v in vs]).contiguous())
+
+    def clear(self):
+        self._c.clear()
+
+
+def pack_weight(w):
+    _f32(w, 'weight')
+    N, K = w.shape
+    out = Packed.empty(N, K, w.device)
+    check(lib().sdb_pack_weight(_p(w), _p(out.t), N, K, _stream()), 'sdb_pack_weight')
+    return out
+
+
+def pack_weight_conv3(w):
+    _f32(w, 'weight')
+    Cout, Cin, kh, kw = w.shape
+    assert kh == 3 and kw == 3
+    out = Packed.empty(Cout, 9 * Cin, w.device)
+    check(lib().sdb_pack_weight_conv3(_p(w), _p(out.t), Cout, Cin, _stream()), 'sdb_pack_weight_conv3')
+    return out
+
+
+# ---------------------------------------------------------------- operand producers
+def pack_rows(x, act=0):
+    """x [M,K] fp32 (last dim contiguous) -> Packed; act 0 none / 1 SiLU / 2 ReLU."""
+    _f32(x)
+    assert x.dim() == 2 and x.stride(1) == 1
+    M, K = x.shape
+    out = Packed.empty(M, K, x.device)
+    check(lib().sdb_pack_rows(_p(x), x.stride(0), _p(out.t), M, K, act, _stream()), 'sdb_pack_rows')
+    return out
+
+
+def layernorm_pack(x, gamma, beta, eps=1e-5, want_fp32=False):
+    _f32(x)
+    C = x.shape[-1]
+    x2 = x.reshape(-1, C)
+    assert x2.is_contiguous()
+    M = x2.shape[0]
+    out = Packed.empty(M, C, x.device)
+    y = torch.empty_like(x2) if want_fp32 else None
+    check(lib().sdb_layernorm_pack(_p(x2), _p(gamma), _p(beta), eps, _p(out.t), _p(y), M, C, _stream()),
+          'sdb_layernorm_pack')
+    return (out, y) if want_fp32 else out
+
+
+def groupnorm_stats(x1, x2, B, HW, G, eps):
+    """x1 [B*HW, C1] (+ x2 [B*HW, C2]) NHWC rows -> stats [B, G, 2] (mean, rstd)."""
+    C1 = x1.shape[-1]
+    C2 = x2.shape[-1] if x2 is not None else 0
+    stats = torch.empty(B, G, 2, dtype=torch.float32, device=x1.device)
+    check(lib().sdb_groupnorm_stats(_p(x1), C1, _p(x2), C2, _p(stats), B, HW, G, eps, _stream()),
+          'sdb_groupnorm_stats')
+    return stats
+
+
+def groupnorm_pack(x1, x2, gamma, beta, B, HW, G=32, eps=1e-5, silu=True, stats=None):
+    C1 = x1.shape[-1]
+    C2 = x2.shape[-1] if x2 is not None else 0
+    if stats is None:
+        stats = groupnorm_stats(x1, x2, B, HW, G, eps)
+    out = Packed.empty(B * HW, C1 + C2, x1.device)
+    check(lib().sdb_groupnorm_apply_pack(_p(x1), C1, _p(x2), C2, _p(stats), _p(gamma), _p(beta), _p(out.t), B, HW,
+                                         G, int(silu), _stream()), 'sdb_groupnorm_apply_pack')
+    return out
+
+
+def pack_nhwc(x1, x2, B, H, W, mode=SDB_PACK_PLAIN, want_cat=False):
+    """raw NHWC rows (+ channel concat) -> Packed in plain / nearest-x2 / stride-2 phase-split layout."""
+    C1 = x1.shape[-1]
+    C2 = x2.shape[-1] if x2 is not None else 0
+    mult = 4 if mode == SDB_PACK_UP2 else 1
+    out = Packed.empty(B * H * W * mult, C1 + C2, x1.device)
+    ycat = torch.empty(B * H * W, C1 + C2, dtype=torch.float32, device=x1.device) if want_cat else None
+    check(lib().sdb_pack_nhwc(_p(x1), C1, _p(x2), C2, _p(out.t), _p(ycat), B, H, W, mode, _stream()), 'sdb_pack_nhwc')
+    return (out, ycat) if want_cat else out
+
+
+def geglu_pack(u):
+    M, F2 = u.shape
+    out = Packed.empty(M, F2 // 2, u.device)
+    check(lib().sdb_geglu_pack(_p(u), _p(out.t), M, F2 // 2, _stream()), 'sdb_geglu_pack')
+    return out
+
+
+def timestep_embedding_pack(t, dim):
+    t = t.to(torch.float32).contiguous()
+    B = t.shape[0]
+    out = Packed.empty(B, dim, t.device)
+    check(lib().sdb_timestep_embedding_pack(_p(t), _p(out.t), B, dim, _stream()), 'sdb_timestep_embedding_pack')
+    return out
+
+
+# ---------------------------------------------------------------- GEMM
+def gemm(a, w, bias=None, rowvec=None, rows_per_group=0, residual=None, relu=False, conv=None, passes=None,
+         out=None):
+    """C = A W^T (+bias)(+rowvec[row // rows_per_group])(+residual); A, W Packed.
+    conv: None (plain) or (mode, B, H, W, C) with H, W the OUTPUT size (see sdb200.h)."""
+    N, K = w.rows, w.K
+    if conv is None:
+        M, mode, geo = a.rows, SDB_A_PLAIN, (0, 0, 0, 0)
+        assert a.K == K, (a.K, K)
+    else:
+        mode, B, H, W, C = conv
+        M, geo = B * H * W, (B, H, W, C)
+        assert K == 9 * C and a.K == C
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32, device=a.t.device)
+    g = SdbGemm()
+    g.a, g.w, g.c = a.t.data_ptr(), w.t.data_ptr(), out.data_ptr()
+    g.bias = bias.data_ptr() if bias is not None else None
+    g.rowvec = rowvec.data_ptr() if rowvec is not None else None
+    g.residual = residual.data_ptr() if residual is not None else None
+    g.a_plane_stride = a.rows * a.K
+    g.ldc = out.stride(0)
+    g.ldv = rowvec.stride(0) if rowvec is not None else 0
+    g.ldr = residual.stride(0) if residual is not None else 0
+    g.M, g.N, g.K, g.mode = M, N, K, mode
+    g.B, g.H, g.W, g.C = geo
+    g.rows_per_group = rows_per_group
+    g.passes = passes or _PASSES
+    g.relu = int(relu)
+    check(lib().sdb_gemm(ctypes.byref(g), _stream()), 'sdb_gemm')
+    return out
+
+
+# ---------------------------------------------------------------- attention / convs / slot attention / sampler
+def attention_pack(q, k, v, B, Lq, Lk, heads, d, scale):
+    """q/k/v: 2-D strided views [B*L, heads*d] (last dim contiguous) -> Packed [B*Lq, heads*d]."""
+    out = Packed.empty(B * Lq, heads * d, q.device)
+    check(lib().sdb_attention_pack(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out.t), B, Lq, Lk,
+                                   heads, d, scale, _stream()), 'sdb_attention_pack')
+    return out
+
+
+def conv3_in(x, w, bias):
+    B, Cin, H, W = x.shape
+    Cout = w.shape[0]
+    y = torch.empty(B * H * W, Cout, dtype=torch.float32, device=x.device)
+    check(lib().sdb_conv3_in(_p(x.contiguous()), _p(w), _p(bias), _p(y), B, Cin, H, W, Cout, _stream()), 'sdb_conv3_in')
+    return y
+
+
+def conv3_out(h, stats, gamma, beta, w, bias, B, H, W, G=32):
+    C = h.shape[-1]
+    Cout = w.shape[0]
+    y = torch.empty(B, Cout, H, W, dtype=torch.float32, device=h.device)
+    check(lib().sdb_conv3_out(_p(h), _p(stats), _p(gamma), _p(beta), _p(w), _p(bias), _p(y), B, H, W, C, G, Cout,
+                              _stream()), 'sdb_conv3_out')
+    return y
+
+
+def slot_attend(kv, q, B, N, S, D, scale, eps, want_mask, want_fp32=False):
+    ws = lib().sdb_slot_attend_workspace(B, N, S, D)
+    work = torch.empty(ws // 4, dtype=torch.float32, device=kv.device)
+    mask = torch.empty(B, S, N, dtype=torch.float32, device=kv.device) if want_mask else None
+    upd = Packed.empty(B * S, D, kv.device)
+    upd32 = torch.empty(B * S, D, dtype=torch.float32, device=kv.device) if want_fp32 else None
+    check(lib().sdb_slot_attend(_p(kv), _p(q), _p(mask), _p(upd.t), _p(upd32), _p(work), B, N, S, D, scale, eps,
+                                _stream()), 'sdb_slot_attend')
+    return upd, mask, upd32
+
+
+def gru_gates(gi, gh, h):
+    R, D = h.shape
+    out = torch.empty_like(h)
+    check(lib().sdb_gru_gates(_p(gi), _p(gh), _p(h), _p(out), R, D, _stream()), 'sdb_gru_gates')
+    return out
+
+
+def dpm_x0(x, eps, alpha, sigma, codebook=None, want_idx=False):
+    B, C = x.shape[:2]
+    HW = x[0, 0].numel()
+    x0 = torch.empty_like(x)
+    idx = torch.empty(B, HW, dtype=torch.int32, device=x.device) if want_idx else None
+    nc = codebook.shape[0] if codebook is not None else 0
+    check(lib().sdb_dpm_x0(_p(x), _p(eps), float(alpha), float(sigma), _p(codebook), nc, _p(x0), _p(idx), B, C, HW,
+                           _stream()), 'sdb_dpm_x0')
+    return (x0, idx) if want_idx else x0
+
+
+def lincomb(x, m0, m1, a, b, c=0.0, out=None):
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib().sdb_lincomb(_p(out), _p(x), _p(m0), _p(m1), float(a), float(b), float(c), x.numel(), _stream()),
+          'sdb_lincomb')
+    return out

@@ -1,0 +1,52 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds, loads without a GPU/driver and exports
+every symbol include/sdb200.h declares; the ctypes signature table covers exactly those symbols."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    hdr = open(os.path.join(ROOT, 'include', 'sdb200.h')).read()
+    return set(re.findall(r'\b(sdb_[a-z0-9_]+)\s*\(', hdr))
+
+
+def test_library_builds_and_exports_header_symbols():
+    from slotdiffusion_b200 import build
+    path = build.build(verbose=False)
+    l = ctypes.CDLL(path)
+    for name in _declared():
+        assert hasattr(l, name), name
+
+
+def test_ctypes_table_matches_header():
+    from slotdiffusion_b200 import _lib
+    assert set(_lib.SIGNATURES) == _declared()
+    assert _lib.lib().sdb_version() >= 1
+
+
+def test_gemm_struct_layout_matches_header():
+    """SdbGemm field order in the header == ctypes Structure order."""
+    from slotdiffusion_b200._lib import SdbGemm
+    hdr = open(os.path.join(ROOT, 'include', 'sdb200.h')).read()
+    body = re.search(r'typedef struct SdbGemm \{(.*?)\} SdbGemm;', hdr, re.S).group(1)
+    body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
+    names = []
+    for stmt in body.split(';'):
+        stmt = stmt.strip()
+        if not stmt:
+            continue
+        decl = stmt.split(None, 1)[1] if not stmt.startswith('const') else stmt.split(None, 2)[2]
+        for n in decl.split(','):
+            names.append(n.replace('*', '').strip())
+    assert names == [f[0] for f in SdbGemm._fields_], names
+
+
+def test_invalid_arguments_are_reported_not_ub():
+    from slotdiffusion_b200 import _lib
+    l = _lib.lib()
+    g = _lib.SdbGemm()
+    assert l.sdb_gemm(ctypes.byref(g), None) == 1          # SDB_ERR_INVALID
+    assert b'null' in l.sdb_last_error()
+    assert l.sdb_slot_attend(None, None, None, None, None, None, 1, 1, 1, 192, 1.0, 1e-6, None) == 1

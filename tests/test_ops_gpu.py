@@ -1,0 +1,219 @@
+"""GPU parity of every C-ABI kernel against a plain torch reference of the same op (fp64 on device).
+Tolerances: 3-pass split-fp16 products are fp32-faithful (<= 2e-6 relative L2); 1-pass is fp16-class."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import rel_l2
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(180)]
+
+
+@pytest.fixture(scope='module')
+def ops():
+    from slotdiffusion_b200 import ops as o
+    return o
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator(device='cuda').manual_seed(seed)
+    return torch.randn(*shape, generator=g, device='cuda') * scale
+
+
+def test_pack_roundtrip(ops):
+    x = rnd(300, 192, seed=1, scale=3.0)
+    p = ops.pack_rows(x)
+    assert rel_l2(p.unpack(), x) < 1e-6
+    w = rnd(96, 64, seed=2, scale=0.02)
+    assert rel_l2(ops.pack_weight(w).unpack(), w) < 2e-6
+    p = ops.pack_rows(x, act=1)
+    assert rel_l2(p.unpack(), F.silu(x.double())) < 2e-6
+    p = ops.pack_rows(x, act=2)
+    assert rel_l2(p.unpack(), F.relu(x.double())) < 1e-6
+
+
+@pytest.mark.parametrize('M,N,K', [(128, 128, 64), (256, 128, 128), (704, 576, 192), (64, 512, 128), (1000, 200, 72),
+                                   (4096, 384, 1024), (33, 48, 512), (65536, 128, 128)])
+def test_gemm_plain(ops, M, N, K):
+    a = rnd(M, K, seed=3)
+    w = rnd(N, K, seed=4, scale=K ** -0.5)
+    bias = rnd(N, seed=5)
+    res = rnd(M, N, seed=6)
+    ref = a.double() @ w.double().t() + bias.double() + res.double()
+    c = ops.gemm(ops.pack_rows(a), ops.pack_weight(w), bias=bias, residual=res)
+    assert rel_l2(c, ref) < 2e-6
+    c1 = ops.gemm(ops.pack_rows(a), ops.pack_weight(w), bias=bias, residual=res, passes=1)
+    assert rel_l2(c1, ref) < 2e-3
+    c = ops.gemm(ops.pack_rows(a), ops.pack_weight(w), relu=True)
+    assert rel_l2(c, F.relu(a.double() @ w.double().t())) < 2e-6
+
+
+def test_gemm_rowvec(ops):
+    B, HW, K, N = 3, 64, 128, 256
+    a = rnd(B * HW, K, seed=7)
+    w = rnd(N, K, seed=8, scale=K ** -0.5)
+    big = rnd(B, 3 * N, seed=9)
+    rv = big[:, N:2 * N]                      # strided view like the fused emb GEMM output
+    ref = (a.double() @ w.double().t()).view(B, HW, N) + rv.double()[:, None]
+    c = ops.gemm(ops.pack_rows(a), ops.pack_weight(w), rowvec=rv, rows_per_group=HW)
+    assert rel_l2(c.view(B, HW, N), ref) < 2e-6
+
+
+@pytest.mark.parametrize('B,H,W,C,Cout', [(2, 32, 32, 128, 128), (3, 16, 16, 256, 384), (5, 8, 8, 384, 128),
+                                          (11, 4, 4, 512, 512), (2, 32, 32, 1024 // 4, 128), (1, 56, 56, 64, 64)])
+def test_gemm_conv3(ops, B, H, W, C, Cout):
+    x = rnd(B, C, H, W, seed=10)
+    w = rnd(Cout, C, 3, 3, seed=11, scale=(9 * C) ** -0.5)
+    bias = rnd(Cout, seed=12)
+    ref = F.conv2d(x.double(), w.double(), bias.double(), padding=1).permute(0, 2, 3, 1).reshape(-1, Cout)
+    xh = x.permute(0, 2, 3, 1).reshape(-1, C).contiguous()       # NHWC rows
+    a = ops.pack_rows(xh)
+    c = ops.gemm(a, ops.pack_weight_conv3(w), bias=bias, conv=(ops.SDB_A_CONV3, B, H, W, C))
+    assert rel_l2(c, ref) < 2e-6
+
+
+@pytest.mark.parametrize('B,H,W,C', [(2, 32, 32, 128), (3, 16, 16, 256), (5, 8, 8, 384)])
+def test_gemm_conv3_stride2(ops, B, H, W, C):
+    x = rnd(B, C, H, W, seed=13)
+    w = rnd(C, C, 3, 3, seed=14, scale=(9 * C) ** -0.5)
+    bias = rnd(C, seed=15)
+    ref = F.conv2d(x.double(), w.double(), bias.double(), stride=2, padding=1).permute(0, 2, 3, 1).reshape(-1, C)
+    xh = x.permute(0, 2, 3, 1).reshape(-1, C).contiguous()
+    a = ops.pack_nhwc(xh, None, B, H, W, mode=ops.SDB_PACK_PHASE2)
+    c = ops.gemm(a, ops.pack_weight_conv3(w), bias=bias, conv=(ops.SDB_A_CONV3S2, B, H // 2, W // 2, C))
+    assert rel_l2(c, ref) < 2e-6
+
+
+def test_pack_nhwc_up2_and_concat(ops):
+    B, H, W, C1, C2 = 2, 8, 8, 64, 128
+    x1, x2 = rnd(B * H * W, C1, seed=16), rnd(B * H * W, C2, seed=17)
+    cat = torch.cat([x1, x2], 1)
+    p, ycat = ops.pack_nhwc(x1, x2, B, H, W, want_cat=True)
+    assert torch.equal(ycat, cat)
+    assert rel_l2(p.unpack(), cat) < 1e-6
+    up = ops.pack_nhwc(x1, None, B, H, W, mode=ops.SDB_PACK_UP2)
+    ref = F.interpolate(x1.view(B, H, W, C1).permute(0, 3, 1, 2), scale_factor=2, mode='nearest')
+    assert rel_l2(up.unpack(), ref.permute(0, 2, 3, 1).reshape(-1, C1)) < 1e-6
+
+
+@pytest.mark.parametrize('C', [192, 256, 384, 512])
+def test_layernorm_pack(ops, C):
+    x = rnd(777, C, seed=18, scale=2.0) + 0.5
+    g, b = rnd(C, seed=19) * 0.1 + 1, rnd(C, seed=20) * 0.1
+    p, y = ops.layernorm_pack(x, g, b, 1e-5, want_fp32=True)
+    ref = F.layer_norm(x.double(), (C,), g.double(), b.double(), 1e-5)
+    assert rel_l2(y, ref) < 2e-6
+    assert rel_l2(p.unpack(), ref) < 2e-6
+
+
+@pytest.mark.parametrize('C1,C2,HW,silu,eps', [(128, 0, 1024, True, 1e-5), (512, 384, 64, True, 1e-5),
+                                               (256, 0, 256, False, 1e-6), (384, 256, 16, True, 1e-5)])
+def test_groupnorm_pack(ops, C1, C2, HW, silu, eps):
+    B = 3
+    x1 = rnd(B * HW, C1, seed=21, scale=1.5) + 0.3
+    x2 = rnd(B * HW, C2, seed=22) if C2 else None
+    C = C1 + C2
+    g, b = rnd(C, seed=23) * 0.1 + 1, rnd(C, seed=24) * 0.1
+    p = ops.groupnorm_pack(x1, x2, g, b, B, HW, 32, eps, silu)
+    x = torch.cat([x1, x2], 1) if C2 else x1
+    xn = x.view(B, HW, C).permute(0, 2, 1).double()
+    ref = F.group_norm(xn, 32, g.double(), b.double(), eps)
+    if silu:
+        ref = F.silu(ref)
+    assert rel_l2(p.unpack(), ref.permute(0, 2, 1).reshape(-1, C)) < 3e-6
+
+
+def test_geglu_and_timestep(ops):
+    u = rnd(100, 2048, seed=25, scale=2.0)
+    ref = u[:, :1024].double() * F.gelu(u[:, 1024:].double())
+    assert rel_l2(ops.geglu_pack(u).unpack(), ref) < 2e-6
+    t = torch.tensor([0.0, 1.0, 333.25, 998.999, 999.0], device='cuda')
+    from oracle.unet_ref import timestep_embedding
+    ref = timestep_embedding(t.cpu(), 128)
+    got = ops.timestep_embedding_pack(t, 128).unpack().cpu()
+    assert (got - ref).abs().max().item() < 2e-4     # fp32 sin/cos of arguments up to 1e3: ~1e-4 abs agreement
+    ti = torch.tensor([3, 500], device='cuda')
+    got = ops.timestep_embedding_pack(ti, 128).unpack().cpu()
+    assert (got - timestep_embedding(ti.cpu(), 128)).abs().max().item() < 2e-4
+
+
+@pytest.mark.parametrize('Lq,Lk,heads', [(256, 256, 8), (64, 64, 12), (16, 16, 16), (256, 11, 8), (100, 24, 4),
+                                         (784, 784, 2)])
+def test_attention(ops, Lq, Lk, heads):
+    B, d = 2, 32
+    C = heads * d
+    qkv = rnd(B * Lq, 3 * C, seed=26)
+    kv = rnd(B * Lk, 2 * C, seed=27)
+    q = qkv[:, :C]
+    k, v = kv[:, :C], kv[:, C:]
+    out = ops.attention_pack(q, k, v, B, Lq, Lk, heads, d, d ** -0.5).unpack()
+    qd = q.double().view(B, Lq, heads, d).transpose(1, 2)
+    kd = k.double().view(B, Lk, heads, d).transpose(1, 2)
+    vd = v.double().view(B, Lk, heads, d).transpose(1, 2)
+    ref = (torch.softmax(qd @ kd.transpose(-1, -2) * d ** -0.5, -1) @ vd).transpose(1, 2).reshape(B * Lq, C)
+    assert rel_l2(out, ref) < 3e-6
+
+
+def test_conv_in_out(ops):
+    B, H, W = 3, 32, 32
+    x = rnd(B, 3, H, W, seed=28)
+    w, b = rnd(128, 3, 3, 3, seed=29, scale=0.2), rnd(128, seed=30)
+    y = ops.conv3_in(x, w, b)
+    ref = F.conv2d(x.double(), w.double(), b.double(), padding=1).permute(0, 2, 3, 1).reshape(-1, 128)
+    assert rel_l2(y, ref) < 2e-6
+    h = rnd(B * H * W, 128, seed=31, scale=2.0)
+    g, be = rnd(128, seed=32) * 0.1 + 1, rnd(128, seed=33) * 0.1
+    w2, b2 = rnd(3, 128, 3, 3, seed=34, scale=0.05), rnd(3, seed=35)
+    stats = ops.groupnorm_stats(h, None, B, H * W, 32, 1e-5)
+    y = ops.conv3_out(h, stats, g, be, w2, b2, B, H, W)
+    hn = h.view(B, H, W, 128).permute(0, 3, 1, 2).double()
+    ref = F.conv2d(F.silu(F.group_norm(hn, 32, g.double(), be.double(), 1e-5)), w2.double(), b2.double(), padding=1)
+    assert rel_l2(y, ref) < 3e-6
+
+
+@pytest.mark.parametrize('B,N,S,D', [(2, 1024, 11, 192), (1, 1024, 24, 192), (3, 196, 7, 256), (5, 77, 5, 192),
+                                     (64, 1024, 11, 192), (2, 100, 15, 64)])
+def test_slot_attend(ops, B, N, S, D):
+    kv = rnd(B * N, 2 * D, seed=36)
+    q = rnd(B * S, D, seed=37)
+    scale, eps = D ** -0.5, 1e-6
+    upd, mask, upd32 = ops.slot_attend(kv, q, B, N, S, D, scale, eps, want_mask=True, want_fp32=True)
+    k = kv[:, :D].double().view(B, N, D)
+    v = kv[:, D:].double().view(B, N, D)
+    attn = torch.softmax(scale * k @ q.double().view(B, S, D).transpose(1, 2), -1)
+    a = attn + eps
+    a = a / a.sum(1, keepdim=True)
+    ref = torch.einsum('bns,bnd->bsd', a, v).reshape(B * S, D)
+    assert rel_l2(mask, attn.transpose(1, 2)) < 3e-6
+    assert rel_l2(upd32, ref) < 3e-6
+    assert rel_l2(upd.unpack(), ref) < 3e-6
+
+
+def test_gru_gates(ops):
+    R, D = 77, 192
+    gi, gh, h = rnd(R, 3 * D, seed=38), rnd(R, 3 * D, seed=39), rnd(R, D, seed=40)
+    out = ops.gru_gates(gi, gh, h)
+    a, b = gi.double(), gh.double()
+    r = torch.sigmoid(a[:, :D] + b[:, :D])
+    z = torch.sigmoid(a[:, D:2 * D] + b[:, D:2 * D])
+    n = torch.tanh(a[:, 2 * D:] + r * b[:, 2 * D:])
+    assert rel_l2(out, (1 - z) * n + z * h.double()) < 2e-6
+
+
+def test_dpm_glue(ops):
+    from oracle import dpm_ref
+    B = 4
+    x, eps = rnd(B, 3, 32, 32, seed=41), rnd(B, 3, 32, 32, seed=42)
+    cb = rnd(4096, 3, seed=43)
+    x0, idx = ops.dpm_x0(x, eps, 0.8, 0.6, cb, want_idx=True)
+    z = (x.cpu() - 0.6 * eps.cpu()) / 0.8
+    zq, ridx = dpm_ref.vq_quantize(z, cb.cpu())
+    agree = (idx.cpu().view(B, 32, 32) == ridx).float().mean().item()
+    assert agree > 0.999                      # ties in fp32 distance may break differently
+    same = (idx.cpu().view(B, 32, 32) == ridx)[:, None].expand_as(zq)
+    assert torch.equal(x0.cpu()[same], zq[same])
+    x0n = ops.dpm_x0(x, eps, 0.8, 0.6, None)
+    assert rel_l2(x0n, z) < 1e-6
+    m0, m1 = rnd(B, 3, 32, 32, seed=44), rnd(B, 3, 32, 32, seed=45)
+    y = ops.lincomb(x, m0, m1, 0.5, -0.25, 2.0)
+    assert rel_l2(y, 0.5 * x - 0.25 * m0 + 2.0 * (m1 - m0)) < 1e-6
