@@ -1,0 +1,72 @@
+"""Forward/backward drivers that sequence the C-ABI kernels for the hot modules.
+
+`slot_attention_apply` runs the whole iterative Slot Attention update
+(reference: img_based/models/slot_attention.py:67-104, sa_diffusion.py:28-70) as a chain of
+hand-written kernels:
+
+  LayerNorm+pack -> [Wk|Wv] GEMM (tcgen05)                               once
+  per iteration: LayerNorm+pack -> Wq GEMM -> fused attend (TMA-staged, one pass over k|v)
+                 -> W_ih / W_hh GEMMs -> GRU gates -> LayerNorm+pack -> MLP GEMMs (+ReLU, +residual)
+"""
+import torch
+
+from . import ops
+
+
+def _needs_grad(*ts):
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in ts)
+
+
+def slot_attention_forward(mod, inputs, slots, want_mask, save=None):
+    """Returns (slots [B,S,D], seg_mask [B,S,N] or None).  `save`: optional list that receives the
+    per-iteration tensors needed by the backward pass."""
+    B, N, Din = inputs.shape
+    S, D = slots.shape[1], slots.shape[2]
+    wc = mod._wcache
+    inputs = inputs.contiguous().float()
+    slots = slots.contiguous().float().reshape(B * S, D)
+
+    # k | v projection of LayerNorm(inputs)                                  (slot_attention.py:68-72)
+    xn = ops.layernorm_pack(inputs.reshape(B * N, Din), mod.norm_inputs.weight, mod.norm_inputs.bias,
+                            mod.norm_inputs.eps)
+    w_kv = wc.linear('kv', mod.project_k.weight, mod.project_v.weight)
+    kv = ops.gemm(xn, w_kv)                                                   # [B*N, 2D]
+    w_q = wc.linear('q', mod.project_q[1].weight)
+    w_ih = wc.linear('ih', mod.gru.weight_ih)
+    w_hh = wc.linear('hh', mod.gru.weight_hh)
+    w_1 = wc.linear('m1', mod.mlp[1].weight)
+    w_2 = wc.linear('m2', mod.mlp[3].weight)
+    if save is not None:
+        save.append(dict(xn=xn, kv=kv))
+    mask = None
+    for it in range(mod.num_iterations):
+        last = it == mod.num_iterations - 1
+        prev = slots
+        sn = ops.layernorm_pack(prev, mod.project_q[0].weight, mod.project_q[0].bias, mod.project_q[0].eps)
+        q = ops.gemm(sn, w_q)                                                 # :82
+        upd, m, upd32 = ops.slot_attend(kv, q, B, N, S, D, mod.attn_scale, mod.eps, want_mask and last,
+                                        want_fp32=save is not None)           # :84-91
+        if want_mask and last:
+            mask = m
+        gi = ops.gemm(upd, w_ih, bias=mod.gru.bias_ih)                        # :97-100
+        hp = ops.pack_rows(prev)
+        gh = ops.gemm(hp, w_hh, bias=mod.gru.bias_hh)
+        h = ops.gru_gates(gi, gh, prev)
+        hn = ops.layernorm_pack(h, mod.mlp[0].weight, mod.mlp[0].bias, mod.mlp[0].eps)
+        y1 = ops.gemm(hn, w_1, bias=mod.mlp[1].bias, relu=True)               # :102
+        y1p = ops.pack_rows(y1)
+        slots = ops.gemm(y1p, w_2, bias=mod.mlp[3].bias, residual=h)
+        if save is not None:
+            save.append(dict(prev=prev, sn=sn, q=q, upd=upd, upd32=upd32, gi=gi, gh=gh, hp=hp, h=h, hn=hn, y1=y1,
+                             y1p=y1p))
+    return slots.view(B, S, D), mask
+
+
+def slot_attention_apply(mod, inputs, slots, want_mask):
+    params = [p for p in mod.parameters()]
+    if _needs_grad(inputs, slots, *params):
+        from .backward import SlotAttentionFn
+        out = SlotAttentionFn.apply(mod, want_mask, inputs, slots, *params)
+        return out[0], (out[1] if want_mask else None)
+    with torch.no_grad():
+        return slot_attention_forward(mod, inputs, slots, want_mask)

