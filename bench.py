@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""Benchmark of the SlotDiffusion hot path on B200 (see DESIGN.md "measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
+
+Workload (BASELINE.json configs[1]): SlotDiffusion img_based LDM, CLEVRTex 128x128, 11 slots --
+one STEP = Slot Attention (3 iterations over 32x32x192 features) on a batch, then the 20-NFE
+DPM-Solver++ sampling loop of the slot-conditioned UNet (vq_denoised) on that batch.
+metric = denoise sample-steps/s = (batch x 20 UNet evaluations) / time, whole job over all ranks.
+One process per GPU (torchrun), batch sharded across ranks, no data-path collective (weak scaling).
+
+--impl reference: the CPU restatement of the reference (oracle/, torch fp32 on the host cores, all threads)
+on a bounded sample of the same workload; rank 0 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = 'dpm_solver_denoise_steps_per_sec'
+UNIT = 'sample-steps/s'
+NFE = 20
+S, D, N_TOK, SA_ITERS = 11, 192, 1024, 3
+# algorithmic work (SURVEY.md 8d / BASELINE.md 2)
+UNET_FLOP_PER_SAMPLE = 21.13e9
+SA_BYTES_PER_SAMPLE = 848384
+SA_WEIGHT_BYTES = 1928448
+
+
+def load_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, 'measured'
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0}, 'fallback'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            f = [c.strip() for c in r.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def build_models(device, seed=0):
+    from slotdiffusion_b200.slot_attention import SlotAttentionWMask
+    from slotdiffusion_b200.unet import UNetModel
+    from slotdiffusion_b200.dpm_solver import DPMSolverSampler
+    torch.manual_seed(seed)
+    sa = SlotAttentionWMask(D, SA_ITERS, S, D, 2 * D).to(device).eval()
+    unet = UNetModel(in_channels=3, model_channels=128, out_channels=3, num_res_blocks=2,
+                     attention_resolutions=(8, 4, 2), dropout=0.1, channel_mult=(1, 2, 3, 4), dims=2,
+                     use_checkpoint=False, num_head_channels=32, resblock_updown=False, conv_resample=True,
+                     transformer_depth=1, context_dim=D, n_embed=None).to(device).eval()
+    with torch.no_grad():   # the reference zero-initialises 187 tensors; re-draw them so the work is non-trivial
+        for p in unet.parameters():
+            if p.abs().max() == 0:
+                p.normal_(0, 0.02)
+    betas = (torch.linspace(0.0015 ** 0.5, 0.0195 ** 0.5, 1000, dtype=torch.float64) ** 2).float()
+    codebook = torch.randn(4096, 3, device=device)
+    sampler = DPMSolverSampler(unet, betas, codebook=codebook, steps=NFE, use_cuda_graph=True)
+    init_slots = torch.randn(1, S, D, device=device)
+    return sa, unet, sampler, init_slots
+
+
+def run_ours(args):
+    from slotdiffusion_b200 import _lib, ops
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+    B = args.batch
+    sa, unet, sampler, init_slots = build_models(dev, seed=rank)
+    g = torch.Generator().manual_seed(1234 + rank)
+    feats_h = torch.randn(B, N_TOK, D, generator=g).pin_memory()      # synthetic encoder features (MOVi/CLEVRTex shape)
+    noise_h = torch.randn(B, 3, 32, 32, generator=g).pin_memory()
+    feats_d, noise_d = feats_h.to(dev), noise_h.to(dev)
+    out_h = torch.empty(B, 3, 32, 32).pin_memory()
+    slots0 = init_slots.expand(B, -1, -1).contiguous()
+
+    def step_device():
+        with torch.no_grad():
+            slots, _mask = sa(feats_d, slots0)
+            return sampler.sample(noise_d, slots)
+
+    def step_e2e():
+        with torch.no_grad():
+            f = feats_h.to(dev, non_blocking=True)
+            n = noise_h.to(dev, non_blocking=True)
+            slots, _mask = sa(f, slots0)
+            lat = sampler.sample(n, slots)
+            out_h.copy_(lat, non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    # launches per step, counted on an un-captured pass (graph replays do not go through the C ABI again)
+    sampler.use_cuda_graph = False
+    step_device()
+    torch.cuda.synchronize()
+    n0 = _lib.launch_count()
+    step_device()
+    torch.cuda.synchronize()
+    launches_per_step = _lib.launch_count() - n0
+    sampler.use_cuda_graph = True
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    clk = ClockSampler(local)
+    clk.start()
+    ms = timed(step_device, args.steps)
+    clocks = clk.stop()
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    # roofline of the dominant kernel (sdb200 gemm_kernel), measured live with CUDA events around every launch
+    roof = gemm_roofline(unet, sampler, B, dev)
+    sa_ms = time_sa(sa, feats_d, slots0)
+
+    if rank == 0:
+        peaks, peak_src = load_peaks()
+        units = B * NFE * world * args.steps
+        value = units / (ms / 1e3)
+        peak_tf = peaks.get('bf16_tflops_sustained', peaks['bf16_tflops'])
+        ach = roof['flops'] / (roof['ms'] / 1e3) / 1e12
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 (split-fp16 x3 tensor-core products, fp32 accumulate)',
+            'data': 'synthetic',
+            'config': {
+                'workload': 'SlotDiffusion img LDM CLEVRTex 128x128: SlotAttention(3 it, 11 slots, 1024x192 features) '
+                            '+ DPM-Solver++ 20 NFE UNet(134M) vq_denoised, per-GPU batch %d' % B,
+                'per_gpu_batch': B, 'global_batch': B * world, 'nfe': NFE, 'num_slots': S,
+                'parallelism': 'batch-sharded replicas, no data-path collective',
+                'l2_policy': 'no flush: per-step working set (1.07 GB packed weights + activations) >> 126 MB L2',
+                'nfe_per_sec': NFE * args.steps * world / (ms / 1e3),
+                'images_per_sec': B * args.steps * world / (ms / 1e3),
+                'slot_attention_ms_B%d' % B: sa_ms,
+                'slot_attention_hbm_frac': ((B * SA_BYTES_PER_SAMPLE + SA_WEIGHT_BYTES) / (sa_ms / 1e3) / 1e9)
+                / peaks['hbm_gbs'],
+            },
+            'clocks': clocks,
+            'e2e': {'value': units / (ms_e2e / 1e3), 'unit': UNIT,
+                    'h2d_bytes_per_step': feats_h.numel() * 4 + noise_h.numel() * 4,
+                    'd2h_bytes_per_step': out_h.numel() * 4},
+            'gpu_launches': int(launches_per_step * args.steps),
+            'roofline': {'bound': 'tensor', 'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s',
+                         'frac': ach / peak_tf, 'traffic': None,
+                         'kernel': 'sdb::gemm_kernel (tcgen05 kind::f16, 3 MMA passes per algorithmic product)',
+                         'peak_source': peak_src + ' bf16 sustained', 'tensor_pipe_frac': 3 * ach / peak_tf,
+                         'gemm_share_of_unet_time': roof['share'], 'launches': roof['launches']},
+            'cpu_baseline': cpu_baseline(sample_nfe=NFE, batch=2),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def profile_once(args):
+    dev = torch.device('cuda', 0)
+    B = args.batch
+    sa, unet, sampler, init_slots = build_models(dev)
+    feats = torch.randn(B, N_TOK, D, device=dev)
+    x = torch.randn(B, 3, 32, 32, device=dev)
+    t = torch.randint(0, 1000, (B,), device=dev)
+    with torch.no_grad():
+        for _ in range(2):      # pass 0 = warm-up (weight packing), pass 1 = the one to read in the profile
+            slots, _ = sa(feats, init_slots.expand(B, -1, -1).contiguous())
+            unet(x, t, context=slots)
+    torch.cuda.synchronize()
+
+
+def gemm_roofline(unet, sampler, B, dev):
+    """One un-captured UNet evaluation with CUDA events around every sdb_gemm launch."""
+    from slotdiffusion_b200 import ops
+    real = ops.gemm
+    recs = []
+
+    def timed_gemm(a, w, *pa, **kw):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = real(a, w, *pa, **kw)
+        e1.record()
+        conv = kw.get('conv')
+        M = a.rows if conv is None else conv[1] * conv[2] * conv[3]
+        recs.append((e0, e1, 2.0 * M * w.rows * w.K))
+        return out
+    x = torch.randn(B, 3, 32, 32, device=dev)
+    t = torch.randint(0, 1000, (B,), device=dev)
+    ctx = torch.randn(B, S, D, device=dev)
+    with torch.no_grad():
+        unet(x, t, context=ctx)
+        torch.cuda.synchronize()
+        import slotdiffusion_b200.unet_exec as ue
+        ops.gemm = timed_gemm
+        try:
+            w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            w0.record()
+            unet(x, t, context=ctx)
+            w1.record()
+        finally:
+            ops.gemm = real
+    torch.cuda.synchronize()
+    ms = sum(e0.elapsed_time(e1) for e0, e1, _ in recs)
+    return {'ms': ms, 'flops': sum(f for _, _, f in recs), 'launches': len(recs), 'share': ms / w0.elapsed_time(w1)}
+
+
+def time_sa(sa, feats, slots0, iters=20):
+    with torch.no_grad():
+        for _ in range(3):
+            sa(feats, slots0)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            sa(feats, slots0)
+        e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def cpu_step(batch, nfe, seed=0, state={}):
+    """One bounded step of the same workload through the CPU oracle (port of the reference)."""
+    from oracle import dpm_ref, unet_ref
+    from oracle import slot_attention_ref as sa_ref
+    if 'sd' not in state:
+        state['sd'] = unet_ref.random_state_dict(seed=seed)
+        state['p'] = sa_ref.random_params(D, D, 2 * D, seed=seed)
+        state['betas'] = dpm_ref.ddpm_buffers(dpm_ref.linear_betas())['betas']
+        state['cb'] = torch.randn(4096, 3)
+    g = torch.Generator().manual_seed(seed)
+    feats = torch.randn(batch, N_TOK, D, generator=g)
+    slots0 = torch.randn(1, S, D, generator=g).expand(batch, -1, -1)
+    xT = torch.randn(batch, 3, 32, 32, generator=g)
+    with torch.no_grad():
+        slots, _ = sa_ref.slot_attention_forward(state['p'], feats, slots0, SA_ITERS)
+        return dpm_ref.dpm_sample(lambda x, t, c: unet_ref.unet_forward(state['sd'], x, t, c), state['betas'], xT,
+                                  slots, state['cb'], steps=nfe)
+
+
+def cpu_baseline(sample_nfe, batch):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cpu_step(batch, 2)   # warm-up (weight generation, thread pool)
+    t0 = time.perf_counter()
+    cpu_step(batch, sample_nfe)
+    dt = time.perf_counter() - t0
+    return {'value': batch * sample_nfe / dt, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+            'sample': f'oracle (torch CPU fp32 restatement of the reference): SlotAttention + {sample_nfe}-NFE '
+                      f'DPM-Solver++ at batch {batch}, 1 run, {dt:.1f} s'}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    batch = 4   # BASELINE configs[0]: the reference's CPU-runnable batch
+    steps = max(1, min(args.steps, 3))
+    warm = 1 if args.warmup > 0 else 0
+    for _ in range(warm):
+        cpu_step(batch, 2)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_step(batch, NFE)
+    dt = time.perf_counter() - t0
+    value = batch * NFE * steps / dt
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': steps,
+        'warmup': warm, 'ms_per_step': dt / steps * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'same workload through the CPU port of the reference (oracle/), batch %d, 20 NFE; '
+                               'steps bounded to %d so the run ends within minutes' % (batch, steps)},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                         'sample': f'{steps} step(s) of batch {batch} x {NFE} NFE'},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--batch', type=int, default=64, help='per-GPU batch')
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--profile-once', action='store_true',
+                    help='ncu helper: SlotAttention + ONE un-captured UNet evaluation (after one warm-up pass), no timing')
+    args = ap.parse_args()
+    if args.profile_once:
+        profile_once(args)
+    elif args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()
