@@ -2,39 +2,39 @@
 //
 // Persistent, warp-specialised kernel (one CTA per SM):
 //   warp 0      TMA producer   cp.async.bulk.tensor (5-D map for A: plain / implicit-im2col 3x3 / stride-2
-//                              phase-split; 2-D map for W), SWIZZLE_128B, 3-stage mbarrier ring
-//   warp 1      MMA issuer     tcgen05.mma.cta_group::1.kind::f16, 128 x BN x 16 per instruction, fp32
-//                              accumulators in TMEM (2 accumulator stages so the epilogue of tile i overlaps
-//                              the main loop of tile i+1)
-//   warps 2..5  epilogue       tcgen05.ld -> registers -> smem transpose -> coalesced fp32 stores with
-//                              bias / timestep-embedding row vector / residual / ReLU fused
+//                              phase-split; 2-D map for W), SWIZZLE_128B, 3..8-stage mbarrier ring
+//   warp 1      MMA issuer     tcgen05.mma.kind::f16, (128*CG) x BN x 16 per instruction (CG = 2: CTA pair,
+//                              cta_group::2), fp32 accumulators in TMEM (2 accumulator stages so the epilogue
+//                              of tile i overlaps the main loop of tile i+1)
+//   warps 2..5  epilogue       tcgen05.ld -> registers -> smem staging -> 128-bit coalesced fp32 stores (or
+//                              red.global.add for split-K) with bias / timestep-embedding row vector /
+//                              residual / ReLU fused; all global loads of a 32x32 block are issued before use
 // Operands are fp16 hi/lo planes (see sdb200.h "packed"); passes=3 issues hi*hi + lo*hi + hi*lo per k-step,
 // which reproduces the fp32 product to ~2^-22 while running on the fp16 tensor pipe.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
 namespace sdb {
 
-constexpr int BM = 128;          // UMMA M
+constexpr int BM = 128;          // rows of A per CTA (UMMA M = 128 * CG)
 constexpr int BK = 64;           // fp16 elements per stage row = 128 B = one swizzle-128B row
 constexpr int UK = 16;           // UMMA K for 16-bit operands
-constexpr int MAX_BN = 128;
-constexpr int STAGES = 3;
+constexpr int MAX_STAGES = 8;
 constexpr int ACC_STAGES = 2;
-constexpr int ACC_COLS = 128;    // TMEM columns per accumulator stage
+constexpr int ACC_COLS = 256;    // TMEM columns per accumulator stage (max UMMA N)
+constexpr int TMEM_COLS = ACC_STAGES * ACC_COLS;
 constexpr int GEMM_THREADS = 192;
 constexpr int EPI_WARPS = 4;
 constexpr uint32_t TILE_A_BYTES = BM * BK * 2;       // 16 KB
-constexpr uint32_t TILE_B_BYTES = MAX_BN * BK * 2;   // 16 KB (allocated for the max BN)
-constexpr uint32_t STAGE_BYTES = 2 * TILE_A_BYTES + 2 * TILE_B_BYTES;  // A_hi, A_lo, B_hi, B_lo
-constexpr uint32_t EPI_STAGE_FLOATS = 32 * 33;
+constexpr int EPI_LD = 36;                           // padded row stride (floats) of the epilogue staging tile
+constexpr int SMEM_LIMIT = 227 * 1024;
 
-struct GemmSmem {
-  // operand ring first: every tile must be 1024-B aligned for SWIZZLE_128B
-  uint8_t ring[STAGES][STAGE_BYTES];
-  float epi[EPI_WARPS][EPI_STAGE_FLOATS];
-  uint64_t full[STAGES];
-  uint64_t empty[STAGES];
+struct GemmCtl {
+  float epi[EPI_WARPS][32 * EPI_LD];
+  uint64_t full[MAX_STAGES];
+  uint64_t empty[MAX_STAGES];
   uint64_t acc_full[ACC_STAGES];
   uint64_t acc_empty[ACC_STAGES];
   uint32_t tmem_base;
@@ -48,30 +48,43 @@ struct GemmArgs {
   long long ldc, ldv, ldr;
   int M, N, K;
   int mode;
-  int tile_rows;        // valid rows per M tile (<= 128)
-  int bn;               // N tile (multiple of 16, <= 128)
-  int n_tiles_m, n_tiles_n;
+  int tile_rows;        // valid rows per CTA M tile (<= 128)
+  int bn;               // N tile of the CTA group (multiple of 16, <= 256)
+  int bnl;              // rows of W each CTA loads per stage (= bn / CG)
+  int n_tiles_m;        // M tiles of the CTA GROUP (each covers CG * tile_rows rows)
+  int n_tiles_n;
   int kblocks;          // K blocks of 64 per tap (plain: ceil(K/64); conv: C/64)
   int ntaps;            // 1 or 9
+  int splits;           // split-K factor (partial sums combined with red.global.add)
+  int stages;
+  uint32_t stage_bytes;
   int passes;
   int relu;
-  int rows_per_group;
-  // conv geometry for A coordinates
-  int box_w, box_h, box_b;   // box extents (rows = box_w*box_h*box_b = tile_rows)
-  int H, W;                  // output H, W (conv modes)
+  int vec_ok;           // 128-bit epilogue accesses allowed (alignment / N % 4)
+  unsigned rows_per_group;
+  int H, W;             // output H, W (conv modes)
 };
 
+// Warp-specialised persistent GEMM.  CG = 1: one CTA per tile (UMMA 128 x bn).  CG = 2: a CTA pair (cluster of 2)
+// per tile, tcgen05 cta_group::2 (UMMA 256 x bn): each CTA stages its own 128 rows of A and HALF of the W tile,
+// which halves the shared-memory fill and read traffic per flop -- with three MMA passes per product the single-CTA
+// form is shared-memory-bandwidth bound well below the tensor peak.
+template <int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
             const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
             const GemmArgs g) {
   extern __shared__ uint8_t smem_raw[];
-  GemmSmem& sm = *reinterpret_cast<GemmSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  GemmCtl& ctl = *reinterpret_cast<GemmCtl*>(ring + (size_t)g.stages * g.stage_bytes);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = g.n_tiles_m * g.n_tiles_n;
-  const int ksteps = g.kblocks * g.ntaps;   // stages consumed per tile
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const int group = blockIdx.x / CG, ngroups = gridDim.x / CG;
+  const int num_items = g.n_tiles_m * g.n_tiles_n * g.splits;
+  const int ksteps = g.kblocks * g.ntaps;   // k-blocks (stages) of a whole tile
   const bool three = g.passes == 3;
+  const uint32_t b_tile_bytes = uint32_t(g.bnl) * BK * 2;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a_hi);
@@ -80,34 +93,36 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
       tma_prefetch_desc(&map_a_lo);
       tma_prefetch_desc(&map_b_lo);
     }
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&sm.full[s], 1);
-      mbar_init(&sm.empty[s], 1);
+    for (int s = 0; s < g.stages; ++s) {
+      mbar_init(&ctl.full[s], 1);
+      mbar_init(&ctl.empty[s], 1);
     }
     for (int a = 0; a < ACC_STAGES; ++a) {
-      mbar_init(&sm.acc_full[a], 1);
-      mbar_init(&sm.acc_empty[a], EPI_WARPS * 32);
+      mbar_init(&ctl.acc_full[a], 1);
+      mbar_init(&ctl.acc_empty[a], EPI_WARPS * CG);
     }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(&sm.tmem_base, ACC_STAGES * ACC_COLS);
-    tmem_relinquish();
+    if (CG == 2) { tmem_alloc_pair(&ctl.tmem_base, TMEM_COLS); tmem_relinquish_pair(); }
+    else { tmem_alloc(&ctl.tmem_base, TMEM_COLS); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = sm.tmem_base;
+  const uint32_t tmem_base = ctl.tmem_base;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (one thread per CTA) =====================
     if (lane == 0) {
-      const uint32_t tx = (three ? 2u : 1u) * (uint32_t(g.tile_rows) * BK * 2 + uint32_t(g.bn) * BK * 2);
+      const uint32_t tx = (three ? 2u : 1u) * (uint32_t(g.tile_rows) * BK * 2 + b_tile_bytes) * CG;
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int tm = tile / g.n_tiles_n, tn = tile % g.n_tiles_n;
-        // A tile origin
+      for (int item = group; item < num_items; item += ngroups) {
+        const int tile = item / g.splits, split = item - tile * g.splits;
+        const int tm = (tile / g.n_tiles_n) * CG + (int)rank, tn = tile % g.n_tiles_n;
+        const int ks_begin = (int)((long long)ksteps * split / g.splits);
+        const int ks_end = (int)((long long)ksteps * (split + 1) / g.splits);
         int x0 = 0, y0 = 0, b0 = 0;
         if (g.mode == SDB_A_PLAIN) {
           x0 = tm * BM;   // row index lives in dim 1
@@ -117,12 +132,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
           b0 = int(m0 / rows_per_img);
           y0 = int((m0 % rows_per_img) / g.W);
         }
-        for (int ks = 0; ks < ksteps; ++ks) {
-          mbar_wait(&sm.empty[stage], phase ^ 1);
-          uint8_t* base = sm.ring[stage];
-          mbar_arrive_expect_tx(&sm.full[stage], tx);
+        const int nrow = tn * g.bn + (int)rank * g.bnl;
+        for (int ks = ks_begin; ks < ks_end; ++ks) {
+          mbar_wait(&ctl.empty[stage], phase ^ 1);
+          uint8_t* base = ring + (size_t)stage * g.stage_bytes;
+          if (rank == 0) mbar_arrive_expect_tx(&ctl.full[stage], tx);
           const int tap = ks / g.kblocks;
-          const int c0 = (ks % g.kblocks) * BK;
+          const int c0 = (ks - tap * g.kblocks) * BK;
           int cx = x0, cy = y0, cp = 0;
           if (g.mode == SDB_A_CONV3) {
             cx = tap % 3 - 1;
@@ -134,67 +150,96 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
             cx = (kx == 0) ? -1 : 0;
             cy = y0 + ((ky == 0) ? -1 : 0);
           }
-          tma_load_5d(base, &map_a_hi, &sm.full[stage], c0, cx, cy, cp, b0);
-          tma_load_2d(base + 2 * TILE_A_BYTES, &map_b_hi, &sm.full[stage], ks * BK, tn * g.bn);
-          if (three) {
-            tma_load_5d(base + TILE_A_BYTES, &map_a_lo, &sm.full[stage], c0, cx, cy, cp, b0);
-            tma_load_2d(base + 2 * TILE_A_BYTES + TILE_B_BYTES, &map_b_lo, &sm.full[stage], ks * BK, tn * g.bn);
+          uint8_t* a_hi = base, * a_lo = base + TILE_A_BYTES;
+          uint8_t* b_hi = base + 2 * TILE_A_BYTES, * b_lo = b_hi + b_tile_bytes;
+          if (CG == 2) {
+            tma_load_5d_pair(a_hi, &map_a_hi, &ctl.full[stage], c0, cx, cy, cp, b0);
+            tma_load_2d_pair(b_hi, &map_b_hi, &ctl.full[stage], ks * BK, nrow);
+            if (three) {
+              tma_load_5d_pair(a_lo, &map_a_lo, &ctl.full[stage], c0, cx, cy, cp, b0);
+              tma_load_2d_pair(b_lo, &map_b_lo, &ctl.full[stage], ks * BK, nrow);
+            }
+          } else {
+            tma_load_5d(a_hi, &map_a_hi, &ctl.full[stage], c0, cx, cy, cp, b0);
+            tma_load_2d(b_hi, &map_b_hi, &ctl.full[stage], ks * BK, nrow);
+            if (three) {
+              tma_load_5d(a_lo, &map_a_lo, &ctl.full[stage], c0, cx, cy, cp, b0);
+              tma_load_2d(b_lo, &map_b_lo, &ctl.full[stage], ks * BK, nrow);
+            }
           }
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == g.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (single thread) =====================
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_f16(BM, g.bn);
+    // ===================== MMA issuer (single thread of the leader CTA) =====================
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = umma_idesc_f16(BM * CG, g.bn);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int item = group; item < num_items; item += ngroups, ++it) {
+        const int tile = item / g.splits, split = item - tile * g.splits;
+        const int ks_begin = (int)((long long)ksteps * split / g.splits);
+        const int ks_end = (int)((long long)ksteps * (split + 1) / g.splits);
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
-        mbar_wait(&sm.acc_empty[as], aphase ^ 1);
+        mbar_wait(&ctl.acc_empty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * ACC_COLS;
-        for (int ks = 0; ks < ksteps; ++ks) {
-          mbar_wait(&sm.full[stage], phase);
+        for (int ks = ks_begin; ks < ks_end; ++ks) {
+          mbar_wait(&ctl.full[stage], phase);
           tc_fence_after();
-          const uint32_t a_hi = smem_u32(sm.ring[stage]);
+          const uint32_t a_hi = smem_u32(ring + (size_t)stage * g.stage_bytes);
           const uint32_t a_lo = a_hi + TILE_A_BYTES;
           const uint32_t b_hi = a_hi + 2 * TILE_A_BYTES;
-          const uint32_t b_lo = b_hi + TILE_B_BYTES;
+          const uint32_t b_lo = b_hi + b_tile_bytes;
           const uint64_t da_hi = umma_desc_kmajor_sw128(a_hi), da_lo = umma_desc_kmajor_sw128(a_lo);
           const uint64_t db_hi = umma_desc_kmajor_sw128(b_hi), db_lo = umma_desc_kmajor_sw128(b_lo);
 #pragma unroll
           for (int k = 0; k < BK / UK; ++k) {
             const uint64_t adv = uint64_t((k * UK * 2) >> 4);   // 32 B per k-step inside the 128-B swizzle row
-            umma_f16(d_tmem, da_hi + adv, db_hi + adv, idesc, (ks | k) != 0);
-            if (three) {
-              umma_f16(d_tmem, da_lo + adv, db_hi + adv, idesc, 1);
-              umma_f16(d_tmem, da_hi + adv, db_lo + adv, idesc, 1);
+            const uint32_t acc = (ks != ks_begin || k != 0) ? 1u : 0u;
+            if (CG == 2) {
+              umma_f16_pair(d_tmem, da_hi + adv, db_hi + adv, idesc, acc);
+              if (three) {
+                umma_f16_pair(d_tmem, da_lo + adv, db_hi + adv, idesc, 1);
+                umma_f16_pair(d_tmem, da_hi + adv, db_lo + adv, idesc, 1);
+              }
+            } else {
+              umma_f16(d_tmem, da_hi + adv, db_hi + adv, idesc, acc);
+              if (three) {
+                umma_f16(d_tmem, da_lo + adv, db_hi + adv, idesc, 1);
+                umma_f16(d_tmem, da_hi + adv, db_lo + adv, idesc, 1);
+              }
             }
           }
-          umma_commit(&sm.empty[stage]);   // smem slot reusable once these MMAs retire
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          // smem slot reusable (in both CTAs) once these MMAs retire
+          if (CG == 2) umma_commit_pair(&ctl.empty[stage]); else umma_commit(&ctl.empty[stage]);
+          if (++stage == g.stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&sm.acc_full[as]);     // accumulator complete
+        if (CG == 2) umma_commit_pair(&ctl.acc_full[as]); else umma_commit(&ctl.acc_full[as]);   // accumulator complete
       }
     }
   } else {
-    // ===================== epilogue warps =====================
+    // ===================== epilogue warps (both CTAs: each drains its own 128 TMEM lanes) =====================
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    float* stg = sm.epi[warp - 2];
+    float* stg = ctl.epi[q];
+    const int c4 = (lane & 7) * 4, rsub = lane >> 3;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int tm = tile / g.n_tiles_n, tn = tile % g.n_tiles_n;
+    for (int item = group; item < num_items; item += ngroups, ++it) {
+      const int tile = item / g.splits, split = item - tile * g.splits;
+      const int tm = (tile / g.n_tiles_n) * CG + (int)rank, tn = tile % g.n_tiles_n;
+      const bool first = split == 0;       // the split that also adds bias / rowvec / residual
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      mbar_wait(&sm.acc_full[as], aphase);
+      mbar_wait(&ctl.acc_full[as], aphase);
       tc_fence_after();
-      const long long row0 = (long long)tm * g.tile_rows + q * 32;   // first output row of this warp
-      const int rows_valid = min(g.tile_rows - q * 32, 32);          // rows of this warp inside the tile
-      for (int cb = 0; cb < g.bn; cb += 32) {
+      const long long row0l = (long long)tm * g.tile_rows + q * 32;   // first output row of this warp
+      const int rows_valid = (int)min((long long)min(g.tile_rows - q * 32, 32), (long long)g.M - row0l);
+      const int row0 = (int)min(row0l, (long long)g.M);
+      const int ncols = min(g.bn, g.N - tn * g.bn);
+      for (int cb = 0; cb < ncols; cb += 32) {
         uint32_t r[32];
         const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * ACC_COLS + cb);
         if (g.bn - cb >= 32) {
@@ -206,35 +251,83 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
           for (int j = 0; j < 16; ++j) { r[j] = r16[j]; r[j + 16] = 0; }
         }
         tmem_ld_wait();
-        // thread `lane` holds row (q*32+lane), columns cb..cb+31 -> transpose through smem
+        if (rows_valid <= 0) continue;       // warp-uniform
+        // thread `lane` holds row (q*32+lane), columns cb..cb+31 -> stage so that 8 lanes cover one 128-B row segment
 #pragma unroll
-        for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(r[j]);
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(stg + lane * EPI_LD + 4 * j) =
+              make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                          __uint_as_float(r[4 * j + 3]));
         __syncwarp();
-        const int n = tn * g.bn + cb + lane;
-        const bool ncol_ok = (cb + lane < g.bn) && (n < g.N);
-        const float bias = (ncol_ok && g.bias) ? g.bias[n] : 0.f;
-        for (int i = 0; i < rows_valid; ++i) {
-          const long long m = row0 + i;
-          if (m >= g.M) break;
-          if (ncol_ok) {
-            float v = stg[i * 33 + lane] + bias;
-            if (g.rowvec) v += g.rowvec[(m / g.rows_per_group) * g.ldv + n];
-            if (g.residual) v += g.residual[m * g.ldr + n];
+        const int n = tn * g.bn + cb + c4;
+        if (g.vec_ok) {
+          const bool col_ok = (cb + c4 < ncols);
+          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (col_ok && first && g.bias) bias4 = *reinterpret_cast<const float4*>(g.bias + n);
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            float4 add[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int rr = (half * 4 + i) * 4 + rsub;
+              add[i] = bias4;
+              if (col_ok && rr < rows_valid && first) {
+                const unsigned m = (unsigned)(row0 + rr);
+                if (g.residual) {
+                  const float4 t = *reinterpret_cast<const float4*>(g.residual + (long long)m * g.ldr + n);
+                  add[i].x += t.x; add[i].y += t.y; add[i].z += t.z; add[i].w += t.w;
+                }
+                if (g.rowvec) {
+                  const float4 t =
+                      *reinterpret_cast<const float4*>(g.rowvec + (long long)(m / g.rows_per_group) * g.ldv + n);
+                  add[i].x += t.x; add[i].y += t.y; add[i].z += t.z; add[i].w += t.w;
+                }
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int rr = (half * 4 + i) * 4 + rsub;
+              if (col_ok && rr < rows_valid) {
+                float4 v = *reinterpret_cast<const float4*>(stg + rr * EPI_LD + c4);
+                v.x += add[i].x; v.y += add[i].y; v.z += add[i].z; v.w += add[i].w;
+                if (g.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                float* dst = g.c + (long long)(row0 + rr) * g.ldc + n;
+                if (g.splits > 1) red_add_v4(dst, v);
+                else *reinterpret_cast<float4*>(dst) = v;
+              }
+            }
+          }
+        } else {
+          // scalar fallback (unaligned views / N % 4 != 0): lane <-> column, rows in sequence
+          const int nn = tn * g.bn + cb + lane;
+          const bool col_ok = (cb + lane < ncols);
+          const float bias = (col_ok && first && g.bias) ? g.bias[nn] : 0.f;
+          for (int rr = 0; rr < rows_valid; ++rr) {
+            if (!col_ok) break;
+            const unsigned m = (unsigned)(row0 + rr);
+            float v = stg[rr * EPI_LD + lane] + bias;
+            if (first && g.rowvec) v += g.rowvec[(long long)(m / g.rows_per_group) * g.ldv + nn];
+            if (first && g.residual) v += g.residual[(long long)m * g.ldr + nn];
             if (g.relu) v = fmaxf(v, 0.f);
-            g.c[m * g.ldc + n] = v;
+            float* dst = g.c + (long long)m * g.ldc + nn;
+            if (g.splits > 1) atomicAdd(dst, v);
+            else *dst = v;
           }
         }
         __syncwarp();
       }
       tc_fence_before();
-      mbar_arrive(&sm.acc_empty[as]);
+      __syncwarp();
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_leader(&ctl.acc_empty[as]); else mbar_arrive(&ctl.acc_empty[as]);
+      }
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, ACC_STAGES * ACC_COLS);
+    if (CG == 2) tmem_dealloc_pair(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -286,16 +379,47 @@ static int make_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* d
   return 0;
 }
 
-static int pick_bn(int N) {
-  // largest multiple of 16 <= 128 that minimises padded work
-  int best = 16;
+// N tile: multiple of 16 (32 for CTA pairs so that each CTA's half is a whole number of 8-row swizzle atoms... 16 rows),
+// <= max_bn, minimising padded columns first and the tile count second.
+static int pick_bn(int N, int max_bn, int step) {
+  int best = step;
   long long best_cost = -1;
-  for (int bn = 128; bn >= 16; bn -= 16) {
+  for (int bn = max_bn; bn >= step; bn -= step) {
     long long tiles = cdiv(N, bn);
-    long long cost = tiles * bn * 1000 + tiles * 40;   // padded columns dominate, then tile count
+    long long cost = tiles * bn * 1000 + tiles * 40;
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
   }
   return best;
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+
+template <int CG>
+static int launch_gemm(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const CUtensorMap& mb_hi,
+                       const CUtensorMap& mb_lo, const GemmArgs& g, int groups, size_t smem, cudaStream_t st) {
+  static size_t attr = 0;
+  if (smem > attr) {
+    SDB_CHECK(cudaFuncSetAttribute(gemm_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(groups * CG));
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CG;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  SDB_CHECK(cudaLaunchKernelEx(&cfg, gemm_kernel<CG>, ma_hi, ma_lo, mb_hi, mb_lo, g));
+  SDB_LAUNCH_CHECK();
+  return 0;
 }
 
 }  // namespace sdb
@@ -314,34 +438,27 @@ extern "C" int sdb_gemm(const SdbGemm* p, void* stream) {
   g.c = p->c; g.bias = p->bias; g.rowvec = p->rowvec; g.residual = p->residual;
   g.ldc = p->ldc; g.ldv = p->ldv; g.ldr = p->ldr;
   g.M = p->M; g.N = p->N; g.K = p->K; g.mode = p->mode; g.passes = p->passes; g.relu = p->relu;
-  g.rows_per_group = p->rows_per_group > 0 ? p->rows_per_group : 1;
-  g.bn = pick_bn(p->N);
-  g.n_tiles_n = (int)cdiv(p->N, g.bn);
+  g.rows_per_group = p->rows_per_group > 0 ? (unsigned)p->rows_per_group : 1u;
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  g.vec_ok = (p->N % 4 == 0) && (p->ldc % 4 == 0) && al16(p->c) && (!p->bias || al16(p->bias)) &&
+             (!p->residual || (al16(p->residual) && p->ldr % 4 == 0)) &&
+             (!p->rowvec || (al16(p->rowvec) && p->ldv % 4 == 0));
 
-  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
-  const __half* a = reinterpret_cast<const __half*>(p->a);
-  const __half* w = reinterpret_cast<const __half*>(p->w);
-  int rc;
+  // ---- A-side tiling (per CTA: up to 128 rows)
+  int n_tiles_m1;   // M tiles of ONE CTA
+  int box_h = 1, box_b = 1;
   if (p->mode == SDB_A_PLAIN) {
     g.tile_rows = BM; g.ntaps = 1; g.kblocks = (int)cdiv(p->K, BK);
-    g.n_tiles_m = (int)cdiv(p->M, BM);
-    g.H = 1; g.W = 1; g.box_w = BM; g.box_h = 1; g.box_b = 1;
-    uint64_t dims[5] = {(uint64_t)p->K, (uint64_t)p->M, 1, 1, 1};
-    uint64_t st[4] = {(uint64_t)p->K * 2, (uint64_t)p->K * 2 * p->M, (uint64_t)p->K * 2 * p->M,
-                      (uint64_t)p->K * 2 * p->M};
-    uint32_t box[5] = {BK, BM, 1, 1, 1};
-    if ((rc = make_map(&ma_hi, a, 5, dims, st, box))) return rc;
-    if ((rc = make_map(&ma_lo, a + p->a_plane_stride, 5, dims, st, box))) return rc;
+    n_tiles_m1 = (int)cdiv(p->M, BM);
+    g.H = 1; g.W = 1;
   } else {
     SDB_REQUIRE(p->mode == SDB_A_CONV3 || p->mode == SDB_A_CONV3S2, "sdb_gemm: bad mode %d", p->mode);
     SDB_REQUIRE(p->C % BK == 0, "sdb_gemm: conv C=%d must be a multiple of 64", p->C);
     SDB_REQUIRE(p->K == 9 * p->C, "sdb_gemm: conv K=%d != 9*C", p->K);
     SDB_REQUIRE((long long)p->M == (long long)p->B * p->H * p->W, "sdb_gemm: conv M != B*H*W");
     SDB_REQUIRE(p->W <= 128, "sdb_gemm: conv W=%d > 128 unsupported", p->W);
-    const int H = p->H, W = p->W, B = p->B, C = p->C;   // output geometry
-    g.H = H; g.W = W; g.ntaps = 9; g.kblocks = C / BK;
-    // tile = box_b images x box_h rows x full width
-    int box_h, box_b;
+    const int H = p->H, W = p->W, B = p->B;   // output geometry
+    g.H = H; g.W = W; g.ntaps = 9; g.kblocks = p->C / BK;
     if (W * H <= BM) {            // whole images per tile
       box_h = H;
       box_b = BM / (W * H);
@@ -351,40 +468,73 @@ extern "C" int sdb_gemm(const SdbGemm* p, void* stream) {
       box_h = BM / W;             // rows per tile
       while (H % box_h) --box_h;  // tiles must not straddle images
     }
-    g.box_w = W; g.box_h = box_h; g.box_b = box_b;
     g.tile_rows = W * box_h * box_b;
-    g.n_tiles_m = (int)cdiv((long long)B * H * W, g.tile_rows);
-    if (p->mode == SDB_A_CONV3) {
-      uint64_t dims[5] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, 1, (uint64_t)B};
-      uint64_t st[4] = {(uint64_t)C * 2, (uint64_t)C * 2 * W, (uint64_t)C * 2 * W * H, (uint64_t)C * 2 * W * H};
-      uint32_t box[5] = {BK, (uint32_t)W, (uint32_t)box_h, 1, (uint32_t)box_b};
-      if ((rc = make_map(&ma_hi, a, 5, dims, st, box))) return rc;
-      if ((rc = make_map(&ma_lo, a + p->a_plane_stride, 5, dims, st, box))) return rc;
-    } else {
-      // phase-split input [B][4][H][W][C]
-      uint64_t dims[5] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, 4, (uint64_t)B};
-      uint64_t st[4] = {(uint64_t)C * 2, (uint64_t)C * 2 * W, (uint64_t)C * 2 * W * H, (uint64_t)C * 2 * W * H * 4};
-      uint32_t box[5] = {BK, (uint32_t)W, (uint32_t)box_h, 1, (uint32_t)box_b};
-      if ((rc = make_map(&ma_hi, a, 5, dims, st, box))) return rc;
-      if ((rc = make_map(&ma_lo, a + p->a_plane_stride, 5, dims, st, box))) return rc;
-    }
+    n_tiles_m1 = (int)cdiv((long long)B * H * W, g.tile_rows);
+  }
+
+  // ---- CTA grouping, N tile, split-K, pipeline depth
+  const int sms = num_sms();
+  int cg = (n_tiles_m1 >= 2) ? 2 : 1;
+  const int force_cg = env_int("SDB_GEMM_CG", 0);
+  if (force_cg == 1 || force_cg == 2) cg = force_cg;
+  g.bn = (cg == 2) ? pick_bn(p->N, 256, 32) : pick_bn(p->N, 128, 16);
+  g.bnl = g.bn / cg;
+  g.n_tiles_m = (int)cdiv(n_tiles_m1, cg);
+  g.n_tiles_n = (int)cdiv(p->N, g.bn);
+  const int ksteps = g.kblocks * g.ntaps;
+  const int units = sms / cg;
+  const long long tiles = (long long)g.n_tiles_m * g.n_tiles_n;
+  g.splits = 1;
+  if (!p->relu && tiles * 4 < (long long)units * 3 && ksteps >= 8) {
+    long long s = units / tiles;
+    if (s > ksteps / 4) s = ksteps / 4;
+    if (s > 32) s = 32;
+    if (s >= 2) g.splits = (int)s;
+  }
+  const int force_split = env_int("SDB_GEMM_SPLITK", 0);
+  if (force_split >= 1 && !p->relu) g.splits = force_split > ksteps ? ksteps : force_split;
+  g.stage_bytes = 2 * TILE_A_BYTES + 2 * (uint32_t)g.bnl * BK * 2;
+  const int avail = SMEM_LIMIT - 1024 - (int)sizeof(GemmCtl);
+  g.stages = avail / (int)g.stage_bytes;
+  if (g.stages > MAX_STAGES) g.stages = MAX_STAGES;
+  SDB_REQUIRE(g.stages >= 2, "sdb_gemm: tile does not fit shared memory");
+
+  // ---- tensor maps
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  const __half* a = reinterpret_cast<const __half*>(p->a);
+  const __half* w = reinterpret_cast<const __half*>(p->w);
+  int rc;
+  if (p->mode == SDB_A_PLAIN) {
+    uint64_t dims[5] = {(uint64_t)p->K, (uint64_t)p->M, 1, 1, 1};
+    uint64_t st[4] = {(uint64_t)p->K * 2, (uint64_t)p->K * 2 * p->M, (uint64_t)p->K * 2 * p->M,
+                      (uint64_t)p->K * 2 * p->M};
+    uint32_t box[5] = {BK, BM, 1, 1, 1};
+    if ((rc = make_map(&ma_hi, a, 5, dims, st, box))) return rc;
+    if ((rc = make_map(&ma_lo, a + p->a_plane_stride, 5, dims, st, box))) return rc;
+  } else {
+    const int H = p->H, W = p->W, B = p->B, C = p->C;
+    const uint64_t phases = (p->mode == SDB_A_CONV3S2) ? 4 : 1;   // phase-split input [B][4][H][W][C]
+    uint64_t dims[5] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, phases, (uint64_t)B};
+    uint64_t st[4] = {(uint64_t)C * 2, (uint64_t)C * 2 * W, (uint64_t)C * 2 * W * H, (uint64_t)C * 2 * W * H * phases};
+    uint32_t box[5] = {BK, (uint32_t)W, (uint32_t)box_h, 1, (uint32_t)box_b};
+    if ((rc = make_map(&ma_hi, a, 5, dims, st, box))) return rc;
+    if ((rc = make_map(&ma_lo, a + p->a_plane_stride, 5, dims, st, box))) return rc;
   }
   {
     uint64_t dims[2] = {(uint64_t)p->K, (uint64_t)p->N};
     uint64_t st[1] = {(uint64_t)p->K * 2};
-    uint32_t box[2] = {BK, (uint32_t)g.bn};
+    uint32_t box[2] = {BK, (uint32_t)g.bnl};
     if ((rc = make_map(&mb_hi, w, 2, dims, st, box))) return rc;
     if ((rc = make_map(&mb_lo, w + (long long)p->N * p->K, 2, dims, st, box))) return rc;
   }
-  const size_t smem = sizeof(GemmSmem) + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    SDB_CHECK(cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+  cudaStream_t st = as_stream(stream);
+  if (g.splits > 1) {   // partial sums are accumulated with red.global.add: C starts at zero
+    if (p->ldc == p->N) SDB_CHECK(cudaMemsetAsync(p->c, 0, (size_t)p->M * p->N * sizeof(float), st));
+    else SDB_CHECK(cudaMemset2DAsync(p->c, (size_t)p->ldc * sizeof(float), 0, (size_t)p->N * sizeof(float), p->M, st));
   }
-  const int tiles = g.n_tiles_m * g.n_tiles_n;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_kernel<<<grid, GEMM_THREADS, smem, as_stream(stream)>>>(ma_hi, ma_lo, mb_hi, mb_lo, g);
-  SDB_LAUNCH_CHECK();
-  return 0;
+  const size_t smem = (size_t)g.stages * g.stage_bytes + sizeof(GemmCtl) + 1024;
+  const long long items = tiles * g.splits;
+  const int groups = (int)(items < units ? items : units);
+  return cg == 2 ? launch_gemm<2>(ma_hi, ma_lo, mb_hi, mb_lo, g, groups, smem, st)
+                 : launch_gemm<1>(ma_hi, ma_lo, mb_hi, mb_lo, g, groups, smem, st);
 }

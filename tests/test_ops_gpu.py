@@ -48,6 +48,70 @@ def test_gemm_plain(ops, M, N, K):
     assert rel_l2(c, F.relu(a.double() @ w.double().t())) < 5e-6
 
 
+@pytest.fixture
+def gemm_env():
+    """Force a GEMM variant through the library's env knobs (read per call); always restored."""
+    import os
+    saved = {k: os.environ.get(k) for k in ('SDB_GEMM_CG', 'SDB_GEMM_SPLITK')}
+
+    def setenv(cg=None, splitk=None):
+        for k, v in (('SDB_GEMM_CG', cg), ('SDB_GEMM_SPLITK', splitk)):
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = str(v)
+    yield setenv
+    for k, v in saved.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
+
+
+@pytest.mark.parametrize('cg', [1, 2])
+@pytest.mark.parametrize('splitk', [1, 3])
+@pytest.mark.parametrize('M,N,K', [(1000, 200, 192), (4096, 384, 1024), (130, 512, 512), (2048, 1152, 256)])
+def test_gemm_variants(ops, gemm_env, cg, splitk, M, N, K):
+    """Single-CTA and CTA-pair (cta_group::2) kernels, with and without split-K, ragged M / N edges."""
+    gemm_env(cg, splitk)
+    a = rnd(M, K, seed=31)
+    w = rnd(N, K, seed=32, scale=K ** -0.5)
+    bias = rnd(N, seed=33)
+    res = rnd(M, N, seed=34)
+    big = rnd(M // 8 + 1, 2 * N, seed=35)
+    rv = big[:, N:]
+    ref = a.double() @ w.double().t() + bias.double() + res.double() + rv.double().repeat_interleave(8, 0)[:M]
+    c = ops.gemm(ops.pack_rows(a), ops.pack_weight(w), bias=bias, residual=res, rowvec=rv, rows_per_group=8)
+    assert rel_l2(c, ref) < 5e-6
+
+
+@pytest.mark.parametrize('cg', [1, 2])
+def test_gemm_scalar_epilogue(ops, gemm_env, cg):
+    """N % 4 != 0 / unaligned output view -> scalar epilogue path."""
+    gemm_env(cg, None)
+    M, N, K = 300, 30, 64
+    a, w, bias = rnd(M, K, seed=36), rnd(N, K, seed=37, scale=K ** -0.5), rnd(N, seed=38)
+    out = torch.zeros(M, N + 3, device='cuda')
+    c = ops.gemm(ops.pack_rows(a), ops.pack_weight(w), bias=bias, out=out[:, 1:N + 1])
+    ref = a.double() @ w.double().t() + bias.double()
+    assert rel_l2(c, ref) < 5e-6
+    assert out[:, 0].abs().max() == 0 and out[:, N + 1:].abs().max() == 0
+
+
+@pytest.mark.parametrize('cg', [1, 2])
+@pytest.mark.parametrize('splitk', [1, 4])
+def test_gemm_conv3_variants(ops, gemm_env, cg, splitk):
+    gemm_env(cg, splitk)
+    B, H, W, C, Cout = 5, 8, 8, 384, 512
+    x = rnd(B, C, H, W, seed=10)
+    w = rnd(Cout, C, 3, 3, seed=11, scale=(9 * C) ** -0.5)
+    bias = rnd(Cout, seed=12)
+    ref = F.conv2d(x.double(), w.double(), bias.double(), padding=1).permute(0, 2, 3, 1).reshape(-1, Cout)
+    xh = x.permute(0, 2, 3, 1).reshape(-1, C).contiguous()
+    c = ops.gemm(ops.pack_rows(xh), ops.pack_weight_conv3(w), bias=bias, conv=(ops.SDB_A_CONV3, B, H, W, C))
+    assert rel_l2(c, ref) < 2e-5
+
+
 def test_gemm_rowvec(ops):
     B, HW, K, N = 3, 64, 128, 256
     a = rnd(B * HW, K, seed=7)
