@@ -228,17 +228,25 @@ def run_ours(args):
 
 
 def profile_once(args):
+    """ncu helper (use with --profile-from-start off): warm-up passes outside the profiled range, then ONE
+    SlotAttention forward + ONE un-captured UNet evaluation between cudaProfilerStart/Stop."""
     dev = torch.device('cuda', 0)
     B = args.batch
     sa, unet, sampler, init_slots = build_models(dev)
     feats = torch.randn(B, N_TOK, D, device=dev)
     x = torch.randn(B, 3, 32, 32, device=dev)
     t = torch.randint(0, 1000, (B,), device=dev)
+    s0 = init_slots.expand(B, -1, -1).contiguous()
     with torch.no_grad():
-        for _ in range(2):      # pass 0 = warm-up (weight packing), pass 1 = the one to read in the profile
-            slots, _ = sa(feats, init_slots.expand(B, -1, -1).contiguous())
+        for _ in range(2):
+            slots, _ = sa(feats, s0)
             unet(x, t, context=slots)
-    torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        slots, _ = sa(feats, s0)
+        unet(x, t, context=slots)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
 
 
 def gemm_roofline(unet, sampler, B, dev):

@@ -67,6 +67,13 @@ typedef struct SdbGemm {
   int32_t rows_per_group; /* H*W for rowvec */
   int32_t passes;         /* 3 = hi*hi + lo*hi + hi*lo (fp32-faithful), 1 = hi*hi only */
   int32_t relu;           /* apply max(.,0) to the result (slot-attention MLP, slot_attention.py:51) */
+  void* out_packed;       /* optional: also emit act(result) as a packed operand [2][M][N] for the next GEMM (c may then be NULL) */
+  float* gsum;            /* optional: atomically accumulate GroupNorm partial sums [M / rows_per_group][N / 4][2] = (sum, sum of
+                             squares) of the result per sample and 4-channel block (consumed by sdb_groupnorm_apply_pack) */
+  int64_t out_plane_stride; /* halves between the hi and lo plane of out_packed */
+  int32_t out_act;        /* activation of the packed copy: 0 none, 1 SiLU, 2 ReLU */
+  int32_t geglu;          /* GEGLU epilogue (attention.py:46-48): W / bias rows interleaved by sdb_pack_weight_geglu; the only
+                             output is out_packed [2][M][N/2] = a * gelu_erf(g) */
 } SdbGemm;
 
 int sdb_gemm(const SdbGemm* p, void* stream);
@@ -94,6 +101,20 @@ int sdb_groupnorm_stats(const float* x1, int64_t C1, const float* x2, int64_t C2
 int sdb_groupnorm_apply_pack(const float* x1, int64_t C1, const float* x2, int64_t C2, const float* stats,
                              const float* gamma, const float* beta, void* out, int64_t B, int64_t HW, int G,
                              int silu, void* stream);
+
+/* Same normalisation with the statistics taken either from `stats` [B,G,2] or (stats == NULL) derived on the fly from
+ * the partial sums gsum1 [B][C1/4][2] (+ gsum2 [B][C2/4][2]) accumulated by the sdb_gemm epilogues that produced x1 / x2
+ * (biased variance as E[x^2] - mean^2 in fp32).  Removes the separate statistics pass over the activation. */
+int sdb_groupnorm_apply_pack_fused(const float* x1, int64_t C1, const float* gsum1, const float* x2, int64_t C2,
+                                   const float* gsum2, const float* stats, const float* gamma, const float* beta,
+                                   void* out, int64_t B, int64_t HW, int G, float eps, int silu, void* stream);
+/* partial sums -> stats [B,G,2] (mean, rstd) */
+int sdb_groupnorm_finalize(const float* gsum1, int64_t C1, const float* gsum2, int64_t C2, float* stats, int64_t B,
+                           int64_t HW, int G, float eps, void* stream);
+/* GEGLU.proj weight [2F,K] (+ bias [2F]) -> packed rows interleaved [16 a | 16 g] per 32-row chunk (+ permuted bias),
+ * the operand layout of sdb_gemm's `geglu` epilogue (attention.py:39-48) */
+int sdb_pack_weight_geglu(const float* w, const float* bias, void* out, float* bias_out, int64_t F, int64_t K,
+                          void* stream);
 
 /* raw NHWC -> packed, with layout transform.  x1 [B,H,W,C1] (+ x2 [B,H,W,C2] concatenated on C).
  *  SDB_PACK_PLAIN : out [2][B*H*W][C]                      (skip_connection 1x1 conv input, unet.py:256-259)

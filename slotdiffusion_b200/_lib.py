@@ -19,6 +19,8 @@ class SdbGemm(Structure):
         ('residual', c_void_p), ('a_plane_stride', c_int64), ('ldc', c_int64), ('ldv', c_int64), ('ldr', c_int64),
         ('M', c_int32), ('N', c_int32), ('K', c_int32), ('mode', c_int32), ('B', c_int32), ('H', c_int32),
         ('W', c_int32), ('C', c_int32), ('rows_per_group', c_int32), ('passes', c_int32), ('relu', c_int32),
+        ('out_packed', c_void_p), ('gsum', c_void_p), ('out_plane_stride', c_int64), ('out_act', c_int32),
+        ('geglu', c_int32),
     ]
 
 
@@ -37,6 +39,12 @@ SIGNATURES = {
                                     c_float, c_void_p]),
     'sdb_groupnorm_apply_pack': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
                                          c_void_p, c_int64, c_int64, c_int, c_int, c_void_p]),
+    'sdb_groupnorm_apply_pack_fused': (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
+                                               c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_int,
+                                               c_void_p]),
+    'sdb_groupnorm_finalize': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int,
+                                       c_float, c_void_p]),
+    'sdb_pack_weight_geglu': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     'sdb_pack_nhwc': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int64,
                               c_int, c_void_p]),
     'sdb_geglu_pack': (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p]),

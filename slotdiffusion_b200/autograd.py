@@ -39,6 +39,7 @@ def slot_attention_forward(mod, inputs, slots, want_mask, save=None):
     if save is not None:
         save.append(dict(xn=xn, kv=kv))
     mask = None
+    hp = None
     for it in range(mod.num_iterations):
         last = it == mod.num_iterations - 1
         prev = slots
@@ -49,16 +50,18 @@ def slot_attention_forward(mod, inputs, slots, want_mask, save=None):
         if want_mask and last:
             mask = m
         gi = ops.gemm(upd, w_ih, bias=mod.gru.bias_ih)                        # :97-100
-        hp = ops.pack_rows(prev)
+        if hp is None:
+            hp = ops.pack_rows(prev)
         gh = ops.gemm(hp, w_hh, bias=mod.gru.bias_hh)
         h = ops.gru_gates(gi, gh, prev)
         hn = ops.layernorm_pack(h, mod.mlp[0].weight, mod.mlp[0].bias, mod.mlp[0].eps)
-        y1 = ops.gemm(hn, w_1, bias=mod.mlp[1].bias, relu=True)               # :102
-        y1p = ops.pack_rows(y1)
-        slots = ops.gemm(y1p, w_2, bias=mod.mlp[3].bias, residual=h)
+        y1, y1p = ops.gemm(hn, w_1, bias=mod.mlp[1].bias, relu=True, pack_out='none',
+                           keep_c=save is not None)                           # :102 (ReLU + operand packing fused)
+        slots, sp = ops.gemm(y1p, w_2, bias=mod.mlp[3].bias, residual=h, pack_out='none')
         if save is not None:
             save.append(dict(prev=prev, sn=sn, q=q, upd=upd, upd32=upd32, gi=gi, gh=gh, hp=hp, h=h, hn=hn, y1=y1,
                              y1p=y1p))
+        hp = sp                                                              # next iteration's W_hh operand
     return slots.view(B, S, D), mask
 
 

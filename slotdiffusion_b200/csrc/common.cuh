@@ -40,6 +40,23 @@ __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
   lo = __float2half_rn(x - __half2float(hi));
 }
 
+__device__ __forceinline__ void store_split4(__half* hi, __half* lo, long long idx, float4 v) {
+  __half h0, h1, h2, h3, l0, l1, l2, l3;
+  split_f16(v.x, h0, l0);
+  split_f16(v.y, h1, l1);
+  split_f16(v.z, h2, l2);
+  split_f16(v.w, h3, l3);
+  __half2 a = __halves2half2(h0, h1), b = __halves2half2(h2, h3);
+  __half2 c = __halves2half2(l0, l1), d = __halves2half2(l2, l3);
+  uint2 ph, pl;
+  ph.x = *reinterpret_cast<uint32_t*>(&a);
+  ph.y = *reinterpret_cast<uint32_t*>(&b);
+  pl.x = *reinterpret_cast<uint32_t*>(&c);
+  pl.y = *reinterpret_cast<uint32_t*>(&d);
+  *reinterpret_cast<uint2*>(hi + idx) = ph;
+  *reinterpret_cast<uint2*>(lo + idx) = pl;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

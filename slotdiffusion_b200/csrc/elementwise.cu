@@ -12,23 +12,6 @@ static inline int grid_for(int64_t work_items, int threads, int max_waves = 8) {
   return (int)blocks;
 }
 
-__device__ __forceinline__ void store_split4(__half* hi, __half* lo, int64_t idx, float4 v) {
-  __half h0, h1, h2, h3, l0, l1, l2, l3;
-  split_f16(v.x, h0, l0);
-  split_f16(v.y, h1, l1);
-  split_f16(v.z, h2, l2);
-  split_f16(v.w, h3, l3);
-  __half2 a = __halves2half2(h0, h1), b = __halves2half2(h2, h3);
-  __half2 c = __halves2half2(l0, l1), d = __halves2half2(l2, l3);
-  uint2 ph, pl;
-  ph.x = *reinterpret_cast<uint32_t*>(&a);
-  ph.y = *reinterpret_cast<uint32_t*>(&b);
-  pl.x = *reinterpret_cast<uint32_t*>(&c);
-  pl.y = *reinterpret_cast<uint32_t*>(&d);
-  *reinterpret_cast<uint2*>(hi + idx) = ph;
-  *reinterpret_cast<uint2*>(lo + idx) = pl;
-}
-
 // ------------------------------------------------------------------ weights
 __global__ void pack_weight_kernel(const float* __restrict__ w, __half* __restrict__ out, int64_t n4, int64_t plane) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -198,6 +181,110 @@ __global__ void groupnorm_apply_pack_kernel(const float* __restrict__ x1, int C1
       r[j] = silu ? silu_f(o) : o;
     }
     store_split4(out, out + plane, row * C + c, make_float4(r[0], r[1], r[2], r[3]));
+  }
+}
+
+// GroupNorm apply (+SiLU) + pack, statistics either given ([B,G,2] mean/rstd) or derived on the fly from the
+// per-(sample, 4-channel block) partial sums that the producing GEMM epilogues accumulated (sdb_gemm `gsum`).
+// Grid (chunks, B); every thread owns 4 fixed channels (scale/shift live in registers) and strides over rows.
+__global__ void __launch_bounds__(256)
+groupnorm_apply_pack_fused_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ gsum1,
+                                  const float* __restrict__ x2, int C2, const float* __restrict__ gsum2,
+                                  const float* __restrict__ stats, const float* __restrict__ gamma,
+                                  const float* __restrict__ beta, __half* __restrict__ out, int64_t B, int HW, int G,
+                                  float eps, int silu, int rows_per_chunk) {
+  __shared__ float s_mean[64], s_rstd[64];
+  const int C = C1 + C2, c4n = C >> 2, cpg = C / G;
+  const int64_t b = blockIdx.y;
+  if (threadIdx.x < G) {
+    const int g = threadIdx.x;
+    if (stats) {
+      s_mean[g] = stats[(b * G + g) * 2];
+      s_rstd[g] = stats[(b * G + g) * 2 + 1];
+    } else {
+      float s = 0.f, ss = 0.f;
+      for (int kb = g * cpg / 4; kb < (g + 1) * cpg / 4; ++kb) {
+        const float* p = (kb * 4 < C1) ? gsum1 + (b * (C1 >> 2) + kb) * 2 : gsum2 + (b * (C2 >> 2) + kb - (C1 >> 2)) * 2;
+        s += p[0];
+        ss += p[1];
+      }
+      const float inv_n = 1.f / ((float)HW * cpg);
+      const float mean = s * inv_n;
+      const float var = fmaxf(ss * inv_n - mean * mean, 0.f);
+      s_mean[g] = mean;
+      s_rstd[g] = rsqrtf(var + eps);
+    }
+  }
+  __syncthreads();
+  const int tx = threadIdx.x % c4n, ty = threadIdx.x / c4n, rpb = blockDim.x / c4n;
+  if (ty >= rpb) return;   // launch width was rounded up for the statistics threads
+  const int c = tx * 4;
+  const float4 gm = *reinterpret_cast<const float4*>(gamma + c);
+  const float4 bt = *reinterpret_cast<const float4*>(beta + c);
+  float sc[4], sh[4];
+  {
+    const float gmv[4] = {gm.x, gm.y, gm.z, gm.w}, btv[4] = {bt.x, bt.y, bt.z, bt.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int g = (c + j) / cpg;
+      sc[j] = s_rstd[g] * gmv[j];
+      sh[j] = btv[j] - s_mean[g] * sc[j];
+    }
+  }
+  const bool from1 = c < C1;
+  const float* src = from1 ? x1 + c : x2 + (c - C1);
+  const int ld = from1 ? C1 : C2;
+  const int64_t plane = B * (int64_t)HW * C;
+  const int r_begin = blockIdx.x * rows_per_chunk;
+  const int r_end = min(HW, r_begin + rows_per_chunk);
+#pragma unroll 4
+  for (int r = r_begin + ty; r < r_end; r += rpb) {
+    const int64_t row = b * HW + r;
+    const float4 v = *reinterpret_cast<const float4*>(src + row * ld);
+    float o[4] = {v.x * sc[0] + sh[0], v.y * sc[1] + sh[1], v.z * sc[2] + sh[2], v.w * sc[3] + sh[3]};
+    if (silu) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = silu_f(o[j]);
+    }
+    store_split4(out, out + plane, row * C + c, make_float4(o[0], o[1], o[2], o[3]));
+  }
+}
+
+// partial sums -> [B,G,2] (mean, rstd) for consumers that want final statistics (output head)
+__global__ void groupnorm_finalize_kernel(const float* __restrict__ gsum1, int C1, const float* __restrict__ gsum2,
+                                          int C2, float* __restrict__ stats, int64_t B, int HW, int G, float eps) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= B * G) return;
+  const int64_t b = i / G;
+  const int g = (int)(i % G);
+  const int cpg = (C1 + C2) / G;
+  float s = 0.f, ss = 0.f;
+  for (int kb = g * cpg / 4; kb < (g + 1) * cpg / 4; ++kb) {
+    const float* p = (kb * 4 < C1) ? gsum1 + (b * (C1 >> 2) + kb) * 2 : gsum2 + (b * (C2 >> 2) + kb - (C1 >> 2)) * 2;
+    s += p[0];
+    ss += p[1];
+  }
+  const float inv_n = 1.f / ((float)HW * cpg);
+  const float mean = s * inv_n;
+  stats[i * 2] = mean;
+  stats[i * 2 + 1] = rsqrtf(fmaxf(ss * inv_n - mean * mean, 0.f) + eps);
+}
+
+// GEGLU weight layout: output row r' (chunk j = r'/32) <- a-row 16j + r'%32 (r'%32 < 16) or g-row F + 16j + r'%32 - 16
+__global__ void pack_weight_geglu_kernel(const float* __restrict__ w, __half* __restrict__ out, int64_t F, int64_t K) {
+  const int64_t k4 = K / 4, total = 2 * F * k4, plane = 2 * F * K;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / k4, j = i % k4;
+    const int64_t chunk = r / 32, within = r % 32;
+    const int64_t srow = within < 16 ? chunk * 16 + within : F + chunk * 16 + within - 16;
+    const float4 v = reinterpret_cast<const float4*>(w + srow * K)[j];
+    store_split4(out, out + plane, r * K + j * 4, v);
+  }
+}
+__global__ void permute_geglu_bias_kernel(const float* __restrict__ bsrc, float* __restrict__ out, int64_t F) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < 2 * F; r += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t chunk = r / 32, within = r % 32;
+    out[r] = bsrc[within < 16 ? chunk * 16 + within : F + chunk * 16 + within - 16];
   }
 }
 
@@ -570,5 +657,56 @@ extern "C" int sdb_lincomb(float* out, const float* x, const float* m0, const fl
   SDB_REQUIRE(out && x && m0 && n > 0, "sdb_lincomb: bad args");
   lincomb_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(out, x, m0, m1, a, b, c, n);
   SDB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sdb_groupnorm_apply_pack_fused(const float* x1, int64_t C1, const float* gsum1, const float* x2,
+                                              int64_t C2, const float* gsum2, const float* stats, const float* gamma,
+                                              const float* beta, void* out, int64_t B, int64_t HW, int G, float eps,
+                                              int silu, void* stream) {
+  SDB_REQUIRE(x1 && gamma && beta && out && B > 0 && HW > 0, "sdb_groupnorm_apply_pack_fused: null argument");
+  SDB_REQUIRE(stats || (gsum1 && (C2 == 0 || gsum2)), "sdb_groupnorm_apply_pack_fused: need stats or partial sums");
+  SDB_REQUIRE(C2 == 0 || x2, "sdb_groupnorm_apply_pack_fused: x2 missing");
+  const int64_t C = C1 + C2;
+  SDB_REQUIRE(G >= 1 && G <= 64 && C % G == 0 && C1 % 4 == 0 && C2 % 4 == 0 && C <= 1024 && B <= 65535,
+              "sdb_groupnorm_apply_pack_fused: unsupported channels C1=%lld C2=%lld G=%d", (long long)C1, (long long)C2, G);
+  SDB_REQUIRE(stats || (C / G) % 4 == 0, "sdb_groupnorm_apply_pack_fused: partial sums need (C/G) %% 4 == 0");
+  const int c4n = (int)(C / 4);
+  const int rpb = 256 / c4n > 0 ? 256 / c4n : 1;
+  int threads = c4n * rpb;
+  if (threads < 64) threads = 64;       // the first G threads also derive the statistics (G <= 64)
+  // note: threads % c4n may be != 0 only in the clamp case; extra threads then map to ty >= rpb rows, still valid rows
+  int64_t chunks = cdiv((int64_t)num_sms() * 6, B);
+  if (chunks > cdiv(HW, rpb)) chunks = cdiv(HW, rpb);
+  if (chunks < 1) chunks = 1;
+  const int rows_per_chunk = (int)cdiv(HW, chunks);
+  chunks = cdiv(HW, rows_per_chunk);
+  dim3 grid((unsigned)chunks, (unsigned)B);
+  groupnorm_apply_pack_fused_kernel<<<grid, threads, 0, as_stream(stream)>>>(
+      x1, (int)C1, gsum1, x2, (int)C2, gsum2, stats, gamma, beta, (__half*)out, B, (int)HW, G, eps, silu, rows_per_chunk);
+  SDB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sdb_groupnorm_finalize(const float* gsum1, int64_t C1, const float* gsum2, int64_t C2, float* stats,
+                                      int64_t B, int64_t HW, int G, float eps, void* stream) {
+  SDB_REQUIRE(gsum1 && stats && B > 0 && (C2 == 0 || gsum2), "sdb_groupnorm_finalize: null argument");
+  SDB_REQUIRE((C1 + C2) % G == 0 && ((C1 + C2) / G) % 4 == 0 && C1 % 4 == 0, "sdb_groupnorm_finalize: bad channels");
+  groupnorm_finalize_kernel<<<(unsigned)cdiv(B * G, 128), 128, 0, as_stream(stream)>>>(gsum1, (int)C1, gsum2, (int)C2,
+                                                                                      stats, B, (int)HW, G, eps);
+  SDB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sdb_pack_weight_geglu(const float* w, const float* bias, void* out, float* bias_out, int64_t F, int64_t K,
+                                     void* stream) {
+  SDB_REQUIRE(w && out && F > 0 && F % 16 == 0 && K > 0 && K % 4 == 0, "sdb_pack_weight_geglu: bad args F=%lld K=%lld",
+              (long long)F, (long long)K);
+  pack_weight_geglu_kernel<<<grid_for(2 * F * K / 4, 256), 256, 0, as_stream(stream)>>>(w, (__half*)out, F, K);
+  SDB_LAUNCH_CHECK();
+  if (bias && bias_out) {
+    permute_geglu_bias_kernel<<<grid_for(2 * F, 256), 256, 0, as_stream(stream)>>>(bias, bias_out, F);
+    SDB_LAUNCH_CHECK();
+  }
   return 0;
 }

@@ -25,14 +25,16 @@ constexpr int MAX_STAGES = 8;
 constexpr int ACC_STAGES = 2;
 constexpr int ACC_COLS = 256;    // TMEM columns per accumulator stage (max UMMA N)
 constexpr int TMEM_COLS = ACC_STAGES * ACC_COLS;
-constexpr int GEMM_THREADS = 192;
-constexpr int EPI_WARPS = 4;
+constexpr int EPI_WARPS = 8;     // two warps per TMEM lane quarter, interleaved over the 32-column chunks
+constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr uint32_t TILE_A_BYTES = BM * BK * 2;       // 16 KB
-constexpr int EPI_LD = 36;                           // padded row stride (floats) of the epilogue staging tile
 constexpr int SMEM_LIMIT = 227 * 1024;
+// epilogue flavours (template parameter)
+constexpr int EPI_F32 = 0;      // fp32 C (+ optional packed copy), bias / rowvec / residual / relu, split-K, GN partial sums
+constexpr int EPI_GEGLU = 1;    // packed out[:, f] = a * gelu(g), W rows interleaved [16 a | 16 g] per 32-column chunk
 
 struct GemmCtl {
-  float epi[EPI_WARPS][32 * EPI_LD];
+  float epi[EPI_WARPS][32 * 32];   // per-warp staging tile, 16-B chunks XOR-swizzled by (row & 7): conflict-free both ways
   uint64_t full[MAX_STAGES];
   uint64_t empty[MAX_STAGES];
   uint64_t acc_full[ACC_STAGES];
@@ -45,7 +47,10 @@ struct GemmArgs {
   const float* bias;
   const float* rowvec;
   const float* residual;
-  long long ldc, ldv, ldr;
+  __half* out_packed;   // optional packed copy of the result (GEGLU: the only output), planes out_plane halves apart
+  float* gsum;          // optional GroupNorm partial sums [M / rows_per_group][N / 4][2] (sum, sum of squares)
+  long long ldc, ldv, ldr, out_plane;
+  int out_act;          // activation applied to the packed copy: 0 none, 1 SiLU, 2 ReLU
   int M, N, K;
   int mode;
   int tile_rows;        // valid rows per CTA M tile (<= 128)
@@ -69,7 +74,7 @@ struct GemmArgs {
 // per tile, tcgen05 cta_group::2 (UMMA 256 x bn): each CTA stages its own 128 rows of A and HALF of the W tile,
 // which halves the shared-memory fill and read traffic per flop -- with three MMA passes per product the single-CTA
 // form is shared-memory-bandwidth bound well below the tensor peak.
-template <int CG>
+template <int CG, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
             const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -223,9 +228,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
     }
   } else {
     // ===================== epilogue warps (both CTAs: each drains its own 128 TMEM lanes) =====================
-    const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    float* stg = ctl.epi[q];
-    const int c4 = (lane & 7) * 4, rsub = lane >> 3;
+    const int ew = warp - 2;                // 0..7
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access (hardware rule: warp id % 4)
+    const int par = ew >> 2;                // parity of the 32-column chunks this warp handles
+    float* stg = ctl.epi[ew];
+    const int c4i = lane & 7, rsub = lane >> 3;
+    const unsigned n4 = (unsigned)g.N >> 2;
     int it = 0;
     for (int item = group; item < num_items; item += ngroups, ++it) {
       const int tile = item / g.splits, split = item - tile * g.splits;
@@ -233,13 +241,38 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
       const bool first = split == 0;       // the split that also adds bias / rowvec / residual
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      mbar_wait(&ctl.acc_full[as], aphase);
-      tc_fence_after();
       const long long row0l = (long long)tm * g.tile_rows + q * 32;   // first output row of this warp
       const int rows_valid = (int)min((long long)min(g.tile_rows - q * 32, 32), (long long)g.M - row0l);
       const int row0 = (int)min(row0l, (long long)g.M);
       const int ncols = min(g.bn, g.N - tn * g.bn);
-      for (int cb = 0; cb < ncols; cb += 32) {
+      const int nch = (ncols + 31) >> 5;
+
+      // global loads feeding chunk j (residual, timestep row vector): issued one chunk ahead of their use
+      auto prefetch = [&](int j, float4 (&dst)[8]) {
+        const int n = tn * g.bn + j * 32 + c4i * 4;
+        const bool col_ok = (j * 32 + c4i * 4 < ncols) && first && EPI == EPI_F32 && g.vec_ok;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = i * 4 + rsub;
+          dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (col_ok && rr < rows_valid) {
+            const unsigned m = (unsigned)(row0 + rr);
+            if (g.residual) dst[i] = *reinterpret_cast<const float4*>(g.residual + (long long)m * g.ldr + n);
+            if (g.rowvec) {
+              const float4 t =
+                  *reinterpret_cast<const float4*>(g.rowvec + (long long)(m / g.rows_per_group) * g.ldv + n);
+              dst[i].x += t.x; dst[i].y += t.y; dst[i].z += t.z; dst[i].w += t.w;
+            }
+          }
+        }
+      };
+      float4 pre[8];
+      if (par < nch) prefetch(par, pre);
+      mbar_wait(&ctl.acc_full[as], aphase);
+      tc_fence_after();
+
+      for (int j = par; j < nch; j += 2) {
+        const int cb = j * 32;
         uint32_t r[32];
         const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * ACC_COLS + cb);
         if (g.bn - cb >= 32) {
@@ -248,52 +281,98 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
           uint32_t r16[16];
           tmem_ld_32x16(taddr, r16);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) { r[j] = r16[j]; r[j + 16] = 0; }
+          for (int k = 0; k < 16; ++k) { r[k] = r16[k]; r[k + 16] = 0; }
         }
+        float4 cur[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cur[i] = pre[i];
+        if (j + 2 < nch) prefetch(j + 2, pre);
         tmem_ld_wait();
         if (rows_valid <= 0) continue;       // warp-uniform
-        // thread `lane` holds row (q*32+lane), columns cb..cb+31 -> stage so that 8 lanes cover one 128-B row segment
+        // thread `lane` holds row (q*32+lane), columns cb..cb+31 -> stage (swizzled) so that 8 lanes cover one
+        // 128-B row segment on the way out
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<float4*>(stg + lane * EPI_LD + 4 * j) =
-              make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
-                          __uint_as_float(r[4 * j + 3]));
+        for (int k = 0; k < 8; ++k)
+          *reinterpret_cast<float4*>(stg + lane * 32 + ((k ^ (lane & 7)) << 2)) =
+              make_float4(__uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1]), __uint_as_float(r[4 * k + 2]),
+                          __uint_as_float(r[4 * k + 3]));
         __syncwarp();
-        const int n = tn * g.bn + cb + c4;
-        if (g.vec_ok) {
-          const bool col_ok = (cb + c4 < ncols);
+        if (EPI == EPI_GEGLU) {
+          // chunk = [16 a columns | 16 g columns]; lane <-> (row = i*8 + lane/4, 4 output columns cc)
+          const int cc = lane & 3, rq = lane >> 2;
+          const int na = tn * g.bn + cb + cc * 4;                 // column of a in the interleaved N space
+          const int fo = (tn * g.bn + cb) / 2 + cc * 4;           // output column
+          const int F = g.N >> 1;
+          float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bg = ba;
+          if (g.bias) {
+            ba = *reinterpret_cast<const float4*>(g.bias + na);
+            bg = *reinterpret_cast<const float4*>(g.bias + na + 16);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rr = i * 8 + rq;
+            if (rr < rows_valid && cb + cc * 4 < ncols) {
+              const float4 a = *reinterpret_cast<const float4*>(stg + rr * 32 + ((cc ^ (rr & 7)) << 2));
+              const float4 gg = *reinterpret_cast<const float4*>(stg + rr * 32 + (((cc + 4) ^ (rr & 7)) << 2));
+              float4 o;
+              o.x = (a.x + ba.x) * gelu_erf_f(gg.x + bg.x);
+              o.y = (a.y + ba.y) * gelu_erf_f(gg.y + bg.y);
+              o.z = (a.z + ba.z) * gelu_erf_f(gg.z + bg.z);
+              o.w = (a.w + ba.w) * gelu_erf_f(gg.w + bg.w);
+              store_split4(g.out_packed, g.out_packed + g.out_plane, (long long)(row0 + rr) * F + fo, o);
+            }
+          }
+        } else if (g.vec_ok) {
+          const int n = tn * g.bn + cb + c4i * 4;
+          const bool col_ok = (cb + c4i * 4 < ncols);
           float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
           if (col_ok && first && g.bias) bias4 = *reinterpret_cast<const float4*>(g.bias + n);
+          float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;   // GroupNorm partial sums of rows 0..15 / 16..31
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            float4 add[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int rr = (half * 4 + i) * 4 + rsub;
-              add[i] = bias4;
-              if (col_ok && rr < rows_valid && first) {
-                const unsigned m = (unsigned)(row0 + rr);
-                if (g.residual) {
-                  const float4 t = *reinterpret_cast<const float4*>(g.residual + (long long)m * g.ldr + n);
-                  add[i].x += t.x; add[i].y += t.y; add[i].z += t.z; add[i].w += t.w;
-                }
-                if (g.rowvec) {
-                  const float4 t =
-                      *reinterpret_cast<const float4*>(g.rowvec + (long long)(m / g.rows_per_group) * g.ldv + n);
-                  add[i].x += t.x; add[i].y += t.y; add[i].z += t.z; add[i].w += t.w;
-                }
-              }
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int rr = (half * 4 + i) * 4 + rsub;
-              if (col_ok && rr < rows_valid) {
-                float4 v = *reinterpret_cast<const float4*>(stg + rr * EPI_LD + c4);
-                v.x += add[i].x; v.y += add[i].y; v.z += add[i].z; v.w += add[i].w;
-                if (g.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-                float* dst = g.c + (long long)(row0 + rr) * g.ldc + n;
+          for (int i = 0; i < 8; ++i) {
+            const int rr = i * 4 + rsub;
+            if (col_ok && rr < rows_valid) {
+              float4 v = *reinterpret_cast<const float4*>(stg + rr * 32 + ((c4i ^ (rr & 7)) << 2));
+              v.x += cur[i].x + bias4.x; v.y += cur[i].y + bias4.y; v.z += cur[i].z + bias4.z; v.w += cur[i].w + bias4.w;
+              if (g.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+              const long long m = row0 + rr;
+              if (g.c) {
+                float* dst = g.c + m * g.ldc + n;
                 if (g.splits > 1) red_add_v4(dst, v);
                 else *reinterpret_cast<float4*>(dst) = v;
+              }
+              if (g.gsum) {
+                const float s = (v.x + v.y) + (v.z + v.w);
+                const float qq = (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+                if (i < 4) { s0 += s; q0 += qq; } else { s1 += s; q1 += qq; }
+              }
+              if (g.out_packed) {
+                if (g.out_act == 1) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
+                else if (g.out_act == 2) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                store_split4(g.out_packed, g.out_packed + g.out_plane, m * g.N + n, v);
+              }
+            }
+          }
+          if (g.gsum) {
+            // rows rr = i*4 + rsub: sum over the 4 row sub-lanes (lanes l, l+8, l+16, l+24 share the columns)
+            s0 += __shfl_xor_sync(0xffffffffu, s0, 8);  q0 += __shfl_xor_sync(0xffffffffu, q0, 8);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 8);  q1 += __shfl_xor_sync(0xffffffffu, q1, 8);
+            s0 += __shfl_xor_sync(0xffffffffu, s0, 16); q0 += __shfl_xor_sync(0xffffffffu, q0, 16);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 16); q1 += __shfl_xor_sync(0xffffffffu, q1, 16);
+            if (rsub == 0 && col_ok) {
+              const unsigned b0 = (unsigned)row0 / g.rows_per_group;
+              const unsigned b1 = (unsigned)(row0 + 16) / g.rows_per_group;
+              if (b1 == b0 || rows_valid <= 16) {
+                float* p = g.gsum + ((long long)b0 * n4 + (n >> 2)) * 2;
+                atomicAdd(p, s0 + s1);
+                atomicAdd(p + 1, q0 + q1);
+              } else {
+                float* p = g.gsum + ((long long)b0 * n4 + (n >> 2)) * 2;
+                atomicAdd(p, s0);
+                atomicAdd(p + 1, q0);
+                p = g.gsum + ((long long)b1 * n4 + (n >> 2)) * 2;
+                atomicAdd(p, s1);
+                atomicAdd(p + 1, q1);
               }
             }
           }
@@ -305,7 +384,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
           for (int rr = 0; rr < rows_valid; ++rr) {
             if (!col_ok) break;
             const unsigned m = (unsigned)(row0 + rr);
-            float v = stg[rr * EPI_LD + lane] + bias;
+            float v = stg[rr * 32 + ((((lane >> 2) ^ (rr & 7)) << 2) | (lane & 3))] + bias;
             if (first && g.rowvec) v += g.rowvec[(long long)(m / g.rows_per_group) * g.ldv + nn];
             if (first && g.residual) v += g.residual[(long long)m * g.ldr + nn];
             if (g.relu) v = fmaxf(v, 0.f);
@@ -397,12 +476,12 @@ static int env_int(const char* name, int dflt) {
   return (v && *v) ? atoi(v) : dflt;
 }
 
-template <int CG>
+template <int CG, int EPI>
 static int launch_gemm(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const CUtensorMap& mb_hi,
                        const CUtensorMap& mb_lo, const GemmArgs& g, int groups, size_t smem, cudaStream_t st) {
   static size_t attr = 0;
   if (smem > attr) {
-    SDB_CHECK(cudaFuncSetAttribute(gemm_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SDB_CHECK(cudaFuncSetAttribute(gemm_kernel<CG, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
   cudaLaunchConfig_t cfg{};
@@ -417,7 +496,7 @@ static int launch_gemm(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  SDB_CHECK(cudaLaunchKernelEx(&cfg, gemm_kernel<CG>, ma_hi, ma_lo, mb_hi, mb_lo, g));
+  SDB_CHECK(cudaLaunchKernelEx(&cfg, gemm_kernel<CG, EPI>, ma_hi, ma_lo, mb_hi, mb_lo, g));
   SDB_LAUNCH_CHECK();
   return 0;
 }
@@ -427,7 +506,7 @@ static int launch_gemm(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const
 using namespace sdb;
 
 extern "C" int sdb_gemm(const SdbGemm* p, void* stream) {
-  SDB_REQUIRE(p && p->a && p->w && p->c, "sdb_gemm: null operand");
+  SDB_REQUIRE(p && p->a && p->w && (p->c || p->out_packed), "sdb_gemm: null operand");
   SDB_REQUIRE(p->M > 0 && p->N > 0 && p->K > 0, "sdb_gemm: empty problem M=%d N=%d K=%d", p->M, p->N, p->K);
   SDB_REQUIRE(p->passes == 1 || p->passes == 3, "sdb_gemm: passes must be 1 or 3");
   SDB_REQUIRE(p->K % 8 == 0, "sdb_gemm: K=%d must be a multiple of 8 (16-byte TMA rows)", p->K);
@@ -436,13 +515,31 @@ extern "C" int sdb_gemm(const SdbGemm* p, void* stream) {
   SDB_REQUIRE(!p->rowvec || p->rows_per_group > 0, "sdb_gemm: rowvec needs rows_per_group");
   GemmArgs g{};
   g.c = p->c; g.bias = p->bias; g.rowvec = p->rowvec; g.residual = p->residual;
+  g.out_packed = reinterpret_cast<__half*>(p->out_packed); g.gsum = p->gsum;
+  g.out_plane = p->out_plane_stride; g.out_act = p->out_act;
   g.ldc = p->ldc; g.ldv = p->ldv; g.ldr = p->ldr;
   g.M = p->M; g.N = p->N; g.K = p->K; g.mode = p->mode; g.passes = p->passes; g.relu = p->relu;
   g.rows_per_group = p->rows_per_group > 0 ? (unsigned)p->rows_per_group : 1u;
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-  g.vec_ok = (p->N % 4 == 0) && (p->ldc % 4 == 0) && al16(p->c) && (!p->bias || al16(p->bias)) &&
+  g.vec_ok = (p->N % 4 == 0) && (!p->c || (p->ldc % 4 == 0 && al16(p->c))) && (!p->bias || al16(p->bias)) &&
              (!p->residual || (al16(p->residual) && p->ldr % 4 == 0)) &&
              (!p->rowvec || (al16(p->rowvec) && p->ldv % 4 == 0));
+
+  const bool geglu = p->geglu != 0;
+  if (geglu) {
+    SDB_REQUIRE(p->out_packed && !p->c && !p->residual && !p->rowvec && !p->relu && !p->gsum,
+                "sdb_gemm: GEGLU epilogue writes only the packed output (no c / residual / rowvec / relu / gsum)");
+    SDB_REQUIRE(p->N % 32 == 0 && (!p->bias || al16(p->bias)), "sdb_gemm: GEGLU needs N %% 32 == 0");
+  }
+  if (p->out_packed) {
+    SDB_REQUIRE(al16(p->out_packed) && p->out_plane_stride % 8 == 0 && p->N % 4 == 0 && g.vec_ok,
+                "sdb_gemm: packed output needs 16-byte aligned planes and vectorisable operands");
+    SDB_REQUIRE(p->out_act >= 0 && p->out_act <= 2, "sdb_gemm: bad out_act %d", p->out_act);
+  }
+  if (p->gsum) {
+    SDB_REQUIRE(g.vec_ok && p->rows_per_group > 0 && p->rows_per_group % 16 == 0,
+                "sdb_gemm: gsum needs vectorisable operands and rows_per_group %% 16 == 0 (got %d)", p->rows_per_group);
+  }
 
   // ---- A-side tiling (per CTA: up to 128 rows)
   int n_tiles_m1;   // M tiles of ONE CTA
@@ -477,7 +574,7 @@ extern "C" int sdb_gemm(const SdbGemm* p, void* stream) {
   int cg = (n_tiles_m1 >= 2) ? 2 : 1;
   const int force_cg = env_int("SDB_GEMM_CG", 0);
   if (force_cg == 1 || force_cg == 2) cg = force_cg;
-  g.bn = (cg == 2) ? pick_bn(p->N, 256, 32) : pick_bn(p->N, 128, 16);
+  g.bn = (cg == 2) ? pick_bn(p->N, 256, 32) : pick_bn(p->N, 128, geglu ? 32 : 16);
   g.bnl = g.bn / cg;
   g.n_tiles_m = (int)cdiv(n_tiles_m1, cg);
   g.n_tiles_n = (int)cdiv(p->N, g.bn);
@@ -485,14 +582,15 @@ extern "C" int sdb_gemm(const SdbGemm* p, void* stream) {
   const int units = sms / cg;
   const long long tiles = (long long)g.n_tiles_m * g.n_tiles_n;
   g.splits = 1;
-  if (!p->relu && tiles * 4 < (long long)units * 3 && ksteps >= 8) {
+  const bool can_split = !p->relu && !p->out_packed && !p->gsum;   // those epilogues need the complete sum
+  if (can_split && tiles * 4 < (long long)units * 3 && ksteps >= 8) {
     long long s = units / tiles;
     if (s > ksteps / 4) s = ksteps / 4;
     if (s > 32) s = 32;
     if (s >= 2) g.splits = (int)s;
   }
   const int force_split = env_int("SDB_GEMM_SPLITK", 0);
-  if (force_split >= 1 && !p->relu) g.splits = force_split > ksteps ? ksteps : force_split;
+  if (force_split >= 1 && can_split) g.splits = force_split > ksteps ? ksteps : force_split;
   g.stage_bytes = 2 * TILE_A_BYTES + 2 * (uint32_t)g.bnl * BK * 2;
   const int avail = SMEM_LIMIT - 1024 - (int)sizeof(GemmCtl);
   g.stages = avail / (int)g.stage_bytes;
@@ -535,6 +633,9 @@ extern "C" int sdb_gemm(const SdbGemm* p, void* stream) {
   const size_t smem = (size_t)g.stages * g.stage_bytes + sizeof(GemmCtl) + 1024;
   const long long items = tiles * g.splits;
   const int groups = (int)(items < units ? items : units);
-  return cg == 2 ? launch_gemm<2>(ma_hi, ma_lo, mb_hi, mb_lo, g, groups, smem, st)
-                 : launch_gemm<1>(ma_hi, ma_lo, mb_hi, mb_lo, g, groups, smem, st);
+  if (geglu)
+    return cg == 2 ? launch_gemm<2, EPI_GEGLU>(ma_hi, ma_lo, mb_hi, mb_lo, g, groups, smem, st)
+                   : launch_gemm<1, EPI_GEGLU>(ma_hi, ma_lo, mb_hi, mb_lo, g, groups, smem, st);
+  return cg == 2 ? launch_gemm<2, EPI_F32>(ma_hi, ma_lo, mb_hi, mb_lo, g, groups, smem, st)
+                 : launch_gemm<1, EPI_F32>(ma_hi, ma_lo, mb_hi, mb_lo, g, groups, smem, st);
 }

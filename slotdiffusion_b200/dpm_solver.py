@@ -168,6 +168,7 @@ class DPMSolverSampler:
         ex, net = self.ex, self.unet
         B, Cin, H, W = x.shape
         emb_all = emb_row   # single row shared by the batch; the epilogue indexes row 0 (ldv = 0)
+        ex.begin(B, x.device)
         conv_in = net.input_blocks[0][0]
         from .unet_exec import Act
         h = Act(ops.conv3_in(x, conv_in.weight, conv_in.bias), H, W, net.model_channels)
@@ -179,9 +180,7 @@ class DPMSolverSampler:
         h = ex.run_block(net.middle_block, h, None, bcast, ctx_kv, B, S)
         for block in net.output_blocks:
             h = ex.run_block(block, h, hs.pop(), bcast, ctx_kv, B, S)
-        gn, conv = net.out[0], net.out[2]
-        stats = ops.groupnorm_stats(h.t, None, B, h.H * h.W, gn.num_groups, gn.eps)
-        return ops.conv3_out(h.t, stats, gn.weight, gn.bias, conv.weight, conv.bias, B, h.H, h.W, gn.num_groups)
+        return ex.head(h, B)
 
     @torch.no_grad()
     def sample(self, x_T, context):

@@ -84,6 +84,10 @@ class WeightCache:
             return pack_weight(w.contiguous())
         return self._get(key, ws, make)
 
+    def geglu(self, key, w, b):
+        """(Packed interleaved weight, permuted bias) of a GEGLU projection."""
+        return self._get(key, (w, b), lambda: pack_weight_geglu(w.detach().contiguous(), b.detach().contiguous()))
+
     def conv3(self, key, w):
         return self._get(key, (w,), lambda: pack_weight_conv3(w.detach().contiguous()))
 
@@ -184,10 +188,17 @@ def timestep_embedding_pack(t, dim):
 
 
 # ---------------------------------------------------------------- GEMM
+_ACTS = {None: 0, 'none': 0, 'silu': 1, 'relu': 2}
+
+
 def gemm(a, w, bias=None, rowvec=None, rows_per_group=0, residual=None, relu=False, conv=None, passes=None,
-         out=None):
+         out=None, pack_out=None, keep_c=True, gsum=None, geglu=False):
     """C = A W^T (+bias)(+rowvec[row // rows_per_group])(+residual); A, W Packed.
-    conv: None (plain) or (mode, B, H, W, C) with H, W the OUTPUT size (see sdb200.h)."""
+    conv: None (plain) or (mode, B, H, W, C) with H, W the OUTPUT size (see sdb200.h).
+    pack_out: None, or 'none' / 'silu' / 'relu' -- the epilogue ALSO emits act(C) as a Packed operand for the next
+              GEMM; returns (C or None, Packed); keep_c=False drops the fp32 copy.
+    gsum:     fp32 [M // rows_per_group, N // 4, 2] zero-initialised buffer that receives GroupNorm partial sums of C.
+    geglu:    W/bias packed by pack_weight_geglu; returns Packed [M, N/2] = a * gelu(g)."""
     N, K = w.rows, w.K
     if conv is None:
         M, mode, geo = a.rows, SDB_A_PLAIN, (0, 0, 0, 0)
@@ -196,15 +207,23 @@ def gemm(a, w, bias=None, rowvec=None, rows_per_group=0, residual=None, relu=Fal
         mode, B, H, W, C = conv
         M, geo = B * H * W, (B, H, W, C)
         assert K == 9 * C and a.K == C
-    if out is None:
-        out = torch.empty(M, N, dtype=torch.float32, device=a.t.device)
+    dev = a.t.device
+    packed = None
+    if geglu:
+        packed = Packed.empty(M, N // 2, dev)
+        keep_c = False
+    elif pack_out is not None:
+        packed = Packed.empty(M, N, dev)
+    if keep_c and out is None:
+        out = torch.empty(M, N, dtype=torch.float32, device=dev)
     g = SdbGemm()
-    g.a, g.w, g.c = a.t.data_ptr(), w.t.data_ptr(), out.data_ptr()
+    g.a, g.w = a.t.data_ptr(), w.t.data_ptr()
+    g.c = out.data_ptr() if keep_c else None
     g.bias = bias.data_ptr() if bias is not None else None
     g.rowvec = rowvec.data_ptr() if rowvec is not None else None
     g.residual = residual.data_ptr() if residual is not None else None
     g.a_plane_stride = a.rows * a.K
-    g.ldc = out.stride(0)
+    g.ldc = out.stride(0) if keep_c else N
     g.ldv = rowvec.stride(0) if rowvec is not None else 0
     g.ldr = residual.stride(0) if residual is not None else 0
     g.M, g.N, g.K, g.mode = M, N, K, mode
@@ -212,8 +231,47 @@ def gemm(a, w, bias=None, rowvec=None, rows_per_group=0, residual=None, relu=Fal
     g.rows_per_group = rows_per_group
     g.passes = passes or _PASSES
     g.relu = int(relu)
+    if packed is not None:
+        g.out_packed = packed.t.data_ptr()
+        g.out_plane_stride = packed.rows * packed.K
+        g.out_act = _ACTS[pack_out]
+    g.gsum = gsum.data_ptr() if gsum is not None else None
+    g.geglu = int(geglu)
     check(lib().sdb_gemm(ctypes.byref(g), _stream()), 'sdb_gemm')
+    if geglu:
+        return packed
+    if pack_out is not None:
+        return (out if keep_c else None), packed
     return out
+
+
+def pack_weight_geglu(w, bias):
+    """GEGLU.proj weight [2F, K] (+bias [2F]) -> (Packed interleaved [16 a | 16 g], permuted bias)."""
+    _f32(w, 'weight')
+    F2, K = w.shape
+    out = Packed.empty(F2, K, w.device)
+    bout = torch.empty_like(bias) if bias is not None else None
+    check(lib().sdb_pack_weight_geglu(_p(w), _p(bias), _p(out.t), _p(bout), F2 // 2, K, _stream()),
+          'sdb_pack_weight_geglu')
+    return out, bout
+
+
+def groupnorm_pack_fused(x1, x2, gamma, beta, B, HW, G=32, eps=1e-5, silu=True, gsum1=None, gsum2=None, stats=None):
+    """GroupNorm(+SiLU)+pack with statistics from the producers' partial sums (gsum*) or from `stats` [B,G,2]."""
+    C1 = x1.shape[-1]
+    C2 = x2.shape[-1] if x2 is not None else 0
+    out = Packed.empty(B * HW, C1 + C2, x1.device)
+    check(lib().sdb_groupnorm_apply_pack_fused(_p(x1), C1, _p(gsum1), _p(x2), C2, _p(gsum2), _p(stats), _p(gamma),
+                                               _p(beta), _p(out.t), B, HW, G, eps, int(silu), _stream()),
+          'sdb_groupnorm_apply_pack_fused')
+    return out
+
+
+def groupnorm_finalize(gsum1, gsum2, C1, C2, B, HW, G, eps):
+    stats = torch.empty(B, G, 2, dtype=torch.float32, device=gsum1.device)
+    check(lib().sdb_groupnorm_finalize(_p(gsum1), C1, _p(gsum2), C2, _p(stats), B, HW, G, eps, _stream()),
+          'sdb_groupnorm_finalize')
+    return stats
 
 
 # ---------------------------------------------------------------- attention / convs / slot attention / sampler

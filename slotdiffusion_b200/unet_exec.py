@@ -15,12 +15,15 @@ from . import ops
 from .ops import SDB_A_CONV3, SDB_A_CONV3S2, SDB_PACK_PHASE2, SDB_PACK_PLAIN, SDB_PACK_UP2
 
 
-class Act:
-    """NHWC activation: rows [B*H*W, C]."""
-    __slots__ = ('t', 'H', 'W', 'C')
+GS_MIN_ROWS = 4096     # below this the producing GEMMs want split-K, which excludes the fused GroupNorm sums
 
-    def __init__(self, t, H, W, C):
-        self.t, self.H, self.W, self.C = t, H, W, C
+
+class Act:
+    """NHWC activation: rows [B*H*W, C]; gs = GroupNorm partial sums [B, C/4, 2] accumulated by its producer."""
+    __slots__ = ('t', 'H', 'W', 'C', 'gs')
+
+    def __init__(self, t, H, W, C, gs=None):
+        self.t, self.H, self.W, self.C, self.gs = t, H, W, C, gs
 
 
 class UNetExecutor:
@@ -44,6 +47,38 @@ class UNetExecutor:
             self.kv_off[id(m)] = off
             off += 2 * m.attn2.to_k.weight.shape[0]
         self.kv_total = off
+        self._gs_arena = None
+        self._gs_off = 0
+
+    # ------------------------------------------------------------------ GroupNorm partial-sum arena
+    def begin(self, B, device):
+        """Start of a forward: one memset clears every partial-sum buffer the epilogues will accumulate into."""
+        need = B * 2 * 16384          # floats: sum over producing sites of C/4 * 2 (~11k) per sample
+        if self._gs_arena is None or self._gs_arena.numel() < need or self._gs_arena.device != device:
+            self._gs_arena = torch.zeros(need, dtype=torch.float32, device=device)
+        else:
+            self._gs_arena.zero_()
+        self._gs_off = 0
+
+    def _gs(self, B, HW, C):
+        """Partial-sum buffer for an activation produced by a GEMM epilogue, or None when not applicable."""
+        if B * HW < GS_MIN_ROWS or HW % 16 or C % 128:     # (C / 32 groups) % 4 == 0
+            return None
+        n = B * (C // 4) * 2
+        if self._gs_arena is None or self._gs_off + n > self._gs_arena.numel():
+            return None
+        v = self._gs_arena[self._gs_off:self._gs_off + n]
+        self._gs_off += n
+        return v
+
+    def group_norm(self, x1, x2, gn, B, HW, silu):
+        """GroupNorm(+SiLU) -> packed operand; statistics from the producers' epilogue sums when available."""
+        x2t = x2.t if x2 is not None else None
+        if x1.gs is not None and (x2 is None or x2.gs is not None):
+            return ops.groupnorm_pack_fused(x1.t, x2t, gn.weight, gn.bias, B, HW, gn.num_groups, gn.eps, silu,
+                                            gsum1=x1.gs, gsum2=x2.gs if x2 is not None else None)
+        stats = ops.groupnorm_stats(x1.t, x2t, B, HW, gn.num_groups, gn.eps)
+        return ops.groupnorm_pack_fused(x1.t, x2t, gn.weight, gn.bias, B, HW, gn.num_groups, gn.eps, silu, stats=stats)
 
     # ------------------------------------------------------------------ pieces
     def time_embedding(self, t, B):
@@ -51,13 +86,14 @@ class UNetExecutor:
         if t.numel() == 1 and B > 1:
             t = t.reshape(1).expand(B)
         tp = ops.timestep_embedding_pack(t, net.model_channels)                          # unet.py:560-561
-        e1 = ops.gemm(tp, wc.linear('te0', net.time_embed[0].weight), bias=net.time_embed[0].bias)
-        emb = ops.gemm(ops.pack_rows(e1, act=1), wc.linear('te2', net.time_embed[2].weight),
-                       bias=net.time_embed[2].bias)                                      # unet.py:562
+        _, e1 = ops.gemm(tp, wc.linear('te0', net.time_embed[0].weight), bias=net.time_embed[0].bias,
+                         pack_out='silu', keep_c=False)
+        _, emb = ops.gemm(e1, wc.linear('te2', net.time_embed[2].weight), bias=net.time_embed[2].bias,
+                          pack_out='silu', keep_c=False)                                 # unet.py:562
         # every ResBlock's Linear(SiLU(emb)) in one GEMM                                   unet.py:279
         w = wc.linear('emb_all', *[m.emb_layers[1].weight for m in self.resblocks])
         b = wc.cat('emb_all_b', *[m.emb_layers[1].bias for m in self.resblocks])
-        return ops.gemm(ops.pack_rows(emb, act=1), w, bias=b)                            # [B, emb_total]
+        return ops.gemm(emb, w, bias=b)                                                  # [B, emb_total]
 
     def context_kv(self, context):
         """to_k | to_v of every cross-attention layer applied to the slots: [B*S, kv_total]."""
@@ -76,20 +112,22 @@ class UNetExecutor:
         Cout = m.out_channels
         x2t = x2.t if x2 is not None else None
         gn1, gn2 = m.in_layers[0], m.out_layers[0]
-        p = ops.groupnorm_pack(x1.t, x2t, gn1.weight, gn1.bias, B, HW, gn1.num_groups, gn1.eps, silu=True)
+        p = self.group_norm(x1, x2, gn1, B, HW, silu=True)
         off = self.emb_off[key]
+        gs_h = self._gs(B, HW, Cout)
         h = ops.gemm(p, wc.conv3((key, 'c1'), m.in_layers[2].weight), bias=m.in_layers[2].bias,
-                     rowvec=emb_all[:, off:off + Cout], rows_per_group=HW, conv=(SDB_A_CONV3, B, H, W, Cin))
-        p2 = ops.groupnorm_pack(h, None, gn2.weight, gn2.bias, B, HW, gn2.num_groups, gn2.eps, silu=True)
+                     rowvec=emb_all[:, off:off + Cout], rows_per_group=HW, conv=(SDB_A_CONV3, B, H, W, Cin), gsum=gs_h)
+        p2 = self.group_norm(Act(h, H, W, Cout, gs_h), None, gn2, B, HW, silu=True)
         if isinstance(m.skip_connection, torch.nn.Identity):
             assert x2 is None
             xs = x1.t
         else:
             xp = ops.pack_nhwc(x1.t, x2t, B, H, W, SDB_PACK_PLAIN)
             xs = ops.gemm(xp, wc.linear((key, 'skip'), m.skip_connection.weight), bias=m.skip_connection.bias)
+        gs_o = self._gs(B, HW, Cout)
         out = ops.gemm(p2, wc.conv3((key, 'c2'), m.out_layers[3].weight), bias=m.out_layers[3].bias, residual=xs,
-                       conv=(SDB_A_CONV3, B, H, W, Cout))
-        return Act(out, H, W, Cout)
+                       conv=(SDB_A_CONV3, B, H, W, Cout), gsum=gs_o, rows_per_group=HW)
+        return Act(out, H, W, Cout, gs_o)
 
     def attention(self, a, xn, B, L, kv=None, S=None, residual=None, key=None):
         """attention.py:182-206.  xn: packed LayerNorm output."""
@@ -108,10 +146,10 @@ class UNetExecutor:
         wc, key = self.wc, id(m)
         H, W, C = x.H, x.W, x.C
         L = H * W
-        pn = ops.groupnorm_pack(x.t, None, m.norm.weight, m.norm.bias, B, L, m.norm.num_groups, m.norm.eps,
-                                silu=False)
+        pn = self.group_norm(x, None, m.norm, B, L, silu=False)
         t = ops.gemm(pn, wc.linear((key, 'pin'), m.proj_in.weight), bias=m.proj_in.bias)
-        for blk in m.transformer_blocks:
+        nblk = len(m.transformer_blocks)
+        for i, blk in enumerate(m.transformer_blocks):
             bk = id(blk)
             n1 = ops.layernorm_pack(t, blk.norm1.weight, blk.norm1.bias, blk.norm1.eps)
             t = self.attention(blk.attn1, n1, B, L, residual=t, key=(bk, 'a1'))
@@ -121,24 +159,33 @@ class UNetExecutor:
             t = self.attention(blk.attn2, n2, B, L, kv=kv, S=S, residual=t, key=(bk, 'a2'))
             n3 = ops.layernorm_pack(t, blk.norm3.weight, blk.norm3.bias, blk.norm3.eps)
             proj = blk.ff.net[0].proj
-            u = ops.gemm(n3, wc.linear((bk, 'ff0'), proj.weight), bias=proj.bias)
-            t = ops.gemm(ops.geglu_pack(u), wc.linear((bk, 'ff2'), blk.ff.net[2].weight), bias=blk.ff.net[2].bias,
-                         residual=t)
-        out = ops.gemm(ops.pack_rows(t), wc.linear((key, 'pout'), m.proj_out.weight), bias=m.proj_out.bias,
-                       residual=x.t)
-        return Act(out, H, W, C)
+            wg, bg = wc.geglu((bk, 'ff0'), proj.weight, proj.bias)
+            u = ops.gemm(n3, wg, bias=bg, geglu=True)            # a * gelu(g) straight from the accumulators
+            w2 = wc.linear((bk, 'ff2'), blk.ff.net[2].weight)
+            if i == nblk - 1:   # only proj_out consumes it: emit the packed operand, skip the fp32 copy
+                _, tp = ops.gemm(u, w2, bias=blk.ff.net[2].bias, residual=t, pack_out='none', keep_c=False)
+            else:
+                t = ops.gemm(u, w2, bias=blk.ff.net[2].bias, residual=t)
+        gs_o = self._gs(B, L, C)
+        out = ops.gemm(tp, wc.linear((key, 'pout'), m.proj_out.weight), bias=m.proj_out.bias, residual=x.t, gsum=gs_o,
+                       rows_per_group=L)
+        return Act(out, H, W, C, gs_o)
 
     def downsample(self, m, x, B):
+        Ho, Wo = x.H // 2, x.W // 2
         xp = ops.pack_nhwc(x.t, None, B, x.H, x.W, SDB_PACK_PHASE2)
+        gs = self._gs(B, Ho * Wo, m.out_channels)
         out = ops.gemm(xp, self.wc.conv3((id(m), 'op'), m.op.weight), bias=m.op.bias,
-                       conv=(SDB_A_CONV3S2, B, x.H // 2, x.W // 2, x.C))
-        return Act(out, x.H // 2, x.W // 2, m.out_channels)
+                       conv=(SDB_A_CONV3S2, B, Ho, Wo, x.C), gsum=gs, rows_per_group=Ho * Wo)
+        return Act(out, Ho, Wo, m.out_channels, gs)
 
     def upsample(self, m, x, B):
+        Ho, Wo = 2 * x.H, 2 * x.W
         xp = ops.pack_nhwc(x.t, None, B, x.H, x.W, SDB_PACK_UP2)
+        gs = self._gs(B, Ho * Wo, m.out_channels)
         out = ops.gemm(xp, self.wc.conv3((id(m), 'conv'), m.conv.weight), bias=m.conv.bias,
-                       conv=(SDB_A_CONV3, B, 2 * x.H, 2 * x.W, x.C))
-        return Act(out, 2 * x.H, 2 * x.W, m.out_channels)
+                       conv=(SDB_A_CONV3, B, Ho, Wo, x.C), gsum=gs, rows_per_group=Ho * Wo)
+        return Act(out, Ho, Wo, m.out_channels, gs)
 
     def run_block(self, block, x1, x2, emb_all, ctx_kv, B, S):
         U = self.U
@@ -162,6 +209,7 @@ class UNetExecutor:
         net = self.net
         B, Cin, H, W = x.shape
         S = context.shape[1]
+        self.begin(B, x.device)
         emb_all = self.time_embedding(timesteps, B)
         if ctx_kv is None:
             ctx_kv = self.context_kv(context)
@@ -174,8 +222,16 @@ class UNetExecutor:
         h = self.run_block(net.middle_block, h, None, emb_all, ctx_kv, B, S)
         for block in net.output_blocks:                                                            # unet.py:570-572
             h = self.run_block(block, h, hs.pop(), emb_all, ctx_kv, B, S)
+        return self.head(h, B)
+
+    def head(self, h, B):
+        """unet.py:537-542: conv3x3(SiLU(GN(h))) -> NCHW."""
+        net = self.net
         gn, conv = net.out[0], net.out[2]
-        stats = ops.groupnorm_stats(h.t, None, B, h.H * h.W, gn.num_groups, gn.eps)
+        if h.gs is not None:
+            stats = ops.groupnorm_finalize(h.gs, None, h.C, 0, B, h.H * h.W, gn.num_groups, gn.eps)
+        else:
+            stats = ops.groupnorm_stats(h.t, None, B, h.H * h.W, gn.num_groups, gn.eps)
         return ops.conv3_out(h.t, stats, gn.weight, gn.bias, conv.weight, conv.bias, B, h.H, h.W, gn.num_groups)
 
     def __call__(self, x, timesteps, context, ctx_kv=None):

@@ -112,6 +112,61 @@ def test_gemm_conv3_variants(ops, gemm_env, cg, splitk):
     assert rel_l2(c, ref) < 2e-5
 
 
+@pytest.mark.parametrize('cg', [1, 2])
+def test_gemm_packed_output_and_geglu(ops, gemm_env, cg):
+    gemm_env(cg, None)
+    M, K, Fh = 520, 256, 512
+    a = rnd(M, K, seed=41)
+    w = rnd(2 * Fh, K, seed=42, scale=K ** -0.5)
+    bias = rnd(2 * Fh, seed=43)
+    u = a.double() @ w.double().t() + bias.double()
+    ref = u[:, :Fh] * F.gelu(u[:, Fh:])
+    wg, bg = ops.pack_weight_geglu(w, bias)
+    out = ops.gemm(ops.pack_rows(a), wg, bias=bg, geglu=True)
+    assert out.rows == M and out.K == Fh
+    assert rel_l2(out.unpack(), ref) < 5e-6
+    # packed copy with activation, with and without the fp32 result
+    w2 = rnd(192, K, seed=44, scale=K ** -0.5)
+    b2 = rnd(192, seed=45)
+    r2 = a.double() @ w2.double().t() + b2.double()
+    c, pk = ops.gemm(ops.pack_rows(a), ops.pack_weight(w2), bias=b2, pack_out='silu')
+    assert rel_l2(c, r2) < 5e-6 and rel_l2(pk.unpack(), F.silu(r2)) < 5e-6
+    c, pk = ops.gemm(ops.pack_rows(a), ops.pack_weight(w2), bias=b2, relu=True, pack_out='none', keep_c=False)
+    assert c is None and rel_l2(pk.unpack(), F.relu(r2)) < 5e-6
+
+
+@pytest.mark.parametrize('cg', [1, 2])
+@pytest.mark.parametrize('B,HW,C1,C2', [(3, 256, 128, 0), (5, 64, 512, 384), (9, 16, 384, 256), (2, 1024, 128, 128)])
+def test_gemm_groupnorm_partial_sums(ops, gemm_env, cg, B, HW, C1, C2):
+    """GN statistics accumulated by the producing GEMM epilogues == statistics of the stats kernel / torch."""
+    gemm_env(cg, None)
+    K = 128
+    xs, gss = [], []
+    for i, C in enumerate([C1, C2]):
+        if C == 0:
+            xs.append(None)
+            gss.append(None)
+            continue
+        a = rnd(B * HW, K, seed=51 + i)
+        w = rnd(C, K, seed=53 + i, scale=K ** -0.5)
+        bias = rnd(C, seed=55 + i) * 2
+        gs = torch.zeros(B, C // 4, 2, device='cuda')
+        xs.append(ops.gemm(ops.pack_rows(a), ops.pack_weight(w), bias=bias, gsum=gs, rows_per_group=HW))
+        gss.append(gs)
+    C = C1 + C2
+    gamma, beta = rnd(C, seed=57), rnd(C, seed=58)
+    out = ops.groupnorm_pack_fused(xs[0], xs[1], gamma, beta, B, HW, 32, 1e-5, True, gsum1=gss[0], gsum2=gss[1])
+    xcat = xs[0] if C2 == 0 else torch.cat([xs[0], xs[1]], 1)
+    xr = xcat.view(B, HW, C).permute(0, 2, 1).double()
+    ref = F.silu(F.group_norm(xr, 32, gamma.double(), beta.double(), 1e-5)).permute(0, 2, 1).reshape(B * HW, C)
+    assert rel_l2(out.unpack(), ref) < 5e-6
+    st = ops.groupnorm_finalize(gss[0], gss[1], C1, C2, B, HW, 32, 1e-5)
+    st_ref = ops.groupnorm_stats(xs[0], xs[1], B, HW, 32, 1e-5)
+    assert rel_l2(st, st_ref) < 1e-5
+    out2 = ops.groupnorm_pack_fused(xs[0], xs[1], gamma, beta, B, HW, 32, 1e-5, True, stats=st_ref)
+    assert rel_l2(out2.unpack(), ref) < 5e-6
+
+
 def test_gemm_rowvec(ops):
     B, HW, K, N = 3, 64, 128, 256
     a = rnd(B * HW, K, seed=7)
