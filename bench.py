@@ -219,7 +219,8 @@ def run_ours(args):
                          'frac': ach / peak_tf, 'traffic': None,
                          'kernel': 'sdb::gemm_kernel (tcgen05 kind::f16, 3 MMA passes per algorithmic product)',
                          'peak_source': peak_src + ' bf16 sustained', 'tensor_pipe_frac': 3 * ach / peak_tf,
-                         'gemm_share_of_unet_time': roof['share'], 'launches': roof['launches']},
+                         'gemm_share_of_unet_time': roof['ms'] / (ms / args.steps / NFE), 'launches': roof['launches'],
+                         'how': 'all %d GEMM launches of one UNet evaluation replayed from a CUDA graph, CUDA events' % roof['launches']},
             'cpu_baseline': cpu_baseline(sample_nfe=NFE, batch=2),
         }
         print(json.dumps(line))
@@ -250,19 +251,23 @@ def profile_once(args):
 
 
 def gemm_roofline(unet, sampler, B, dev):
-    """One un-captured UNet evaluation with CUDA events around every sdb_gemm launch."""
+    """Device time of the dominant kernel: every sdb_gemm call of ONE UNet evaluation is recorded (operands kept
+    alive), then exactly those launches are captured in a CUDA graph and replayed back to back, timed with CUDA
+    events on the launching stream -- no host launch latency, no other kernels in the interval."""
     from slotdiffusion_b200 import ops
     real = ops.gemm
-    recs = []
+    calls = []
 
-    def timed_gemm(a, w, *pa, **kw):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+    def recording_gemm(a, w, *pa, **kw):
         out = real(a, w, *pa, **kw)
-        e1.record()
         conv = kw.get('conv')
         M = a.rows if conv is None else conv[1] * conv[2] * conv[3]
-        recs.append((e0, e1, 2.0 * M * w.rows * w.K))
+        kw2 = dict(kw)
+        if kw2.get('gsum') is not None:
+            kw2['gsum'] = torch.zeros_like(kw2['gsum'])     # private copy: replays must not touch the live arena
+        calls.append((a, w, pa, kw2, 2.0 * M * w.rows * w.K,
+                      (M, w.rows, w.K, 'conv' if conv else 'lin', 'res' if kw.get('residual') is not None else '',
+                       'geglu' if kw.get('geglu') else '')))
         return out
     x = torch.randn(B, 3, 32, 32, device=dev)
     t = torch.randint(0, 1000, (B,), device=dev)
@@ -270,18 +275,48 @@ def gemm_roofline(unet, sampler, B, dev):
     with torch.no_grad():
         unet(x, t, context=ctx)
         torch.cuda.synchronize()
-        import slotdiffusion_b200.unet_exec as ue
-        ops.gemm = timed_gemm
+        ops.gemm = recording_gemm
         try:
-            w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            w0.record()
             unet(x, t, context=ctx)
-            w1.record()
         finally:
             ops.gemm = real
-    torch.cuda.synchronize()
-    ms = sum(e0.elapsed_time(e1) for e0, e1, _ in recs)
-    return {'ms': ms, 'flops': sum(f for _, _, f in recs), 'launches': len(recs), 'share': ms / w0.elapsed_time(w1)}
+        torch.cuda.synchronize()
+
+        def replay(sel):
+            for a, w, pa, kw, _, _ in sel:
+                real(a, w, *pa, **kw)
+
+        def graph_ms(sel, reps=5):
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                replay(sel)
+            torch.cuda.current_stream().wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                replay(sel)
+            g.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps
+        ms = graph_ms(calls)
+        if os.environ.get('SDB_GEMM_TABLE'):
+            import collections
+            agg = collections.OrderedDict()
+            for c in calls:
+                agg.setdefault(c[5], []).append(c)
+            rows = []
+            for k, sel in agg.items():
+                rows.append((k, len(sel), graph_ms(sel, 3) * 1e3, sum(c[4] for c in sel)))
+            print('%-44s %4s %9s %8s %9s' % ('M,N,K,kind', 'n', 'total us', 'avg us', 'alg TF/s'), file=sys.stderr)
+            for k, n, us, fl in sorted(rows, key=lambda r: -r[2]):
+                print('%-44s %4d %9.1f %8.1f %9.1f' % (str(k), n, us, us / n, fl / us / 1e6), file=sys.stderr)
+    return {'ms': ms, 'flops': sum(c[4] for c in calls), 'launches': len(calls)}
 
 
 def time_sa(sa, feats, slots0, iters=20):
