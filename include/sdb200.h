@@ -12,8 +12,8 @@
  *     sequence of calls is CUDA-graph capturable;
  *   - return 0 on success, SDB_ERR_* otherwise; sdb_last_error() gives the message (thread-local);
  *   - fp32 tensors are row-major contiguous unless a leading dimension is passed;
- *   - "packed" = GEMM operand format: fp16 [2][rows][K], plane 0 = hi = fp16(x), plane 1 = lo =
- *     fp16(x - hi).  hi*hi + hi*lo + lo*hi on the fp16 tensor pipe with fp32 accumulation
+ *   - "packed" = GEMM operand format: 16-bit [2][rows][K], plane 0 = hi = fp16(x), plane 1 = lo =
+ *     fp16(x - hi) (gradient operands of the backward pass use the same layout with bf16, see SdbGemm.a_bf16).  hi*hi + hi*lo + lo*hi on the fp16 tensor pipe with fp32 accumulation
  *     reproduces an fp32 product to ~2^-22 (DESIGN.md "precision").
  */
 #ifndef SDB200_H_
@@ -51,6 +51,12 @@ int64_t sdb_launch_count(void);
 #define SDB_A_PLAIN 0
 #define SDB_A_CONV3 1
 #define SDB_A_CONV3S2 2
+/* weight-gradient forms (training, nn.Conv2d backward of the lines above): the contraction runs over the OUTPUT PIXELS.
+ * A is the SAME packed NHWC activation the forward conv consumed ([B,H_in,W_in,C]; mode 4: the stride-2 phase split),
+ * W is the packed output gradient rows [B*H*W][N] (N contiguous): both are MN-major tensor-core operands, the 3x3 taps
+ * and zero padding are again TMA box shifts.  H, W = OUTPUT size.  C[9*C, N] with row = tap*C + ci;  M = 9*C, K = B*H*W. */
+#define SDB_A_WGRAD 3
+#define SDB_A_WGRAD_S2 4
 
 typedef struct SdbGemm {
   const void* a;         /* packed A, planes are a_plane_stride halves apart */
@@ -74,6 +80,9 @@ typedef struct SdbGemm {
   int32_t out_act;        /* activation of the packed copy: 0 none, 1 SiLU, 2 ReLU */
   int32_t geglu;          /* GEGLU epilogue (attention.py:46-48): W / bias rows interleaved by sdb_pack_weight_geglu; the only
                              output is out_packed [2][M][N/2] = a * gelu_erf(g) */
+  int32_t a_bf16, w_bf16; /* the planes of A / W hold a BF16 hi/lo split (gradient operands from sdb_grad_pack /
+                             sdb_pack_zero_up2: fp32 exponent range, ~16 mantissa bits) instead of the FP16 split.
+                             tcgen05 kind::f16 takes ONE input format: a_bf16 must equal w_bf16 */
 } SdbGemm;
 
 int sdb_gemm(const SdbGemm* p, void* stream);
@@ -108,6 +117,11 @@ int sdb_groupnorm_apply_pack(const float* x1, int64_t C1, const float* x2, int64
 int sdb_groupnorm_apply_pack_fused(const float* x1, int64_t C1, const float* gsum1, const float* x2, int64_t C2,
                                    const float* gsum2, const float* stats, const float* gamma, const float* beta,
                                    void* out, int64_t B, int64_t HW, int G, float eps, int silu, void* stream);
+/* training form: nn.Dropout(p) after the SiLU (ResBlock out_layers, unet.py:245-246) with a counter-based mask
+ * (seed, element index) that sdb_groupnorm_bwd regenerates; stats [B,G,2] required. */
+int sdb_groupnorm_apply_pack_dropout(const float* x1, int64_t C1, const float* x2, int64_t C2, const float* stats,
+                                     const float* gamma, const float* beta, void* out, int64_t B, int64_t HW, int G,
+                                     int silu, float drop_p, uint64_t seed, void* stream);
 /* partial sums -> stats [B,G,2] (mean, rstd) */
 int sdb_groupnorm_finalize(const float* gsum1, int64_t C1, const float* gsum2, int64_t C2, float* stats, int64_t B,
                            int64_t HW, int G, float eps, void* stream);
@@ -159,6 +173,10 @@ int sdb_conv3_out(const float* h, const float* stats, const float* gamma, const 
 int64_t sdb_slot_attend_workspace(int64_t B, int64_t N, int64_t S, int64_t D);
 int sdb_slot_attend(const float* kv, const float* q, float* seg_mask, void* upd_packed, float* upd32, float* work,
                     int64_t B, int64_t N, int64_t S, int64_t D, float scale, float eps, void* stream);
+/* same, also returning colsum[b,s] = sum_n (attn + eps) (needed by sdb_slot_attend_bwd) */
+int sdb_slot_attend_train(const float* kv, const float* q, float* seg_mask, void* upd_packed, float* upd32,
+                          float* colsum, float* work, int64_t B, int64_t N, int64_t S, int64_t D, float scale, float eps,
+                          void* stream);
 /* GRUCell pointwise part (PyTorch gate order r,z,n; slot_attention.py:97-100): gi = x W_ih^T + b_ih and
  * gh = h W_hh^T + b_hh come from sdb_gemm; h_new = (1-z) n + z h.  All [R, 3D] / [R, D]. */
 int sdb_gru_gates(const float* gi, const float* gh, const float* h, float* h_new, int64_t R, int64_t D,
@@ -172,6 +190,66 @@ int sdb_dpm_x0(const float* x, const float* eps, float alpha, float sigma, const
 /* out = a*x + b*m0 + c*(m1 - m0)   (m1 may be NULL -> c ignored) */
 int sdb_lincomb(float* out, const float* x, const float* m0, const float* m1, float a, float b, float c,
                 int64_t n, void* stream);
+
+
+/* ================================================================== backward (training) entry points
+ * Replace torch autograd of the forward lines cited above (LDM.loss_function, ldm.py:59-83 -> UNet backward;
+ * SlotAttention backward through all iterations, slot_attention.py:78-102).  The contractions of the backward pass are
+ * sdb_gemm calls (dgrad: pack(dY) x pack_T(W); wgrad: SDB_A_WGRAD / plain on transposed operands, split-K). */
+
+/* dy [M,N] (row stride ld) -> any of: packed rows [2][M][N]; packed transpose [2][N][ldt >= M] (the caller zero-fills
+ * the padding columns when ldt > M; ldt % 8 == 0 makes it a valid GEMM operand); bias_grad[N] += column sums;
+ * group_grad[row / rows_per_group][n] (row stride ldg) += column sums per group (timestep-embedding gradient). */
+int sdb_grad_pack(const float* dy, int64_t ld, void* out_rows, void* out_T, int64_t ldt, float* bias_grad,
+                  float* group_grad, int64_t ldg, int64_t M, int64_t N, int rows_per_group, void* stream);
+/* packed [2][M][K] -> packed [2][K][ldt >= M]; to_bf16: re-split an fp16 operand as bf16 on the way */
+int sdb_transpose_packed(const void* in, void* out, int64_t ldt, int64_t M, int64_t K, int to_bf16, void* stream);
+/* fp16-split packed operand (n elements per plane) -> bf16-split, same layout */
+int sdb_repack_bf16(const void* in, void* out, int64_t n, void* stream);
+/* conv weight [Cout,Cin,3,3] -> dgrad operand packed [2][Cin][9*Cout] (taps rotated by 180 degrees), fp16 or bf16 split */
+int sdb_pack_weight_conv3_dgrad(const float* w, void* out, int64_t Cout, int64_t Cin, int bf16, void* stream);
+/* wgrad GEMM result c9 [9*Cin][ldc >= Cout] -> dw [Cout][Cin_w][3][3] (= or +=) */
+int sdb_wgrad_conv3_scatter(const float* c9, int64_t ldc, float* dw, int64_t Cout, int64_t Cin, int64_t Cin_w,
+                            int accumulate, void* stream);
+/* out = a + b + c (b, c optional), n % 4 == 0 */
+int sdb_add3(float* out, const float* a, const float* b, const float* c, int64_t n, void* stream);
+/* dx = dy * act'(pre); act 1 SiLU, 2 ReLU */
+int sdb_act_bwd(const float* dy, int64_t ldy, const float* pre, int64_t ldp, float* dx, int64_t ldx, int64_t M, int64_t N,
+                int act, void* stream);
+/* GroupNorm(+SiLU)(+dropout) backward.  da [B*HW, C1+C2] = gradient w.r.t. the normalised/activated operand;
+ * dx1/dx2 = gradients of the two concatenated sources (+ add1/add2 if given); dgamma/dbeta are accumulated (+=).
+ * sums_work: fp32 scratch [B][C][2]. */
+int sdb_groupnorm_bwd(const float* x1, int64_t C1, const float* x2, int64_t C2, const float* da, const float* stats,
+                      const float* gamma, const float* beta, float* sums_work, float* dx1, float* dx2, const float* add1,
+                      const float* add2, float* dgamma, float* dbeta, int64_t B, int64_t HW, int G, int silu, float drop_p,
+                      uint64_t seed, void* stream);
+/* LayerNorm backward: dx = LN'(x) dn (+ add); dgamma/dbeta accumulated (+=) */
+int sdb_layernorm_bwd(const float* x, const float* dn, const float* gamma, float eps, const float* add, float* dx,
+                      float* dgamma, float* dbeta, int64_t M, int64_t C, void* stream);
+/* attention core backward; work: fp32 scratch of 2*B*heads*Lq floats */
+int sdb_attention_bwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                      const float* dout, int64_t ldo, float* dq, int64_t lddq, float* dk, int64_t lddk, float* dv,
+                      int64_t lddv, float* work, int64_t B, int64_t Lq, int64_t Lk, int heads, int d, float scale,
+                      void* stream);
+/* GEGLU backward: u [M,2F], dg [M,F] -> du [M,2F] */
+int sdb_geglu_bwd(const float* u, const float* dg, float* du, int64_t M, int64_t F, void* stream);
+/* adjoint of the nearest x2 upsample: dup [B,2H,2W,C] -> dx [B,H,W,C] */
+int sdb_up2_adjoint(const float* dup, float* dx, int64_t B, int64_t H, int64_t W, int64_t C, void* stream);
+/* zero insertion dy [B,H,W,C] -> packed [2][B*2H*2W][C] (dgrad of a stride-2 conv = stride-1 conv of it, rotated taps) */
+int sdb_pack_zero_up2(const float* dy, void* out, int64_t B, int64_t H, int64_t W, int64_t C, void* stream);
+/* NCHW [B,Cs,HW] -> NHWC packed with channels zero-padded to Cp; NHWC <-> NCHW converters for the 3-channel ends */
+int sdb_pack_nchw_pad(const float* x, void* out, int64_t B, int64_t Cs, int64_t HW, int64_t Cp, void* stream);
+int sdb_nhwc_to_nchw(const float* in, int64_t ld, float* out, int64_t B, int64_t Cs, int64_t HW, void* stream);
+int sdb_nchw_to_nhwc_pad(const float* in, float* out, int64_t B, int64_t Cs, int64_t HW, int64_t Cp, void* stream);
+/* explicit transposed im2col (feature maps narrower than 8): packed [2][B*H*W][C] -> packed [2][9*C][B*H*W] */
+int sdb_im2col_t(const void* in, void* out, int64_t B, int64_t H, int64_t W, int64_t C, void* stream);
+/* GRUCell pointwise backward */
+int sdb_gru_gates_bwd(const float* gi, const float* gh, const float* h, const float* dh_new, float* dgi, float* dgh,
+                      float* dh, int64_t R, int64_t D, void* stream);
+/* one Slot-Attention iteration backward: dkv [B,N,2D] (= or +=), dq [B,S,D] (overwritten) */
+int sdb_slot_attend_bwd(const float* kv, const float* q, const float* upd, const float* colsum, const float* d_upd,
+                        float* dkv, float* dq, int64_t B, int64_t N, int64_t S, int64_t D, float scale, float eps,
+                        int accumulate, void* stream);
 
 #ifdef __cplusplus
 }

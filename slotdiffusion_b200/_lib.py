@@ -4,12 +4,12 @@ There is NO fallback: if the shared library is missing or a call fails, a Runtim
 """
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_uint64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libsdb200.so')
 
-SDB_A_PLAIN, SDB_A_CONV3, SDB_A_CONV3S2 = 0, 1, 2
+SDB_A_PLAIN, SDB_A_CONV3, SDB_A_CONV3S2, SDB_A_WGRAD, SDB_A_WGRAD_S2 = 0, 1, 2, 3, 4
 SDB_PACK_PLAIN, SDB_PACK_UP2, SDB_PACK_PHASE2 = 0, 1, 2
 
 
@@ -20,7 +20,7 @@ class SdbGemm(Structure):
         ('M', c_int32), ('N', c_int32), ('K', c_int32), ('mode', c_int32), ('B', c_int32), ('H', c_int32),
         ('W', c_int32), ('C', c_int32), ('rows_per_group', c_int32), ('passes', c_int32), ('relu', c_int32),
         ('out_packed', c_void_p), ('gsum', c_void_p), ('out_plane_stride', c_int64), ('out_act', c_int32),
-        ('geglu', c_int32),
+        ('geglu', c_int32), ('a_bf16', c_int32), ('w_bf16', c_int32),
     ]
 
 
@@ -58,6 +58,38 @@ SIGNATURES = {
     'sdb_slot_attend_workspace': (c_int64, [c_int64, c_int64, c_int64, c_int64]),
     'sdb_slot_attend': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                 c_int64, c_int64, c_float, c_float, c_void_p]),
+    'sdb_slot_attend_train': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                      c_int64, c_int64, c_int64, c_float, c_float, c_void_p]),
+    'sdb_groupnorm_apply_pack_dropout': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
+                                                 c_void_p, c_int64, c_int64, c_int, c_int, c_float, c_uint64, c_void_p]),
+    'sdb_grad_pack': (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64,
+                              c_int64, c_int, c_void_p]),
+    'sdb_transpose_packed': (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p]),
+    'sdb_repack_bf16': (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    'sdb_pack_weight_conv3_dgrad': (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p]),
+    'sdb_wgrad_conv3_scatter': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p]),
+    'sdb_add3': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    'sdb_act_bwd': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int,
+                            c_void_p]),
+    'sdb_groupnorm_bwd': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int,
+                                  c_int, c_float, c_uint64, c_void_p]),
+    'sdb_layernorm_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_int64, c_int64, c_void_p]),
+    'sdb_attention_bwd': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
+                                  c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64,
+                                  c_int, c_int, c_float, c_void_p]),
+    'sdb_geglu_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
+    'sdb_up2_adjoint': (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p]),
+    'sdb_pack_zero_up2': (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p]),
+    'sdb_pack_nchw_pad': (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p]),
+    'sdb_nhwc_to_nchw': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
+    'sdb_nchw_to_nhwc_pad': (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p]),
+    'sdb_im2col_t': (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p]),
+    'sdb_gru_gates_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                  c_int64, c_void_p]),
+    'sdb_slot_attend_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                    c_int64, c_int64, c_int64, c_float, c_float, c_int, c_void_p]),
     'sdb_gru_gates': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     'sdb_dpm_x0': (c_int, [c_void_p, c_void_p, c_float, c_float, c_void_p, c_int64, c_void_p, c_void_p, c_int64,
                            c_int64, c_int64, c_void_p]),

@@ -1,6 +1,7 @@
 // Shared host/device helpers for libsdb200.
 #pragma once
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -57,6 +58,32 @@ __device__ __forceinline__ void store_split4(__half* hi, __half* lo, long long i
   *reinterpret_cast<uint2*>(lo + idx) = pl;
 }
 
+// Gradient operands: bf16 hi/lo split (x ~= hi + lo, ~16 mantissa bits, fp32 exponent range).  Loss gradients are
+// routinely 1e-6 and smaller, far inside fp16's subnormal range where the fp16 split would keep only a few bits.
+// Stored in the same 16-bit planes; sdb_gemm is told per operand which format the planes hold.
+__device__ __forceinline__ void split_bf16(float x, __half& hi, __half& lo) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(x);
+  const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+  hi = __ushort_as_half(__bfloat16_as_ushort(h));
+  lo = __ushort_as_half(__bfloat16_as_ushort(l));
+}
+__device__ __forceinline__ void store_split4_bf16(__half* hi, __half* lo, long long idx, float4 v) {
+  __half h0, h1, h2, h3, l0, l1, l2, l3;
+  split_bf16(v.x, h0, l0);
+  split_bf16(v.y, h1, l1);
+  split_bf16(v.z, h2, l2);
+  split_bf16(v.w, h3, l3);
+  __half2 a = __halves2half2(h0, h1), b = __halves2half2(h2, h3);
+  __half2 cc = __halves2half2(l0, l1), d = __halves2half2(l2, l3);
+  uint2 ph, pl;
+  ph.x = *reinterpret_cast<uint32_t*>(&a);
+  ph.y = *reinterpret_cast<uint32_t*>(&b);
+  pl.x = *reinterpret_cast<uint32_t*>(&cc);
+  pl.y = *reinterpret_cast<uint32_t*>(&d);
+  *reinterpret_cast<uint2*>(hi + idx) = ph;
+  *reinterpret_cast<uint2*>(lo + idx) = pl;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -71,5 +98,15 @@ __device__ __forceinline__ float warp_max(float v) {
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + __expf(-x)); }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+
+// counter-based dropout mask: keep-scale (1/(1-p)) or 0 for element `idx` of the tensor identified by `seed`
+__device__ __forceinline__ float dropout_scale(unsigned long long seed, unsigned long long idx, float p, float inv_keep) {
+  unsigned long long z = seed + idx * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  const float u = (float)(unsigned)(z >> 40) * (1.f / 16777216.f);   // 24 random bits -> [0,1)
+  return u < p ? 0.f : inv_keep;
+}
 
 }  // namespace sdb

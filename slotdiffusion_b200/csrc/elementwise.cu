@@ -192,7 +192,7 @@ groupnorm_apply_pack_fused_kernel(const float* __restrict__ x1, int C1, const fl
                                   const float* __restrict__ x2, int C2, const float* __restrict__ gsum2,
                                   const float* __restrict__ stats, const float* __restrict__ gamma,
                                   const float* __restrict__ beta, __half* __restrict__ out, int64_t B, int HW, int G,
-                                  float eps, int silu, int rows_per_chunk) {
+                                  float eps, int silu, int rows_per_chunk, float drop_p, unsigned long long seed) {
   __shared__ float s_mean[64], s_rstd[64];
   const int C = C1 + C2, c4n = C >> 2, cpg = C / G;
   const int64_t b = blockIdx.y;
@@ -245,6 +245,12 @@ groupnorm_apply_pack_fused_kernel(const float* __restrict__ x1, int C1, const fl
     if (silu) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) o[j] = silu_f(o[j]);
+    }
+    if (drop_p > 0.f) {
+      const float inv_keep = 1.f / (1.f - drop_p);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        o[j] *= dropout_scale(seed, (unsigned long long)(row * C + c + j), drop_p, inv_keep);
     }
     store_split4(out, out + plane, row * C + c, make_float4(o[0], o[1], o[2], o[3]));
   }
@@ -660,6 +666,9 @@ extern "C" int sdb_lincomb(float* out, const float* x, const float* m0, const fl
   return 0;
 }
 
+static thread_local float g_drop_p = 0.f;                 // set only by sdb_groupnorm_apply_pack_dropout
+static thread_local unsigned long long g_drop_seed = 0;
+
 extern "C" int sdb_groupnorm_apply_pack_fused(const float* x1, int64_t C1, const float* gsum1, const float* x2,
                                               int64_t C2, const float* gsum2, const float* stats, const float* gamma,
                                               const float* beta, void* out, int64_t B, int64_t HW, int G, float eps,
@@ -683,9 +692,24 @@ extern "C" int sdb_groupnorm_apply_pack_fused(const float* x1, int64_t C1, const
   chunks = cdiv(HW, rows_per_chunk);
   dim3 grid((unsigned)chunks, (unsigned)B);
   groupnorm_apply_pack_fused_kernel<<<grid, threads, 0, as_stream(stream)>>>(
-      x1, (int)C1, gsum1, x2, (int)C2, gsum2, stats, gamma, beta, (__half*)out, B, (int)HW, G, eps, silu, rows_per_chunk);
+      x1, (int)C1, gsum1, x2, (int)C2, gsum2, stats, gamma, beta, (__half*)out, B, (int)HW, G, eps, silu, rows_per_chunk,
+      g_drop_p, g_drop_seed);
   SDB_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int sdb_groupnorm_apply_pack_dropout(const float* x1, int64_t C1, const float* x2, int64_t C2,
+                                                const float* stats, const float* gamma, const float* beta, void* out,
+                                                int64_t B, int64_t HW, int G, int silu, float drop_p, uint64_t seed,
+                                                void* stream) {
+  SDB_REQUIRE(stats, "sdb_groupnorm_apply_pack_dropout: stats required");
+  SDB_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "sdb_groupnorm_apply_pack_dropout: bad p");
+  g_drop_p = drop_p;
+  g_drop_seed = seed;
+  const int rc = sdb_groupnorm_apply_pack_fused(x1, C1, nullptr, x2, C2, nullptr, stats, gamma, beta, out, B, HW, G, 0.f,
+                                                silu, stream);
+  g_drop_p = 0.f;
+  return rc;
 }
 
 extern "C" int sdb_groupnorm_finalize(const float* gsum1, int64_t C1, const float* gsum2, int64_t C2, float* stats,

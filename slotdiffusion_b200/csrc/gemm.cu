@@ -68,6 +68,8 @@ struct GemmArgs {
   int vec_ok;           // 128-bit epilogue accesses allowed (alignment / N % 4)
   unsigned rows_per_group;
   int H, W;             // output H, W (conv modes)
+  int ctiles;           // WGRAD modes: channel blocks per tap
+  int a_bf16, w_bf16;   // operand planes hold bf16 (gradient operands) instead of fp16
 };
 
 // Warp-specialised persistent GEMM.  CG = 1: one CTA per tile (UMMA 128 x bn).  CG = 2: a CTA pair (cluster of 2)
@@ -129,8 +131,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
         const int ks_begin = (int)((long long)ksteps * split / g.splits);
         const int ks_end = (int)((long long)ksteps * (split + 1) / g.splits);
         int x0 = 0, y0 = 0, b0 = 0;
+        const bool wgrad = (g.mode == SDB_A_WGRAD || g.mode == SDB_A_WGRAD_S2);
+        int wtap = 0, wc0 = 0;
         if (g.mode == SDB_A_PLAIN) {
           x0 = tm * BM;   // row index lives in dim 1
+        } else if (wgrad) {
+          // output row block tm = (tap, channel block): A rows are CHANNELS of the transposed activation, K = pixels
+          wtap = tm / g.ctiles;
+          wc0 = (tm - wtap * g.ctiles) * g.tile_rows;
         } else {
           const int rows_per_img = g.H * g.W;
           const long long m0 = (long long)tm * g.tile_rows;
@@ -142,10 +150,31 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
           mbar_wait(&ctl.empty[stage], phase ^ 1);
           uint8_t* base = ring + (size_t)stage * g.stage_bytes;
           if (rank == 0) mbar_arrive_expect_tx(&ctl.full[stage], tx);
-          const int tap = ks / g.kblocks;
-          const int c0 = (ks - tap * g.kblocks) * BK;
+          int tap = ks / g.kblocks;
+          int c0 = (ks - tap * g.kblocks) * BK;
           int cx = x0, cy = y0, cp = 0;
-          if (g.mode == SDB_A_CONV3) {
+          int c3 = cp, c4 = b0;
+          if (wgrad) {
+            // k-block ks = 64 consecutive output pixels (64/W rows of one image, or 64/(H*W) whole images).  A is the
+            // NHWC activation itself: box {64 channels, W, rows, 1, images} shifted by the tap in the OUTER dims only.
+            const int m0 = ks * BK;
+            const int hw = g.H * g.W;
+            const int bimg = m0 / hw;
+            const int yrow = (m0 - bimg * hw) / g.W;
+            tap = wtap;
+            c0 = wc0;
+            if (g.mode == SDB_A_WGRAD) {
+              cx = tap % 3 - 1;
+              cy = yrow + tap / 3 - 1;
+              c3 = 0;
+            } else {
+              const int ky = tap / 3, kx = tap % 3;
+              cx = (kx == 0) ? -1 : 0;
+              cy = yrow + ((ky == 0) ? -1 : 0);
+              c3 = ((ky != 1) ? 2 : 0) + ((kx != 1) ? 1 : 0);
+            }
+            c4 = bimg;
+          } else if (g.mode == SDB_A_CONV3) {
             cx = tap % 3 - 1;
             cy = y0 + tap / 3 - 1;
           } else if (g.mode == SDB_A_CONV3S2) {
@@ -155,20 +184,38 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
             cx = (kx == 0) ? -1 : 0;
             cy = y0 + ((ky == 0) ? -1 : 0);
           }
+          if (!wgrad) { c3 = cp; c4 = b0; }
           uint8_t* a_hi = base, * a_lo = base + TILE_A_BYTES;
           uint8_t* b_hi = base + 2 * TILE_A_BYTES, * b_lo = b_hi + b_tile_bytes;
-          if (CG == 2) {
-            tma_load_5d_pair(a_hi, &map_a_hi, &ctl.full[stage], c0, cx, cy, cp, b0);
+          if (wgrad) {
+            // MN-major operands: 64-wide (128-byte) column blocks of [64 pixels] x [64 channels], 8 KB apart
+            const int na = g.tile_rows / 64, nb = g.bnl / 64;
+            for (int pl = 0; pl < (three ? 2 : 1); ++pl) {
+              const CUtensorMap* ma = pl ? &map_a_lo : &map_a_hi;
+              const CUtensorMap* mb = pl ? &map_b_lo : &map_b_hi;
+              uint8_t* ap = pl ? a_lo : a_hi;
+              uint8_t* bp = pl ? b_lo : b_hi;
+              for (int j = 0; j < na; ++j) {
+                if (CG == 2) tma_load_5d_pair(ap + j * 8192, ma, &ctl.full[stage], c0 + j * 64, cx, cy, c3, c4);
+                else tma_load_5d(ap + j * 8192, ma, &ctl.full[stage], c0 + j * 64, cx, cy, c3, c4);
+              }
+              for (int j = 0; j < nb; ++j) {
+                if (CG == 2) tma_load_2d_pair(bp + j * 8192, mb, &ctl.full[stage], nrow + j * 64, ks * BK);
+                else tma_load_2d(bp + j * 8192, mb, &ctl.full[stage], nrow + j * 64, ks * BK);
+              }
+            }
+          } else if (CG == 2) {
+            tma_load_5d_pair(a_hi, &map_a_hi, &ctl.full[stage], c0, cx, cy, c3, c4);
             tma_load_2d_pair(b_hi, &map_b_hi, &ctl.full[stage], ks * BK, nrow);
             if (three) {
-              tma_load_5d_pair(a_lo, &map_a_lo, &ctl.full[stage], c0, cx, cy, cp, b0);
+              tma_load_5d_pair(a_lo, &map_a_lo, &ctl.full[stage], c0, cx, cy, c3, c4);
               tma_load_2d_pair(b_lo, &map_b_lo, &ctl.full[stage], ks * BK, nrow);
             }
           } else {
-            tma_load_5d(a_hi, &map_a_hi, &ctl.full[stage], c0, cx, cy, cp, b0);
+            tma_load_5d(a_hi, &map_a_hi, &ctl.full[stage], c0, cx, cy, c3, c4);
             tma_load_2d(b_hi, &map_b_hi, &ctl.full[stage], ks * BK, nrow);
             if (three) {
-              tma_load_5d(a_lo, &map_a_lo, &ctl.full[stage], c0, cx, cy, cp, b0);
+              tma_load_5d(a_lo, &map_a_lo, &ctl.full[stage], c0, cx, cy, c3, c4);
               tma_load_2d(b_lo, &map_b_lo, &ctl.full[stage], ks * BK, nrow);
             }
           }
@@ -179,7 +226,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
   } else if (warp == 1) {
     // ===================== MMA issuer (single thread of the leader CTA) =====================
     if (lane == 0 && rank == 0) {
-      const uint32_t idesc = umma_idesc_f16(BM * CG, g.bn);
+      const bool mn_major = (g.mode == SDB_A_WGRAD || g.mode == SDB_A_WGRAD_S2);
+      // wgrad: both operands are MN-major in shared memory (pixels = K run along the 128-byte rows' ROW index)
+      const uint32_t idesc = umma_idesc_f16(BM * CG, g.bn) | (mn_major ? ((1u << 15) | (1u << 16)) : 0u) |
+                             (g.a_bf16 ? (1u << 7) : 0u) | (g.w_bf16 ? (1u << 10) : 0u);   // a_format / b_format = BF16
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -199,11 +249,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
           const uint32_t a_lo = a_hi + TILE_A_BYTES;
           const uint32_t b_hi = a_hi + 2 * TILE_A_BYTES;
           const uint32_t b_lo = b_hi + b_tile_bytes;
-          const uint64_t da_hi = umma_desc_kmajor_sw128(a_hi), da_lo = umma_desc_kmajor_sw128(a_lo);
-          const uint64_t db_hi = umma_desc_kmajor_sw128(b_hi), db_lo = umma_desc_kmajor_sw128(b_lo);
+          const uint64_t da_hi = mn_major ? umma_desc_mnmajor_sw128(a_hi) : umma_desc_kmajor_sw128(a_hi);
+          const uint64_t da_lo = mn_major ? umma_desc_mnmajor_sw128(a_lo) : umma_desc_kmajor_sw128(a_lo);
+          const uint64_t db_hi = mn_major ? umma_desc_mnmajor_sw128(b_hi) : umma_desc_kmajor_sw128(b_hi);
+          const uint64_t db_lo = mn_major ? umma_desc_mnmajor_sw128(b_lo) : umma_desc_kmajor_sw128(b_lo);
 #pragma unroll
           for (int k = 0; k < BK / UK; ++k) {
-            const uint64_t adv = uint64_t((k * UK * 2) >> 4);   // 32 B per k-step inside the 128-B swizzle row
+            // K-major: 32 B per k-step inside the 128-B swizzle row; MN-major: 16 K rows = two 1024-B atoms per k-step
+            const uint64_t adv = mn_major ? uint64_t((k * UK * 128) >> 4) : uint64_t((k * UK * 2) >> 4);
             const uint32_t acc = (ks != ks_begin || k != 0) ? 1u : 0u;
             if (CG == 2) {
               umma_f16_pair(d_tmem, da_hi + adv, db_hi + adv, idesc, acc);
@@ -509,7 +562,9 @@ extern "C" int sdb_gemm(const SdbGemm* p, void* stream) {
   SDB_REQUIRE(p && p->a && p->w && (p->c || p->out_packed), "sdb_gemm: null operand");
   SDB_REQUIRE(p->M > 0 && p->N > 0 && p->K > 0, "sdb_gemm: empty problem M=%d N=%d K=%d", p->M, p->N, p->K);
   SDB_REQUIRE(p->passes == 1 || p->passes == 3, "sdb_gemm: passes must be 1 or 3");
-  SDB_REQUIRE(p->K % 8 == 0, "sdb_gemm: K=%d must be a multiple of 8 (16-byte TMA rows)", p->K);
+  SDB_REQUIRE((p->a_bf16 != 0) == (p->w_bf16 != 0), "sdb_gemm: A and W must use the same 16-bit format (fp16 or bf16)");
+  SDB_REQUIRE(p->K % 8 == 0 || p->mode == SDB_A_WGRAD || p->mode == SDB_A_WGRAD_S2,
+              "sdb_gemm: K=%d must be a multiple of 8 (16-byte TMA rows)", p->K);
   SDB_REQUIRE((reinterpret_cast<uintptr_t>(p->a) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->w) & 15) == 0,
               "sdb_gemm: operands must be 16-byte aligned");
   SDB_REQUIRE(!p->rowvec || p->rows_per_group > 0, "sdb_gemm: rowvec needs rows_per_group");
@@ -517,6 +572,7 @@ extern "C" int sdb_gemm(const SdbGemm* p, void* stream) {
   g.c = p->c; g.bias = p->bias; g.rowvec = p->rowvec; g.residual = p->residual;
   g.out_packed = reinterpret_cast<__half*>(p->out_packed); g.gsum = p->gsum;
   g.out_plane = p->out_plane_stride; g.out_act = p->out_act;
+  g.a_bf16 = p->a_bf16 != 0; g.w_bf16 = p->w_bf16 != 0;
   g.ldc = p->ldc; g.ldv = p->ldv; g.ldr = p->ldr;
   g.M = p->M; g.N = p->N; g.K = p->K; g.mode = p->mode; g.passes = p->passes; g.relu = p->relu;
   g.rows_per_group = p->rows_per_group > 0 ? (unsigned)p->rows_per_group : 1u;
@@ -548,6 +604,21 @@ extern "C" int sdb_gemm(const SdbGemm* p, void* stream) {
     g.tile_rows = BM; g.ntaps = 1; g.kblocks = (int)cdiv(p->K, BK);
     n_tiles_m1 = (int)cdiv(p->M, BM);
     g.H = 1; g.W = 1;
+  } else if (p->mode == SDB_A_WGRAD || p->mode == SDB_A_WGRAD_S2) {
+    // C[9*Cin, N] (row = tap*Cin + ci) = sum over output pixels of X_tap[pix, ci] * dY[pix, n];  K = B*H*W
+    SDB_REQUIRE(p->C % 64 == 0, "sdb_gemm: wgrad C=%d must be a multiple of 64", p->C);
+    SDB_REQUIRE(p->M == 9 * p->C, "sdb_gemm: wgrad M=%d != 9*C", p->M);
+    SDB_REQUIRE((long long)p->K == (long long)p->B * p->H * p->W, "sdb_gemm: wgrad K != B*H*W");
+    SDB_REQUIRE(p->W <= 64 && 64 % p->W == 0 && ((p->H * p->W) % 64 == 0 || 64 % (p->H * p->W) == 0),
+                "sdb_gemm: wgrad needs W | 64 and H*W a multiple or divisor of 64 (got %dx%d)", p->H, p->W);
+    SDB_REQUIRE(p->N % 8 == 0, "sdb_gemm: wgrad N=%d must be a multiple of 8", p->N);
+    g.H = p->H; g.W = p->W;
+    box_h = 64 / p->W < p->H ? 64 / p->W : p->H;
+    box_b = 64 / (p->W * box_h);
+    g.tile_rows = (p->C % 128 == 0) ? 128 : 64;   // 64: the upper half of the UMMA tile is computed on stale rows and dropped
+    g.ctiles = p->C / g.tile_rows;
+    g.ntaps = 1; g.kblocks = (int)cdiv(p->K, BK);
+    n_tiles_m1 = 9 * g.ctiles;
   } else {
     SDB_REQUIRE(p->mode == SDB_A_CONV3 || p->mode == SDB_A_CONV3S2, "sdb_gemm: bad mode %d", p->mode);
     SDB_REQUIRE(p->C % BK == 0, "sdb_gemm: conv C=%d must be a multiple of 64", p->C);
@@ -574,7 +645,9 @@ extern "C" int sdb_gemm(const SdbGemm* p, void* stream) {
   int cg = (n_tiles_m1 >= 2) ? 2 : 1;
   const int force_cg = env_int("SDB_GEMM_CG", 0);
   if (force_cg == 1 || force_cg == 2) cg = force_cg;
-  g.bn = (cg == 2) ? pick_bn(p->N, 256, 32) : pick_bn(p->N, 128, geglu ? 32 : 16);
+  const bool wgrad_mode = (p->mode == SDB_A_WGRAD || p->mode == SDB_A_WGRAD_S2);
+  if (wgrad_mode) g.bn = pick_bn(p->N, 128 * cg, 64 * cg);   // each CTA stages whole 64-column (128-byte) blocks of dY
+  else g.bn = (cg == 2) ? pick_bn(p->N, 256, 32) : pick_bn(p->N, 128, geglu ? 32 : 16);
   g.bnl = g.bn / cg;
   g.n_tiles_m = (int)cdiv(n_tiles_m1, cg);
   g.n_tiles_n = (int)cdiv(p->N, g.bn);
@@ -609,6 +682,15 @@ extern "C" int sdb_gemm(const SdbGemm* p, void* stream) {
     uint32_t box[5] = {BK, BM, 1, 1, 1};
     if ((rc = make_map(&ma_hi, a, 5, dims, st, box))) return rc;
     if ((rc = make_map(&ma_lo, a + p->a_plane_stride, 5, dims, st, box))) return rc;
+  } else if (wgrad_mode) {
+    // the NHWC activation (or its stride-2 phase split): box = 64 channels x 64 pixels
+    const int H = p->H, W = p->W, B = p->B, C = p->C;
+    const uint64_t phases = (p->mode == SDB_A_WGRAD_S2) ? 4 : 1;
+    uint64_t dims[5] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, phases, (uint64_t)B};
+    uint64_t st[4] = {(uint64_t)C * 2, (uint64_t)C * 2 * W, (uint64_t)C * 2 * W * H, (uint64_t)C * 2 * W * H * phases};
+    uint32_t box[5] = {64, (uint32_t)W, (uint32_t)box_h, 1, (uint32_t)box_b};
+    if ((rc = make_map(&ma_hi, a, 5, dims, st, box))) return rc;
+    if ((rc = make_map(&ma_lo, a + p->a_plane_stride, 5, dims, st, box))) return rc;
   } else {
     const int H = p->H, W = p->W, B = p->B, C = p->C;
     const uint64_t phases = (p->mode == SDB_A_CONV3S2) ? 4 : 1;   // phase-split input [B][4][H][W][C]
@@ -618,7 +700,13 @@ extern "C" int sdb_gemm(const SdbGemm* p, void* stream) {
     if ((rc = make_map(&ma_hi, a, 5, dims, st, box))) return rc;
     if ((rc = make_map(&ma_lo, a + p->a_plane_stride, 5, dims, st, box))) return rc;
   }
-  {
+  if (wgrad_mode) {   // dY rows [K = pixels][N], N contiguous: 64 x 64 boxes
+    uint64_t dims[2] = {(uint64_t)p->N, (uint64_t)p->K};
+    uint64_t st[1] = {(uint64_t)p->N * 2};
+    uint32_t box[2] = {64, BK};
+    if ((rc = make_map(&mb_hi, w, 2, dims, st, box))) return rc;
+    if ((rc = make_map(&mb_lo, w + (long long)p->N * p->K, 2, dims, st, box))) return rc;
+  } else {
     uint64_t dims[2] = {(uint64_t)p->K, (uint64_t)p->N};
     uint64_t st[1] = {(uint64_t)p->K * 2};
     uint32_t box[2] = {BK, (uint32_t)g.bnl};

@@ -217,6 +217,18 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
+// MN-major operand, SWIZZLE_128B: canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units -- atoms of
+// [8 K-rows][64 MN elements = 128 B] (what a TMA box {64 inner, rows} produces), K atoms SBO = 1024 B apart,
+// 64-element MN blocks LBO = 8192 B apart (one [64 K-rows][128 B] box per block).
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(8192 >> 4) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
 // Instruction descriptor, kind::f16: fp16 A/B (format 0), fp32 D (c_format 1), both K-major, dense.
 __host__ __device__ __forceinline__ uint32_t umma_idesc_f16(int M, int N) {
   return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);

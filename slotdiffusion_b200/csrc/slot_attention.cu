@@ -205,14 +205,15 @@ slot_attend_kernel(const float* __restrict__ kv, const float* __restrict__ q, fl
 
 // updates[b,s,:] = sum_chunks part_upd / sum_chunks part_cs  -> packed (+ fp32)
 __global__ void slot_attend_finalize_kernel(const float* __restrict__ part_upd, const float* __restrict__ part_cs,
-                                            __half* __restrict__ out, float* __restrict__ upd32, int64_t BS, int S,
-                                            int D, int chunks) {
+                                            __half* __restrict__ out, float* __restrict__ upd32,
+                                            float* __restrict__ colsum, int64_t BS, int S, int D, int chunks) {
   const int64_t bs = blockIdx.x;
   const int64_t b = bs / S;
   const int s = (int)(bs % S);
   float cs = 0.f;
   for (int c = 0; c < chunks; ++c) cs += part_cs[(b * chunks + c) * S + s];
   const float inv = 1.f / cs;
+  if (colsum && threadIdx.x == 0) colsum[bs] = cs;
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
     float v = 0.f;
     for (int c = 0; c < chunks; ++c) v += part_upd[((b * chunks + c) * S + s) * D + d];
@@ -263,6 +264,12 @@ extern "C" int64_t sdb_slot_attend_workspace(int64_t B, int64_t N, int64_t S, in
 extern "C" int sdb_slot_attend(const float* kv, const float* q, float* seg_mask, void* upd_packed, float* upd32,
                                float* work, int64_t B, int64_t N, int64_t S, int64_t D, float scale, float eps,
                                void* stream) {
+  return sdb_slot_attend_train(kv, q, seg_mask, upd_packed, upd32, nullptr, work, B, N, S, D, scale, eps, stream);
+}
+
+extern "C" int sdb_slot_attend_train(const float* kv, const float* q, float* seg_mask, void* upd_packed, float* upd32,
+                                     float* colsum, float* work, int64_t B, int64_t N, int64_t S, int64_t D, float scale,
+                                     float eps, void* stream) {
   SDB_REQUIRE(kv && q && upd_packed && work, "sdb_slot_attend: null argument");
   SDB_REQUIRE(B > 0 && B <= 65535 && N > 0, "sdb_slot_attend: bad B=%lld N=%lld", (long long)B, (long long)N);
   SDB_REQUIRE(S >= 1 && S <= 32, "sdb_slot_attend: num_slots=%lld must be in 1..32", (long long)S);
@@ -285,8 +292,8 @@ extern "C" int sdb_slot_attend(const float* kv, const float* q, float* seg_mask,
   SA_CASE(64, 64) else SA_CASE(128, 64) else SA_CASE(192, 32) else SA_CASE(256, 32)
 #undef SA_CASE
   if (rc) return rc;
-  slot_attend_finalize_kernel<<<(unsigned)(B * S), 128, 0, st>>>(part_upd, part_cs, (__half*)upd_packed, upd32, B * S,
-                                                                 (int)S, (int)D, chunks);
+  slot_attend_finalize_kernel<<<(unsigned)(B * S), 128, 0, st>>>(part_upd, part_cs, (__half*)upd_packed, upd32, colsum,
+                                                                 B * S, (int)S, (int)D, chunks);
   SDB_LAUNCH_CHECK();
   return 0;
 }

@@ -43,19 +43,20 @@ def _f32(t, name='tensor'):
 
 
 class Packed:
-    """GEMM operand: fp16 [2][rows][K] (hi plane, lo plane)."""
-    __slots__ = ('t', 'rows', 'K')
+    """GEMM operand: 16-bit [2][rows][K] (hi plane, lo plane); fp16 split, or bf16 split for gradient operands."""
+    __slots__ = ('t', 'rows', 'K', 'bf16')
 
-    def __init__(self, t, rows, K):
-        self.t, self.rows, self.K = t, rows, K
+    def __init__(self, t, rows, K, bf16=False):
+        self.t, self.rows, self.K, self.bf16 = t, rows, K, bf16
 
     @staticmethod
-    def empty(rows, K, device):
-        return Packed(torch.empty(2 * rows * K, dtype=torch.float16, device=device), rows, K)
+    def empty(rows, K, device, bf16=False):
+        return Packed(torch.empty(2 * rows * K, dtype=torch.float16, device=device), rows, K, bf16)
 
     def unpack(self):
         """fp32 value of the operand (tests only)."""
-        t = self.t.view(2, self.rows, self.K).float()
+        t = self.t.view(torch.bfloat16) if self.bf16 else self.t
+        t = t.view(2, self.rows, self.K).float()
         return t[0] + t[1]
 
 
@@ -237,6 +238,7 @@ def gemm(a, w, bias=None, rowvec=None, rows_per_group=0, residual=None, relu=Fal
         g.out_act = _ACTS[pack_out]
     g.gsum = gsum.data_ptr() if gsum is not None else None
     g.geglu = int(geglu)
+    g.a_bf16, g.w_bf16 = int(a.bf16), int(w.bf16)
     check(lib().sdb_gemm(ctypes.byref(g), _stream()), 'sdb_gemm')
     if geglu:
         return packed
@@ -335,3 +337,219 @@ def lincomb(x, m0, m1, a, b, c=0.0, out=None):
     check(lib().sdb_lincomb(_p(out), _p(x), _p(m0), _p(m1), float(a), float(b), float(c), x.numel(), _stream()),
           'sdb_lincomb')
     return out
+
+
+# ================================================================== backward (training) wrappers
+from ._lib import SDB_A_WGRAD, SDB_A_WGRAD_S2  # noqa: E402
+
+
+def grad_pack(dy, want_rows=True, want_T=True, bias_grad=None, group_grad=None, rows_per_group=0):
+    """dy [M,N] fp32 (last dim contiguous) -> (Packed [M,N] | None, Packed [N,M] | None); bias_grad[N] += colsum(dy);
+    group_grad[M // rows_per_group, N] += per-group column sums."""
+    assert dy.dim() == 2 and dy.stride(1) == 1
+    M, N = dy.shape
+    rows = Packed.empty(M, N, dy.device, bf16=True) if want_rows else None
+    tr = _packed_T(N, M, dy.device, bf16=True) if want_T else None
+    check(lib().sdb_grad_pack(_p(dy), dy.stride(0), _p(rows.t) if rows else None, _p(tr.t) if tr else None,
+                              tr.K if tr else 0, _p(bias_grad), _p(group_grad),
+                              group_grad.stride(0) if group_grad is not None else 0, M, N, rows_per_group, _stream()),
+          'sdb_grad_pack')
+    return rows, tr
+
+
+def _packed_T(rows, M, device, bf16=False):
+    """Transposed operand [rows, M]: the contraction length is padded to a multiple of 8 (16-byte TMA rows); padding
+    columns are zero in BOTH operands of the wgrad GEMM, so they contribute nothing."""
+    Kp = (M + 7) // 8 * 8
+    if Kp == M:
+        return Packed.empty(rows, M, device, bf16)
+    return Packed(torch.zeros(2 * rows * Kp, dtype=torch.float16, device=device), rows, Kp, bf16)
+
+
+def transpose_packed(a, to_bf16=False):
+    """Packed [M,K] -> Packed [K, M(+pad)]; to_bf16 re-splits an fp16 operand as bf16 (backward GEMMs run bf16 x bf16)."""
+    conv = to_bf16 and not a.bf16
+    out = _packed_T(a.K, a.rows, a.t.device, a.bf16 or to_bf16)
+    check(lib().sdb_transpose_packed(_p(a.t), _p(out.t), out.K, a.rows, a.K, int(conv), _stream()),
+          'sdb_transpose_packed')
+    return out
+
+
+def repack_bf16(a):
+    """fp16-split Packed -> bf16-split Packed (same shape)."""
+    if a.bf16:
+        return a
+    out = Packed.empty(a.rows, a.K, a.t.device, bf16=True)
+    check(lib().sdb_repack_bf16(_p(a.t), _p(out.t), a.rows * a.K, _stream()), 'sdb_repack_bf16')
+    return out
+
+
+def pack_weight_T(w):
+    """W [N,K] fp32 -> Packed [K,N] bf16 split (operand of dX = dY W next to the bf16 gradient operand)."""
+    w2 = w.reshape(w.shape[0], -1).contiguous()
+    return transpose_packed(pack_weight(w2), to_bf16=True)
+
+
+def pack_weight_conv3_dgrad(w):
+    Cout, Cin = w.shape[0], w.shape[1]
+    out = Packed.empty(Cin, 9 * Cout, w.device, bf16=True)
+    check(lib().sdb_pack_weight_conv3_dgrad(_p(w), _p(out.t), Cout, Cin, 1, _stream()), 'sdb_pack_weight_conv3_dgrad')
+    return out
+
+
+def wgrad_conv3_scatter(c9, dw, Cin, accumulate=False):
+    Cout, Cin_w = dw.shape[0], dw.shape[1]
+    check(lib().sdb_wgrad_conv3_scatter(_p(c9), c9.stride(0), _p(dw), Cout, Cin, Cin_w, int(accumulate), _stream()),
+          'sdb_wgrad_conv3_scatter')
+
+
+def gemm_wgrad_conv(x, dy, B, H, W, C, stride2=False, passes=None):
+    """Conv weight gradient: x Packed NHWC activation [B*H_in*W_in, C] (the operand the forward conv consumed; the phase
+    split for stride 2), dy Packed rows [B*H*W, Cout] -> c9 fp32 [9*C, Cout] (row = tap*C + ci).  H, W = OUTPUT size."""
+    Mpix, Cout = dy.rows, dy.K
+    assert Mpix == B * H * W and x.K == C
+    if dy.bf16 and not x.bf16:
+        x = repack_bf16(x)
+    out = torch.empty(9 * C, Cout, dtype=torch.float32, device=dy.t.device)
+    g = SdbGemm()
+    g.a, g.w, g.c = x.t.data_ptr(), dy.t.data_ptr(), out.data_ptr()
+    g.a_plane_stride = x.rows * x.K
+    g.ldc = Cout
+    g.M, g.N, g.K = 9 * C, Cout, Mpix
+    g.mode = SDB_A_WGRAD_S2 if stride2 else SDB_A_WGRAD
+    g.B, g.H, g.W, g.C = B, H, W, C
+    g.passes = passes or _PASSES
+    g.a_bf16, g.w_bf16 = int(x.bf16), int(dy.bf16)
+    check(lib().sdb_gemm(ctypes.byref(g), _stream()), 'sdb_gemm(wgrad)')
+    return out
+
+
+def add3(a, b=None, c=None, out=None):
+    if out is None:
+        out = torch.empty_like(a)
+    assert a.is_contiguous() and (b is None or b.is_contiguous()) and (c is None or c.is_contiguous())
+    check(lib().sdb_add3(_p(out), _p(a), _p(b), _p(c), a.numel(), _stream()), 'sdb_add3')
+    return out
+
+
+def act_bwd(dy, pre, act):
+    """dx = dy * act'(pre); dy, pre 2-D (strided rows ok); act 'silu' | 'relu'."""
+    M, N = dy.shape
+    dx = torch.empty(M, N, dtype=torch.float32, device=dy.device)
+    check(lib().sdb_act_bwd(_p(dy), dy.stride(0), _p(pre), pre.stride(0), _p(dx), N, M, N, _ACTS[act], _stream()),
+          'sdb_act_bwd')
+    return dx
+
+
+def groupnorm_pack_dropout(x1, x2, gamma, beta, stats, B, HW, G, silu, drop_p, seed):
+    C1 = x1.shape[-1]
+    C2 = x2.shape[-1] if x2 is not None else 0
+    out = Packed.empty(B * HW, C1 + C2, x1.device)
+    check(lib().sdb_groupnorm_apply_pack_dropout(_p(x1), C1, _p(x2), C2, _p(stats), _p(gamma), _p(beta), _p(out.t), B,
+                                                 HW, G, int(silu), float(drop_p), int(seed), _stream()),
+          'sdb_groupnorm_apply_pack_dropout')
+    return out
+
+
+def groupnorm_bwd(x1, x2, da, stats, gamma, beta, dgamma, dbeta, B, HW, G, silu, add1=None, add2=None, drop_p=0.0,
+                  seed=0):
+    """-> (dx1, dx2 | None); dgamma/dbeta accumulated in place."""
+    C1 = x1.shape[-1]
+    C2 = x2.shape[-1] if x2 is not None else 0
+    work = torch.empty(B * (C1 + C2) * 2, dtype=torch.float32, device=x1.device)
+    dx1 = torch.empty_like(x1)
+    dx2 = torch.empty_like(x2) if x2 is not None else None
+    check(lib().sdb_groupnorm_bwd(_p(x1), C1, _p(x2), C2, _p(da), _p(stats), _p(gamma), _p(beta), _p(work), _p(dx1),
+                                  _p(dx2), _p(add1), _p(add2), _p(dgamma), _p(dbeta), B, HW, G, int(silu),
+                                  float(drop_p), int(seed), _stream()), 'sdb_groupnorm_bwd')
+    return dx1, dx2
+
+
+def layernorm_bwd(x, dn, gamma, eps, dgamma, dbeta, add=None):
+    M, C = x.shape
+    dx = torch.empty_like(x)
+    check(lib().sdb_layernorm_bwd(_p(x), _p(dn), _p(gamma), eps, _p(add), _p(dx), _p(dgamma), _p(dbeta), M, C,
+                                  _stream()), 'sdb_layernorm_bwd')
+    return dx
+
+
+def attention_bwd(q, k, v, dout, dq, dk, dv, B, Lq, Lk, heads, d, scale):
+    """All 2-D strided views [B*L, heads*d]; dq/dk/dv are written (views into the caller's gradient buffers)."""
+    work = torch.empty(2 * B * heads * Lq, dtype=torch.float32, device=q.device)
+    check(lib().sdb_attention_bwd(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(dout), dout.stride(0),
+                                  _p(dq), dq.stride(0), _p(dk), dk.stride(0), _p(dv), dv.stride(0), _p(work), B, Lq, Lk,
+                                  heads, d, scale, _stream()), 'sdb_attention_bwd')
+
+
+def geglu_bwd(u, dg):
+    M, F2 = u.shape
+    du = torch.empty_like(u)
+    check(lib().sdb_geglu_bwd(_p(u), _p(dg), _p(du), M, F2 // 2, _stream()), 'sdb_geglu_bwd')
+    return du
+
+
+def up2_adjoint(dup, B, H, W, C):
+    dx = torch.empty(B * H * W, C, dtype=torch.float32, device=dup.device)
+    check(lib().sdb_up2_adjoint(_p(dup), _p(dx), B, H, W, C, _stream()), 'sdb_up2_adjoint')
+    return dx
+
+
+def pack_zero_up2(dy, B, H, W, C):
+    out = Packed.empty(B * 4 * H * W, C, dy.device, bf16=True)
+    check(lib().sdb_pack_zero_up2(_p(dy), _p(out.t), B, H, W, C, _stream()), 'sdb_pack_zero_up2')
+    return out
+
+
+def pack_nchw_pad(x, Cp):
+    B, Cs = x.shape[:2]
+    HW = x[0, 0].numel()
+    out = Packed.empty(B * HW, Cp, x.device)
+    check(lib().sdb_pack_nchw_pad(_p(x.contiguous()), _p(out.t), B, Cs, HW, Cp, _stream()), 'sdb_pack_nchw_pad')
+    return out
+
+
+def nhwc_to_nchw(rows, B, Cs, H, W):
+    out = torch.empty(B, Cs, H, W, dtype=torch.float32, device=rows.device)
+    check(lib().sdb_nhwc_to_nchw(_p(rows), rows.stride(0), _p(out), B, Cs, H * W, _stream()), 'sdb_nhwc_to_nchw')
+    return out
+
+
+def nchw_to_nhwc_pad(x, Cp):
+    B, Cs = x.shape[:2]
+    HW = x[0, 0].numel()
+    out = torch.empty(B * HW, Cp, dtype=torch.float32, device=x.device)
+    check(lib().sdb_nchw_to_nhwc_pad(_p(x.contiguous()), _p(out), B, Cs, HW, Cp, _stream()), 'sdb_nchw_to_nhwc_pad')
+    return out
+
+
+def im2col_T(a, B, H, W, C):
+    out = Packed.empty(9 * C, B * H * W, a.t.device)
+    check(lib().sdb_im2col_t(_p(a.t), _p(out.t), B, H, W, C, _stream()), 'sdb_im2col_t')
+    return out
+
+
+def gru_gates_bwd(gi, gh, h, dh_new):
+    dgi, dgh, dh = torch.empty_like(gi), torch.empty_like(gh), torch.empty_like(h)
+    R, D = h.shape
+    check(lib().sdb_gru_gates_bwd(_p(gi), _p(gh), _p(h), _p(dh_new), _p(dgi), _p(dgh), _p(dh), R, D, _stream()),
+          'sdb_gru_gates_bwd')
+    return dgi, dgh, dh
+
+
+def slot_attend_train(kv, q, B, N, S, D, scale, eps, want_mask):
+    ws = lib().sdb_slot_attend_workspace(B, N, S, D)
+    work = torch.empty(ws // 4, dtype=torch.float32, device=kv.device)
+    mask = torch.empty(B, S, N, dtype=torch.float32, device=kv.device) if want_mask else None
+    upd = Packed.empty(B * S, D, kv.device)
+    upd32 = torch.empty(B * S, D, dtype=torch.float32, device=kv.device)
+    cs = torch.empty(B * S, dtype=torch.float32, device=kv.device)
+    check(lib().sdb_slot_attend_train(_p(kv), _p(q), _p(mask), _p(upd.t), _p(upd32), _p(cs), _p(work), B, N, S, D, scale,
+                                      eps, _stream()), 'sdb_slot_attend_train')
+    return upd, mask, upd32, cs
+
+
+def slot_attend_bwd(kv, q, upd32, cs, d_upd, dkv, B, N, S, D, scale, eps, accumulate):
+    dq = torch.empty(B * S, D, dtype=torch.float32, device=kv.device)
+    check(lib().sdb_slot_attend_bwd(_p(kv), _p(q), _p(upd32), _p(cs), _p(d_upd), _p(dkv), _p(dq), B, N, S, D, scale, eps,
+                                    int(accumulate), _stream()), 'sdb_slot_attend_bwd')
+    return dq
