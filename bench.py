@@ -187,6 +187,12 @@ def run_ours(args):
     roof = gemm_roofline(unet, sampler, B, dev)
     sa_ms = time_sa(sa, feats_d, slots0)
 
+    train = None
+    if not args.no_train:
+        del feats_d, noise_d
+        torch.cuda.empty_cache()
+        train = train_bench(args, dev, world, rank)
+
     if rank == 0:
         peaks, peak_src = load_peaks()
         units = B * NFE * world * args.steps
@@ -222,10 +228,103 @@ def run_ours(args):
                          'gemm_share_of_unet_time': roof['ms'] / (ms / args.steps / NFE), 'launches': roof['launches'],
                          'how': 'all %d GEMM launches of one UNet evaluation replayed from a CUDA graph, CUDA events' % roof['launches']},
             'cpu_baseline': cpu_baseline(sample_nfe=NFE, batch=2),
+            'train': train,
         }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def train_bench(args, dev, world, rank):
+    """One TRAINING step of the hot path (LDM.loss_function shape, ldm.py:59-83): slots = SlotAttention(features);
+    x_t = q_sample(x0, t, eps); loss = mse(UNet(x_t, t, slots), eps); backward through both modules (hand-written
+    kernels), data-parallel gradient all-reduce, Adam step.  Encoder features and VQ-VAE latents are synthetic inputs
+    (both encoders are out of scope)."""
+    import torch.distributed as dist
+    from slotdiffusion_b200 import parallel
+    from slotdiffusion_b200.slot_attention import SlotAttentionWMask
+    from slotdiffusion_b200.unet import UNetModel
+    B = args.train_batch
+    torch.manual_seed(rank)
+    sa = SlotAttentionWMask(D, SA_ITERS, S, D, 2 * D).to(dev).train()
+    unet = UNetModel(in_channels=3, model_channels=128, out_channels=3, num_res_blocks=2,
+                     attention_resolutions=(8, 4, 2), dropout=0.1, channel_mult=(1, 2, 3, 4), dims=2,
+                     use_checkpoint=False, num_head_channels=32, resblock_updown=False, conv_resample=True,
+                     transformer_depth=1, context_dim=D, n_embed=None).to(dev).train()
+    with torch.no_grad():
+        for p in unet.parameters():
+            if p.abs().max() == 0:
+                p.normal_(0, 0.02)
+    init_slots = torch.nn.Parameter(torch.randn(1, S, D, device=dev))
+    params = list(sa.parameters()) + list(unet.parameters()) + [init_slots]
+    if world > 1:
+        for p in params:
+            dist.broadcast(p.data, 0)
+        parallel.enable_grad_allreduce()
+    opt = torch.optim.Adam(params, lr=1e-4, fused=True)
+    betas = (torch.linspace(0.0015 ** 0.5, 0.0195 ** 0.5, 1000, dtype=torch.float64) ** 2)
+    acp = torch.cumprod(1 - betas, 0).float().to(dev)
+    g = torch.Generator().manual_seed(4321 + rank)
+    feats_h = torch.randn(B, N_TOK, D, generator=g).pin_memory()
+    x0_h = torch.randn(B, 3, 32, 32, generator=g).pin_memory()
+    feats_d, x0_d = feats_h.to(dev), x0_h.to(dev)
+
+    def step(feats, x0):
+        t = torch.randint(0, 1000, (B,), device=dev)
+        eps = torch.randn_like(x0)
+        a = acp[t].view(B, 1, 1, 1)
+        xt = a.sqrt() * x0 + (1 - a).sqrt() * eps                    # q_sample, ddpm.py:161-165 (caller side)
+        slots, _ = sa(feats, init_slots.expand(B, -1, -1))
+        loss = torch.nn.functional.mse_loss(unet(xt, t, context=slots), eps)
+        loss.backward()
+        if world > 1 and init_slots.grad is not None:
+            dist.all_reduce(init_slots.grad, op=dist.ReduceOp.AVG)
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        return loss
+
+    def timed(fn, steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            tt = torch.tensor([ms], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = tt.item()
+        return ms
+    from slotdiffusion_b200 import _lib
+    for _ in range(max(args.warmup, 3)):
+        step(feats_d, x0_d)
+    torch.cuda.synchronize()
+    n0 = _lib.launch_count()
+    ms = timed(lambda: step(feats_d, x0_d), args.train_steps)
+    launches = _lib.launch_count() - n0
+    out = {}
+
+    def e2e_step():
+        loss = step(feats_h.to(dev, non_blocking=True), x0_h.to(dev, non_blocking=True))
+        out['loss'] = loss.item()                                    # device -> host read of the step result
+    ms_e2e = timed(e2e_step, args.train_steps)
+    if world > 1:
+        parallel.disable_grad_allreduce()
+    fl = B * (3 * UNET_FLOP_PER_SAMPLE + 3 * 203.7e6)                # fwd + bwd (dgrad + wgrad) of the two hot modules
+    return {'metric': 'train_step_samples_per_sec', 'value': B * world * args.train_steps / (ms / 1e3), 'unit': 'samples/s',
+            'ms_per_step': ms / args.train_steps, 'per_gpu_batch': B, 'global_batch': B * world,
+            'e2e_value': B * world * args.train_steps / (ms_e2e / 1e3),
+            'h2d_bytes_per_step': (feats_h.numel() + x0_h.numel()) * 4, 'd2h_bytes_per_step': 4,
+            'gpu_launches_per_step': launches // args.train_steps, 'loss': out.get('loss'),
+            'algorithmic_tflops': fl * args.train_steps / (ms / 1e3) / 1e12,
+            'what': 'SlotAttention(3 it) + UNet(134M) forward+backward (dropout 0.1) + gradient all-reduce + fused Adam; '
+                    'encoder features / VQ latents synthetic'}
 
 
 def profile_once(args):
@@ -399,6 +498,9 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--batch', type=int, default=64, help='per-GPU batch')
+    ap.add_argument('--train-batch', type=int, default=32, help='per-GPU batch of the training-step measurement')
+    ap.add_argument('--train-steps', type=int, default=5)
+    ap.add_argument('--no-train', action='store_true', help='skip the training-step measurement')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--profile-once', action='store_true',
                     help='ncu helper: SlotAttention + ONE un-captured UNet evaluation (after one warm-up pass), no timing')

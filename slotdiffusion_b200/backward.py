@@ -13,7 +13,7 @@ import itertools
 
 import torch
 
-from . import ops
+from . import ops, parallel
 from .ops import (SDB_A_CONV3, SDB_A_CONV3S2, SDB_PACK_PHASE2, SDB_PACK_PLAIN, SDB_PACK_UP2)
 
 _step_counter = itertools.count(1)
@@ -537,6 +537,8 @@ class UNetFn(torch.autograd.Function):
         tr = ctx.trainer
         dx, dctx = tr.backward(ctx.tape, ctx.y, dy, ctx.x_shape, ctx.need_dx)
         ctx.tape = None
+        if parallel.enabled():              # one all-reduce of the whole flat gradient buffer (data parallel)
+            parallel.allreduce_flat(tr.G.flat, async_op=False)
         grads = tuple(tr.G.view(p) if p.requires_grad else None for p in ctx.params)
         dcontext = dctx.view(ctx.ctx_shape) if dctx is not None and ctx.needs_input_grad[3] else None
         return (None, dx, None, dcontext) + grads
@@ -653,6 +655,8 @@ class SlotAttentionFn(torch.autograd.Function):
         dx = tp.pop(ctx.x)
         ds0 = tp.pop(ctx.s0)
         ctx.tape = None
+        if parallel.enabled():
+            parallel.allreduce_flat(G.flat, async_op=False)
         grads = tuple(G.view(p) if p.requires_grad else None for p in ctx.params)
         dx = dx.view(ctx.shapes[0]) if dx is not None and ctx.needs_input_grad[2] else None
         ds0 = ds0.view(ctx.shapes[1]) if ds0 is not None and ctx.needs_input_grad[3] else None

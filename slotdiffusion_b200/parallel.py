@@ -1,0 +1,68 @@
+"""Data-parallel training support: batch sharding with ONE gradient all-reduce per module and step.
+
+The reference trains with DistributedDataParallel inside the un-vendored `nerv` trainer (scripts/train.py:21-27,65-73:
+`--ddp`, one process per GPU, NCCL).  Every hot-path op is per-sample (GroupNorm / LayerNorm only, no BatchNorm), so
+the only exchange is the sum of parameter gradients.  The backward of each hand-written module produces all of its
+parameter gradients in ONE flat fp32 buffer (backward.GradBuffer); when a process group is registered here that buffer
+is averaged across ranks with a single all-reduce enqueued the moment the module's backward has finished (537 MB for
+the UNet: ~1 ms on NVLink 5 / NVSwitch against a >100 ms step, so it is issued in stream order rather than bucketed).
+Works with any torch.distributed backend (gloo in the CPU tests, nccl on the B200 box).
+"""
+import torch
+import torch.distributed as dist
+
+_group = None
+_enabled = False
+_pending = []
+
+
+def enable_grad_allreduce(group=None):
+    """Average the parameter gradients of the B200 modules across `group` (default: the world) in their backward.
+    Do NOT also wrap those modules in DistributedDataParallel."""
+    global _group, _enabled
+    if not dist.is_initialized():
+        raise RuntimeError('torch.distributed is not initialised')
+    _group, _enabled = group, True
+
+
+def disable_grad_allreduce():
+    global _enabled
+    _enabled = False
+    wait_all()
+
+
+def enabled():
+    return _enabled and dist.is_initialized() and dist.get_world_size(_group) > 1
+
+
+def allreduce_flat(flat, async_op=True):
+    """Average `flat` (a 1-D gradient buffer) over the group; returns immediately when async_op (see wait_all)."""
+    if not enabled():
+        return None
+    world = dist.get_world_size(_group)
+    if flat.is_cuda:
+        work = dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=_group, async_op=async_op)
+    else:                                  # gloo has no AVG
+        work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=_group, async_op=False)
+        flat.div_(world)
+        work = None
+    if work is not None and async_op:
+        _pending.append(work)
+    return work
+
+
+def wait_all():
+    """Block the current stream on every outstanding gradient all-reduce (call before the optimizer step; the modules'
+    backward already does it before returning gradients to autograd)."""
+    while _pending:
+        _pending.pop().wait()
+
+
+def shard_batch(global_batch, rank=None, world=None):
+    """[start, end) of this rank's samples/clips (clips, never frames: frames are sequentially dependent)."""
+    rank = dist.get_rank(_group) if rank is None else rank
+    world = dist.get_world_size(_group) if world is None else world
+    per = global_batch // world
+    rem = global_batch % world
+    start = rank * per + min(rank, rem)
+    return start, start + per + (1 if rank < rem else 0)
