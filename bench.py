@@ -261,15 +261,18 @@ def train_bench(args, dev, world, rank):
         for p in params:
             dist.broadcast(p.data, 0)
         parallel.enable_grad_allreduce()
-    opt = torch.optim.Adam(params, lr=1e-4, fused=True)
+    use_graph = not args.no_train_graph
+    opt = torch.optim.Adam(params, lr=1e-4, fused=True, capturable=use_graph)
     betas = (torch.linspace(0.0015 ** 0.5, 0.0195 ** 0.5, 1000, dtype=torch.float64) ** 2)
     acp = torch.cumprod(1 - betas, 0).float().to(dev)
     g = torch.Generator().manual_seed(4321 + rank)
     feats_h = torch.randn(B, N_TOK, D, generator=g).pin_memory()
     x0_h = torch.randn(B, 3, 32, 32, generator=g).pin_memory()
     feats_d, x0_d = feats_h.to(dev), x0_h.to(dev)
+    from slotdiffusion_b200 import _lib, ops
 
     def step(feats, x0):
+        ops.dropout_step_counter(dev).add_(1)                        # new dropout masks every step (also under replay)
         t = torch.randint(0, 1000, (B,), device=dev)
         eps = torch.randn_like(x0)
         a = acp[t].view(B, 1, 1, 1)
@@ -301,17 +304,57 @@ def train_bench(args, dev, world, rank):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             ms = tt.item()
         return ms
-    from slotdiffusion_b200 import _lib
-    for _ in range(max(args.warmup, 3)):
+
+    # launches per step: counted on eager steps (graph replays do not pass through the C ABI again)
+    for _ in range(2):
         step(feats_d, x0_d)
     torch.cuda.synchronize()
     n0 = _lib.launch_count()
-    ms = timed(lambda: step(feats_d, x0_d), args.train_steps)
+    step(feats_d, x0_d)
+    torch.cuda.synchronize()
     launches = _lib.launch_count() - n0
+    mode = 'eager'
+    run = step
+    if use_graph:
+        # the caller captures the WHOLE step (forward, backward, all-reduce, Adam) in one CUDA graph: every kernel of
+        # the library is enqueue-only and allocation-free, weight re-packing is part of the captured step
+        try:
+            sf, sx = feats_d.clone(), x0_d.clone()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    step(sf, sx)
+            torch.cuda.current_stream().wait_stream(side)
+            sa._wcache.clear()
+            unet._exec.wc.clear()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_loss = step(sf, sx)
+
+            def run(feats, x0):
+                if feats is not sf:
+                    sf.copy_(feats, non_blocking=True)
+                    sx.copy_(x0, non_blocking=True)
+                graph.replay()
+                return static_loss
+            run(sf, sx)
+            torch.cuda.synchronize()
+            mode = 'cuda-graph (whole step captured by the caller)'
+        except Exception as e:                                         # noqa: BLE001
+            print('train: CUDA-graph capture failed, timing the eager step:', repr(e)[:300], file=sys.stderr)
+            torch.cuda.synchronize()
+            run, mode = step, 'eager'
+            feats_d2, x0_d2 = feats_d, x0_d
+    first = run(feats_d, x0_d) if mode == 'eager' else None
+    for _ in range(max(args.warmup, 3)):
+        run(feats_d, x0_d)
+    ms = timed(lambda: run(feats_d, x0_d), args.train_steps)
     out = {}
 
     def e2e_step():
-        loss = step(feats_h.to(dev, non_blocking=True), x0_h.to(dev, non_blocking=True))
+        loss = run(feats_h.to(dev, non_blocking=True), x0_h.to(dev, non_blocking=True)) if mode == 'eager' \
+            else run(feats_h, x0_h)
         out['loss'] = loss.item()                                    # device -> host read of the step result
     ms_e2e = timed(e2e_step, args.train_steps)
     if world > 1:
@@ -321,7 +364,7 @@ def train_bench(args, dev, world, rank):
             'ms_per_step': ms / args.train_steps, 'per_gpu_batch': B, 'global_batch': B * world,
             'e2e_value': B * world * args.train_steps / (ms_e2e / 1e3),
             'h2d_bytes_per_step': (feats_h.numel() + x0_h.numel()) * 4, 'd2h_bytes_per_step': 4,
-            'gpu_launches_per_step': launches // args.train_steps, 'loss': out.get('loss'),
+            'gpu_launches_per_step': launches, 'loss': out.get('loss'), 'mode': mode,
             'algorithmic_tflops': fl * args.train_steps / (ms / 1e3) / 1e12,
             'what': 'SlotAttention(3 it) + UNet(134M) forward+backward (dropout 0.1) + gradient all-reduce + fused Adam; '
                     'encoder features / VQ latents synthetic'}
@@ -498,9 +541,10 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--batch', type=int, default=64, help='per-GPU batch')
-    ap.add_argument('--train-batch', type=int, default=32, help='per-GPU batch of the training-step measurement')
+    ap.add_argument('--train-batch', type=int, default=64, help='per-GPU batch of the training-step measurement')
     ap.add_argument('--train-steps', type=int, default=5)
     ap.add_argument('--no-train', action='store_true', help='skip the training-step measurement')
+    ap.add_argument('--no-train-graph', action='store_true', help='time the eager training step (no CUDA graph)')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--profile-once', action='store_true',
                     help='ncu helper: SlotAttention + ONE un-captured UNet evaluation (after one warm-up pass), no timing')

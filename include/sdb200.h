@@ -118,10 +118,11 @@ int sdb_groupnorm_apply_pack_fused(const float* x1, int64_t C1, const float* gsu
                                    const float* gsum2, const float* stats, const float* gamma, const float* beta,
                                    void* out, int64_t B, int64_t HW, int G, float eps, int silu, void* stream);
 /* training form: nn.Dropout(p) after the SiLU (ResBlock out_layers, unet.py:245-246) with a counter-based mask
- * (seed, element index) that sdb_groupnorm_bwd regenerates; stats [B,G,2] required. */
+ * (seed, element index) that sdb_groupnorm_bwd regenerates; stats [B,G,2] required.  seed_dev (optional): device
+ * pointer to a per-step counter mixed into the seed, so a CUDA-graph-captured step draws a new mask per replay. */
 int sdb_groupnorm_apply_pack_dropout(const float* x1, int64_t C1, const float* x2, int64_t C2, const float* stats,
                                      const float* gamma, const float* beta, void* out, int64_t B, int64_t HW, int G,
-                                     int silu, float drop_p, uint64_t seed, void* stream);
+                                     int silu, float drop_p, uint64_t seed, const uint64_t* seed_dev, void* stream);
 /* partial sums -> stats [B,G,2] (mean, rstd) */
 int sdb_groupnorm_finalize(const float* gsum1, int64_t C1, const float* gsum2, int64_t C2, float* stats, int64_t B,
                            int64_t HW, int G, float eps, void* stream);
@@ -222,7 +223,7 @@ int sdb_act_bwd(const float* dy, int64_t ldy, const float* pre, int64_t ldp, flo
 int sdb_groupnorm_bwd(const float* x1, int64_t C1, const float* x2, int64_t C2, const float* da, const float* stats,
                       const float* gamma, const float* beta, float* sums_work, float* dx1, float* dx2, const float* add1,
                       const float* add2, float* dgamma, float* dbeta, int64_t B, int64_t HW, int G, int silu, float drop_p,
-                      uint64_t seed, void* stream);
+                      uint64_t seed, const uint64_t* seed_dev, void* stream);
 /* LayerNorm backward: dx = LN'(x) dn (+ add); dgamma/dbeta accumulated (+=) */
 int sdb_layernorm_bwd(const float* x, const float* dn, const float* gamma, float eps, const float* add, float* dx,
                       float* dgamma, float* dbeta, int64_t M, int64_t C, void* stream);

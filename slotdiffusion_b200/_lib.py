@@ -61,7 +61,7 @@ SIGNATURES = {
     'sdb_slot_attend_train': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                       c_int64, c_int64, c_int64, c_float, c_float, c_void_p]),
     'sdb_groupnorm_apply_pack_dropout': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
-                                                 c_void_p, c_int64, c_int64, c_int, c_int, c_float, c_uint64, c_void_p]),
+                                                 c_void_p, c_int64, c_int64, c_int, c_int, c_float, c_uint64, c_void_p, c_void_p]),
     'sdb_grad_pack': (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64,
                               c_int64, c_int, c_void_p]),
     'sdb_transpose_packed': (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p]),
@@ -73,7 +73,7 @@ SIGNATURES = {
                             c_void_p]),
     'sdb_groupnorm_bwd': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int,
-                                  c_int, c_float, c_uint64, c_void_p]),
+                                  c_int, c_float, c_uint64, c_void_p, c_void_p]),
     'sdb_layernorm_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_int64, c_int64, c_void_p]),
     'sdb_attention_bwd': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p,

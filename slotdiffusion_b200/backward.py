@@ -496,8 +496,11 @@ class UNetTrainer:
         y = ops.nhwc_to_nchw(y_rows, B, Co, h.H, h.W)
         hC, hH, hW = h.C, h.H, h.W
 
+        ykey = self._ykey = object()     # NOT the output tensor: ctx -> output -> grad_fn -> ctx would be a reference
+        #                                  cycle that keeps stale AccumulateGrad nodes alive (breaks CUDA-graph capture)
+
         def bw_head():
-            dy = tp.pop(y)                                   # [B, Co, H, W]
+            dy = tp.pop(ykey)                                # [B, Co, H, W]
             dyr = ops.nchw_to_nhwc_pad(dy, 64)               # [M, 64] zero-padded channels
             btmp = torch.zeros(64, dtype=torch.float32, device=dev)
             dyp, _ = ops.grad_pack(dyr, want_T=False, bias_grad=btmp)
@@ -509,8 +512,8 @@ class UNetTrainer:
         tp.push(bw_head)
         return y
 
-    def backward(self, tp, y, dy, x_shape, need_dx):
-        tp.set(y, dy.contiguous().float())
+    def backward(self, tp, ykey, dy, x_shape, need_dx):
+        tp.set(ykey, dy.contiguous().float())
         tp.run()
         dctx = self._dctx
         dx = None
@@ -527,7 +530,7 @@ class UNetFn(torch.autograd.Function):
         tp = Tape()
         need_dx = x.requires_grad
         y = trainer.forward(tp, x.detach(), timesteps, context.detach(), need_dx)
-        ctx.trainer, ctx.tape, ctx.y, ctx.need_dx = trainer, tp, y, need_dx
+        ctx.trainer, ctx.tape, ctx.ykey, ctx.need_dx = trainer, tp, trainer._ykey, need_dx
         ctx.x_shape, ctx.ctx_shape = tuple(x.shape), tuple(context.shape)
         ctx.params = params
         return y
@@ -535,7 +538,7 @@ class UNetFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         tr = ctx.trainer
-        dx, dctx = tr.backward(ctx.tape, ctx.y, dy, ctx.x_shape, ctx.need_dx)
+        dx, dctx = tr.backward(ctx.tape, ctx.ykey, dy, ctx.x_shape, ctx.need_dx)
         ctx.tape = None
         if parallel.enabled():              # one all-reduce of the whole flat gradient buffer (data parallel)
             parallel.allreduce_flat(tr.G.flat, async_op=False)

@@ -251,7 +251,7 @@ struct GnBwdArgs {
   float* dx1; float* dx2; // outputs of the apply pass
   const float* add1; const float* add2;   // optional gradients to accumulate into dx1 / dx2
   int64_t B; int C1, C2, HW, G, silu, rows_per_chunk;
-  float drop_p; unsigned long long seed;
+  float drop_p; unsigned long long seed; const unsigned long long* seed_dev;
 };
 
 template <bool APPLY>
@@ -291,6 +291,7 @@ __global__ void __launch_bounds__(256) groupnorm_bwd_kernel(const GnBwdArgs a) {
   float* dst = from1 ? a.dx1 + c : (a.dx2 ? a.dx2 + (c - a.C1) : nullptr);
   const float* add = from1 ? (a.add1 ? a.add1 + c : nullptr) : (a.add2 ? a.add2 + (c - a.C1) : nullptr);
   const float inv_keep = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
+  const unsigned long long seed = a.seed + (a.seed_dev ? *a.seed_dev * 0x9E3779B97F4A7C15ull : 0ull);
   float accA[4] = {0.f, 0.f, 0.f, 0.f}, accB[4] = {0.f, 0.f, 0.f, 0.f};
   const int r_begin = blockIdx.x * a.rows_per_chunk;
   const int r_end = min(a.HW, r_begin + a.rows_per_chunk);
@@ -305,7 +306,7 @@ __global__ void __launch_bounds__(256) groupnorm_bwd_kernel(const GnBwdArgs a) {
     for (int j = 0; j < 4; ++j) {
       const float xh = (x[j] - mu[j]) * rs[j];
       float dz = d[j];
-      if (a.drop_p > 0.f) dz *= dropout_scale(a.seed, (unsigned long long)(row * C + c + j), a.drop_p, inv_keep);
+      if (a.drop_p > 0.f) dz *= dropout_scale(seed, (unsigned long long)(row * C + c + j), a.drop_p, inv_keep);
       if (a.silu) dz *= silu_grad_f(xh * gm[j] + bt[j]);
       if (APPLY) {
         o[j] = rs[j] * (dz * gm[j] - m1[j] - xh * m2[j]);
@@ -885,7 +886,7 @@ extern "C" int sdb_groupnorm_bwd(const float* x1, int64_t C1, const float* x2, i
                                  const float* stats, const float* gamma, const float* beta, float* sums_work,
                                  float* dx1, float* dx2, const float* add1, const float* add2, float* dgamma,
                                  float* dbeta, int64_t B, int64_t HW, int G, int silu, float drop_p, uint64_t seed,
-                                 void* stream) {
+                                 const uint64_t* seed_dev, void* stream) {
   SDB_REQUIRE(x1 && da && stats && gamma && beta && sums_work && dx1 && dgamma && dbeta, "sdb_groupnorm_bwd: null argument");
   const int64_t C = C1 + C2;
   SDB_REQUIRE(G >= 1 && G <= 64 && C % G == 0 && C1 % 4 == 0 && C2 % 4 == 0 && C <= 1024 && B <= 65535 &&
@@ -894,6 +895,7 @@ extern "C" int sdb_groupnorm_bwd(const float* x1, int64_t C1, const float* x2, i
   a.x1 = x1; a.x2 = x2; a.da = da; a.stats = stats; a.gamma = gamma; a.beta = beta; a.sums = sums_work;
   a.dx1 = dx1; a.dx2 = dx2; a.add1 = add1; a.add2 = add2;
   a.B = B; a.C1 = (int)C1; a.C2 = (int)C2; a.HW = (int)HW; a.G = G; a.silu = silu; a.drop_p = drop_p; a.seed = seed;
+  a.seed_dev = reinterpret_cast<const unsigned long long*>(seed_dev);
   const int c4n = (int)(C / 4);
   const int rpb = 256 / c4n > 0 ? 256 / c4n : 1;
   int threads = c4n * rpb;

@@ -192,7 +192,9 @@ groupnorm_apply_pack_fused_kernel(const float* __restrict__ x1, int C1, const fl
                                   const float* __restrict__ x2, int C2, const float* __restrict__ gsum2,
                                   const float* __restrict__ stats, const float* __restrict__ gamma,
                                   const float* __restrict__ beta, __half* __restrict__ out, int64_t B, int HW, int G,
-                                  float eps, int silu, int rows_per_chunk, float drop_p, unsigned long long seed) {
+                                  float eps, int silu, int rows_per_chunk, float drop_p, unsigned long long seed,
+                                  const unsigned long long* __restrict__ seed_dev) {
+  if (seed_dev) seed += *seed_dev * 0x9E3779B97F4A7C15ull;   // per-step counter living in device memory (graph replays)
   __shared__ float s_mean[64], s_rstd[64];
   const int C = C1 + C2, c4n = C >> 2, cpg = C / G;
   const int64_t b = blockIdx.y;
@@ -668,6 +670,7 @@ extern "C" int sdb_lincomb(float* out, const float* x, const float* m0, const fl
 
 static thread_local float g_drop_p = 0.f;                 // set only by sdb_groupnorm_apply_pack_dropout
 static thread_local unsigned long long g_drop_seed = 0;
+static thread_local const unsigned long long* g_drop_seed_dev = nullptr;
 
 extern "C" int sdb_groupnorm_apply_pack_fused(const float* x1, int64_t C1, const float* gsum1, const float* x2,
                                               int64_t C2, const float* gsum2, const float* stats, const float* gamma,
@@ -693,7 +696,7 @@ extern "C" int sdb_groupnorm_apply_pack_fused(const float* x1, int64_t C1, const
   dim3 grid((unsigned)chunks, (unsigned)B);
   groupnorm_apply_pack_fused_kernel<<<grid, threads, 0, as_stream(stream)>>>(
       x1, (int)C1, gsum1, x2, (int)C2, gsum2, stats, gamma, beta, (__half*)out, B, (int)HW, G, eps, silu, rows_per_chunk,
-      g_drop_p, g_drop_seed);
+      g_drop_p, g_drop_seed, g_drop_seed_dev);
   SDB_LAUNCH_CHECK();
   return 0;
 }
@@ -701,14 +704,16 @@ extern "C" int sdb_groupnorm_apply_pack_fused(const float* x1, int64_t C1, const
 extern "C" int sdb_groupnorm_apply_pack_dropout(const float* x1, int64_t C1, const float* x2, int64_t C2,
                                                 const float* stats, const float* gamma, const float* beta, void* out,
                                                 int64_t B, int64_t HW, int G, int silu, float drop_p, uint64_t seed,
-                                                void* stream) {
+                                                const uint64_t* seed_dev, void* stream) {
   SDB_REQUIRE(stats, "sdb_groupnorm_apply_pack_dropout: stats required");
   SDB_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "sdb_groupnorm_apply_pack_dropout: bad p");
   g_drop_p = drop_p;
   g_drop_seed = seed;
+  g_drop_seed_dev = reinterpret_cast<const unsigned long long*>(seed_dev);
   const int rc = sdb_groupnorm_apply_pack_fused(x1, C1, nullptr, x2, C2, nullptr, stats, gamma, beta, out, B, HW, G, 0.f,
                                                 silu, stream);
   g_drop_p = 0.f;
+  g_drop_seed_dev = nullptr;
   return rc;
 }
 

@@ -441,12 +441,25 @@ def act_bwd(dy, pre, act):
     return dx
 
 
+_dropout_step = {}
+
+
+def dropout_step_counter(device):
+    """Device-resident int64 step counter mixed into every dropout seed.  A training loop that replays a captured CUDA
+    graph advances it inside the graph (`dropout_step_counter(dev).add_(1)`) to get a fresh mask per replay."""
+    t = _dropout_step.get(device)
+    if t is None:
+        t = _dropout_step[device] = torch.zeros(1, dtype=torch.int64, device=device)
+    return t
+
+
 def groupnorm_pack_dropout(x1, x2, gamma, beta, stats, B, HW, G, silu, drop_p, seed):
     C1 = x1.shape[-1]
     C2 = x2.shape[-1] if x2 is not None else 0
     out = Packed.empty(B * HW, C1 + C2, x1.device)
     check(lib().sdb_groupnorm_apply_pack_dropout(_p(x1), C1, _p(x2), C2, _p(stats), _p(gamma), _p(beta), _p(out.t), B,
-                                                 HW, G, int(silu), float(drop_p), int(seed), _stream()),
+                                                 HW, G, int(silu), float(drop_p), int(seed),
+                                                 _p(dropout_step_counter(x1.device)), _stream()),
           'sdb_groupnorm_apply_pack_dropout')
     return out
 
@@ -461,7 +474,8 @@ def groupnorm_bwd(x1, x2, da, stats, gamma, beta, dgamma, dbeta, B, HW, G, silu,
     dx2 = torch.empty_like(x2) if x2 is not None else None
     check(lib().sdb_groupnorm_bwd(_p(x1), C1, _p(x2), C2, _p(da), _p(stats), _p(gamma), _p(beta), _p(work), _p(dx1),
                                   _p(dx2), _p(add1), _p(add2), _p(dgamma), _p(dbeta), B, HW, G, int(silu),
-                                  float(drop_p), int(seed), _stream()), 'sdb_groupnorm_bwd')
+                                  float(drop_p), int(seed), _p(dropout_step_counter(x1.device)) if drop_p > 0 else None,
+                                  _stream()), 'sdb_groupnorm_bwd')
     return dx1, dx2
 
 
