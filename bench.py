@@ -392,6 +392,38 @@ def profile_once(args):
         torch.cuda.profiler.stop()
 
 
+def profile_train_once(args):
+    """ncu helper (use with --profile-from-start off): ONE eager training step between cudaProfilerStart/Stop."""
+    dev = torch.device('cuda', 0)
+    args.no_train_graph = True
+    args.train_steps = 1
+    args.warmup = 3
+    import slotdiffusion_b200.backward as bw
+    real_run = bw.Tape.run
+    state = {'n': 0}
+    orig_train = train_bench
+
+    # profile the LAST timed step only: start the profiler when the timed region begins
+    real_event_record = torch.cuda.Event.record
+    counter = {'rec': 0}
+
+    def rec(self, *a, **k):
+        counter['rec'] += 1
+        if counter['rec'] == 1:
+            torch.cuda.synchronize()
+            torch.cuda.profiler.start()
+        r = real_event_record(self, *a, **k)
+        if counter['rec'] == 2:
+            torch.cuda.synchronize()
+            torch.cuda.profiler.stop()
+        return r
+    torch.cuda.Event.record = rec
+    try:
+        orig_train(args, dev, 1, 0)
+    finally:
+        torch.cuda.Event.record = real_event_record
+
+
 def gemm_roofline(unet, sampler, B, dev):
     """Device time of the dominant kernel: every sdb_gemm call of ONE UNet evaluation is recorded (operands kept
     alive), then exactly those launches are captured in a CUDA graph and replayed back to back, timed with CUDA
@@ -546,10 +578,13 @@ def main():
     ap.add_argument('--no-train', action='store_true', help='skip the training-step measurement')
     ap.add_argument('--no-train-graph', action='store_true', help='time the eager training step (no CUDA graph)')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--profile-train-once', action='store_true', help='ncu helper: one eager training step')
     ap.add_argument('--profile-once', action='store_true',
                     help='ncu helper: SlotAttention + ONE un-captured UNet evaluation (after one warm-up pass), no timing')
     args = ap.parse_args()
-    if args.profile_once:
+    if args.profile_train_once:
+        profile_train_once(args)
+    elif args.profile_once:
         profile_once(args)
     elif args.impl == 'reference':
         run_reference(args)

@@ -70,6 +70,7 @@ struct GemmArgs {
   int H, W;             // output H, W (conv modes)
   int ctiles;           // WGRAD modes: channel blocks per tap
   int a_bf16, w_bf16;   // operand planes hold bf16 (gradient operands) instead of fp16
+  int debug;            // SDB_GEMM_DEBUG (launch-floor experiments): 1 = exit at entry, 2 = prologue + teardown only
 };
 
 // Warp-specialised persistent GEMM.  CG = 1: one CTA per tile (UMMA 128 x bn).  CG = 2: a CTA pair (cluster of 2)
@@ -82,6 +83,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
             const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
             const GemmArgs g) {
   extern __shared__ uint8_t smem_raw[];
+  if (g.debug == 1) return;
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   GemmCtl& ctl = *reinterpret_cast<GemmCtl*>(ring + (size_t)g.stages * g.stage_bytes);
   const int warp = threadIdx.x >> 5;
@@ -119,7 +121,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = ctl.tmem_base;
 
-  if (warp == 0) {
+  if (g.debug == 2) {
+    // skip the work
+  } else if (warp == 0) {
     // ===================== TMA producer (one thread per CTA) =====================
     if (lane == 0) {
       const uint32_t tx = (three ? 2u : 1u) * (uint32_t(g.tile_rows) * BK * 2 + b_tile_bytes) * CG;
@@ -573,6 +577,7 @@ extern "C" int sdb_gemm(const SdbGemm* p, void* stream) {
   g.out_packed = reinterpret_cast<__half*>(p->out_packed); g.gsum = p->gsum;
   g.out_plane = p->out_plane_stride; g.out_act = p->out_act;
   g.a_bf16 = p->a_bf16 != 0; g.w_bf16 = p->w_bf16 != 0;
+  g.debug = env_int("SDB_GEMM_DEBUG", 0);
   g.ldc = p->ldc; g.ldv = p->ldv; g.ldr = p->ldr;
   g.M = p->M; g.N = p->N; g.K = p->K; g.mode = p->mode; g.passes = p->passes; g.relu = p->relu;
   g.rows_per_group = p->rows_per_group > 0 ? (unsigned)p->rows_per_group : 1u;
@@ -642,7 +647,10 @@ extern "C" int sdb_gemm(const SdbGemm* p, void* stream) {
 
   // ---- CTA grouping, N tile, split-K, pipeline depth
   const int sms = num_sms();
-  int cg = (n_tiles_m1 >= 2) ? 2 : 1;
+  // CTA pairs pay ~3 us of extra fixed latency (cluster barriers, remote arrives: 12.0 vs 8.8 us for a 3-k-block
+  // problem) and win on large problems through halved shared-memory traffic: crossover measured near 6 GFLOP
+  const double flop = 2.0 * (double)p->M * (double)p->N * (double)p->K;
+  int cg = (n_tiles_m1 >= 2 && flop >= 6e9) ? 2 : 1;
   const int force_cg = env_int("SDB_GEMM_CG", 0);
   if (force_cg == 1 || force_cg == 2) cg = force_cg;
   const bool wgrad_mode = (p->mode == SDB_A_WGRAD || p->mode == SDB_A_WGRAD_S2);

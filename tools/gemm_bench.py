@@ -49,6 +49,7 @@ def main():
     ap.add_argument('--cg', type=int, default=0)
     ap.add_argument('--splitk', type=int, default=0)
     ap.add_argument('--passes', type=int, default=3)
+    ap.add_argument('--only', default='', help='substring filter on shape names')
     args = ap.parse_args()
     if args.cg:
         os.environ['SDB_GEMM_CG'] = str(args.cg)
@@ -59,6 +60,8 @@ def main():
     print(f'{"shape":34s} {"us":>8s} {"alg TF/s":>9s} {"issued TF/s":>11s}')
     for spec in SHAPES:
         name, kind = spec[0], spec[1]
+        if args.only and args.only not in name:
+            continue
         if kind == 'lin':
             M, N, K = spec[2:]
             conv = None
