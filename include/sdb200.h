@@ -178,6 +178,18 @@ int sdb_slot_attend(const float* kv, const float* q, float* seg_mask, void* upd_
 int sdb_slot_attend_train(const float* kv, const float* q, float* seg_mask, void* upd_packed, float* upd32,
                           float* colsum, float* work, int64_t B, int64_t N, int64_t S, int64_t D, float scale, float eps,
                           void* stream);
+/* Tensor-core form of one Slot-Attention iteration for the inference path (slot_attention.py:67-91 with the k / v
+ * projections folded away): x [B,N,Din] RAW encoder features (the LayerNorm of slot_attention.py:68 is applied
+ * in-kernel without its affine part, which the caller folds into qa and into the GRU input weight);
+ * qa [B*S, ldq]: columns [0,Din) = scale * gamma * (Wk^T Wq LN_q(slots)), column Din = the beta term of the logits.
+ * Returns U[b,s,:] = sum_n a[n,s] n[n,:] / sum_n a[n,s] (a = softmax_s(logits) + eps, n = normalised features) as a
+ * packed GEMM operand [2][B*S][Din] (+ optional fp32 copy) and the seg mask [B,S,N] (optional).
+ * Supported: Din in {128,192,256}, S <= 32 (sdb_slot_attend_fused_supported); work: _workspace() bytes. */
+int sdb_slot_attend_fused_supported(int64_t S, int64_t Din);
+int64_t sdb_slot_attend_fused_workspace(int64_t B, int64_t N, int64_t S, int64_t Din);
+int sdb_slot_attend_fused(const float* x, const float* qa, int64_t ldq, float* seg_mask, void* upd_packed,
+                          float* upd32, float* work, int64_t B, int64_t N, int64_t S, int64_t Din, float ln_eps,
+                          float eps, void* stream);
 /* GRUCell pointwise part (PyTorch gate order r,z,n; slot_attention.py:97-100): gi = x W_ih^T + b_ih and
  * gh = h W_hh^T + b_hh come from sdb_gemm; h_new = (1-z) n + z h.  All [R, 3D] / [R, D]. */
 int sdb_gru_gates(const float* gi, const float* gh, const float* h, float* h_new, int64_t R, int64_t D,

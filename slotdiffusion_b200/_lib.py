@@ -60,6 +60,10 @@ SIGNATURES = {
                                 c_int64, c_int64, c_float, c_float, c_void_p]),
     'sdb_slot_attend_train': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                       c_int64, c_int64, c_int64, c_float, c_float, c_void_p]),
+    'sdb_slot_attend_fused_supported': (c_int, [c_int64, c_int64]),
+    'sdb_slot_attend_fused_workspace': (c_int64, [c_int64, c_int64, c_int64, c_int64]),
+    'sdb_slot_attend_fused': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                      c_int64, c_int64, c_int64, c_float, c_float, c_void_p]),
     'sdb_groupnorm_apply_pack_dropout': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
                                                  c_void_p, c_int64, c_int64, c_int, c_int, c_float, c_uint64, c_void_p, c_void_p]),
     'sdb_grad_pack': (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64,

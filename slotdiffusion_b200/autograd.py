@@ -13,6 +13,9 @@ import torch
 from . import ops
 
 
+FUSED_ATTEND = True   # inference: tensor-core attend over the raw features (no k / v tensors)
+
+
 def _needs_grad(*ts):
     return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in ts)
 
@@ -25,6 +28,8 @@ def slot_attention_forward(mod, inputs, slots, want_mask, save=None):
     wc = mod._wcache
     inputs = inputs.contiguous().float()
     slots = slots.contiguous().float().reshape(B * S, D)
+    if save is None and FUSED_ATTEND and ops.slot_attend_fused_supported(S, Din):
+        return _slot_attention_forward_fused(mod, inputs, slots, want_mask, B, N, Din, S, D)
 
     # k | v projection of LayerNorm(inputs)                                  (slot_attention.py:68-72)
     xn = ops.layernorm_pack(inputs.reshape(B * N, Din), mod.norm_inputs.weight, mod.norm_inputs.bias,
@@ -62,6 +67,36 @@ def slot_attention_forward(mod, inputs, slots, want_mask, save=None):
             save.append(dict(prev=prev, sn=sn, q=q, upd=upd, upd32=upd32, gi=gi, gh=gh, hp=hp, h=h, hn=hn, y1=y1,
                              y1p=y1p))
         hp = sp                                                              # next iteration's W_hh operand
+    return slots.view(B, S, D), mask
+
+
+def _slot_attention_forward_fused(mod, inputs, slots, want_mask, B, N, Din, S, D):
+    """Inference path: no k / v tensors.  Per iteration: LayerNorm+pack -> folded slot-side projection (GEMM) ->
+    tensor-core attend over the RAW features (csrc/slot_attention_fused.cu) -> GRU / MLP tail."""
+    wc = mod._wcache
+    fold = wc.slot_attention_fold(mod)
+    w_hh = wc.linear('hh', mod.gru.weight_hh)
+    w_1 = wc.linear('m1', mod.mlp[1].weight)
+    w_2 = wc.linear('m2', mod.mlp[3].weight)
+    mask = None
+    hp = None
+    for it in range(mod.num_iterations):
+        last = it == mod.num_iterations - 1
+        prev = slots
+        sn = ops.layernorm_pack(prev, mod.project_q[0].weight, mod.project_q[0].bias, mod.project_q[0].eps)
+        qa = ops.gemm(sn, fold['w_qa'])                                       # [B*S, Din+4]  (:82 and k-side of :84)
+        upd, m, _ = ops.slot_attend_fused(inputs, qa, B, N, S, Din, mod.norm_inputs.eps, mod.eps,
+                                          want_mask and last)                 # :68-72, :84-91
+        if want_mask and last:
+            mask = m
+        gi = ops.gemm(upd, fold['w_iv'], bias=fold['b_iv'])                   # v-side of :91 folded into :97-100
+        if hp is None:
+            hp = ops.pack_rows(prev)
+        gh = ops.gemm(hp, w_hh, bias=mod.gru.bias_hh)
+        h = ops.gru_gates(gi, gh, prev)
+        hn = ops.layernorm_pack(h, mod.mlp[0].weight, mod.mlp[0].bias, mod.mlp[0].eps)
+        _, y1p = ops.gemm(hn, w_1, bias=mod.mlp[1].bias, relu=True, pack_out='none', keep_c=False)
+        slots, hp = ops.gemm(y1p, w_2, bias=mod.mlp[3].bias, residual=h, pack_out='none')
     return slots.view(B, S, D), mask
 
 

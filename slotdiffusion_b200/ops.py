@@ -92,6 +92,28 @@ class WeightCache:
     def conv3(self, key, w):
         return self._get(key, (w,), lambda: pack_weight_conv3(w.detach().contiguous()))
 
+    def slot_attention_fold(self, mod):
+        """Parameter-only preprocessing for the tensor-core Slot-Attention path (done once per parameter version, in
+        fp64): the k / v projections and the affine part of norm_inputs are folded into the slot-side projection and
+        into the GRU input weight (see csrc/slot_attention_fused.cu):
+          W_qa [Din+4, D]: rows c < Din = scale * gamma_c * (Wk^T Wq)[c, :], row Din = scale * beta^T Wk^T Wq, rest 0
+          W_iv [3D, Din]  = W_ih Wv diag(gamma);   b_iv = W_ih (Wv beta) + b_ih"""
+        ps = (mod.project_q[1].weight, mod.project_k.weight, mod.project_v.weight, mod.norm_inputs.weight,
+              mod.norm_inputs.bias, mod.gru.weight_ih, mod.gru.bias_ih)
+
+        def make():
+            wq, wk, wv, g, b, wih, bih = [p.detach().double() for p in ps]
+            Din = wk.shape[1]
+            wqk = (wk.t() @ wq) * mod.attn_scale                      # [Din, D]
+            wqa = torch.zeros(Din + 4, wq.shape[1], dtype=torch.float64, device=wq.device)
+            wqa[:Din] = wqk * g[:, None]
+            wqa[Din] = b @ wqk
+            wiv = (wih @ wv) * g[None, :]                             # [3D, Din]
+            biv = wih @ (wv @ b) + bih
+            return dict(w_qa=pack_weight(wqa.float().contiguous()), w_iv=pack_weight(wiv.float().contiguous()),
+                        b_iv=biv.float().contiguous())
+        return self._get('sa_fold', ps, make)
+
     def cat(self, key, *vs):
         """Concatenation of fp32 vectors (fused biases)."""
         return self._get(key, vs, lambda: torch.cat([v.detach().reshape(-1) for v in vs]).contiguous())
@@ -310,6 +332,25 @@ def slot_attend(kv, q, B, N, S, D, scale, eps, want_mask, want_fp32=False):
     upd32 = torch.empty(B * S, D, dtype=torch.float32, device=kv.device) if want_fp32 else None
     check(lib().sdb_slot_attend(_p(kv), _p(q), _p(mask), _p(upd.t), _p(upd32), _p(work), B, N, S, D, scale, eps,
                                 _stream()), 'sdb_slot_attend')
+    return upd, mask, upd32
+
+
+def slot_attend_fused_supported(S, Din):
+    return bool(lib().sdb_slot_attend_fused_supported(S, Din))
+
+
+def slot_attend_fused(x, qa, B, N, S, Din, ln_eps, eps, want_mask, want_fp32=False):
+    """Tensor-core Slot-Attention iteration on the RAW features x [B,N,Din] (LayerNorm folded in-kernel);
+    qa [B*S, ldq] = folded slot-side projection (logit weights | logit bias).  Returns (U Packed [B*S,Din], mask, U fp32)."""
+    _f32(x), _f32(qa)
+    assert x.is_contiguous() and qa.stride(1) == 1
+    ws = lib().sdb_slot_attend_fused_workspace(B, N, S, Din)
+    work = torch.empty(ws // 4, dtype=torch.float32, device=x.device)
+    mask = torch.empty(B, S, N, dtype=torch.float32, device=x.device) if want_mask else None
+    upd = Packed.empty(B * S, Din, x.device)
+    upd32 = torch.empty(B * S, Din, dtype=torch.float32, device=x.device) if want_fp32 else None
+    check(lib().sdb_slot_attend_fused(_p(x), _p(qa), qa.stride(0), _p(mask), _p(upd.t), _p(upd32), _p(work), B, N, S,
+                                      Din, ln_eps, eps, _stream()), 'sdb_slot_attend_fused')
     return upd, mask, upd32
 
 

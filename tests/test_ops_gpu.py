@@ -308,6 +308,33 @@ def test_slot_attend(ops, B, N, S, D):
     assert rel_l2(upd.unpack(), ref) < 3e-6
 
 
+@pytest.mark.parametrize('B,N,S,Din', [(2, 1024, 11, 192), (1, 1024, 24, 192), (3, 196, 7, 256), (5, 77, 5, 192),
+                                       (64, 1024, 11, 192), (2, 300, 15, 128), (1, 784, 7, 256), (160, 1024, 11, 192),
+                                       (2, 130, 20, 256)])
+def test_slot_attend_fused(ops, B, N, S, Din):
+    """Tensor-core attend over raw features: in-kernel LayerNorm (no affine), logits = n . qa[:, :Din] + qa[:, Din],
+    softmax over slots, U = (a^T n) / sum_n a  -- vs fp64 torch math of the same definition."""
+    x = rnd(B, N, Din, seed=46, scale=2.0) + 0.3
+    qa = torch.zeros(B * S, Din + 4, device='cuda')
+    qa[:, :Din] = rnd(B * S, Din, seed=47, scale=Din ** -0.5)
+    qa[:, Din] = rnd(B * S, seed=48)
+    ln_eps, eps = 1e-5, 1e-6
+    upd, mask, upd32 = ops.slot_attend_fused(x, qa, B, N, S, Din, ln_eps, eps, want_mask=True, want_fp32=True)
+    xd = x.double()
+    n = (xd - xd.mean(-1, keepdim=True)) / torch.sqrt(xd.var(-1, unbiased=False, keepdim=True) + ln_eps)
+    qd = qa.double().view(B, S, Din + 4)
+    logits = n @ qd[:, :, :Din].transpose(1, 2) + qd[:, :, Din][:, None, :]
+    attn = torch.softmax(logits, -1)
+    a = attn + eps
+    ref = torch.einsum('bns,bnd->bsd', a / a.sum(1, keepdim=True), n).reshape(B * S, Din)
+    assert rel_l2(mask, attn.transpose(1, 2)) < 3e-6
+    assert rel_l2(upd32, ref) < 6e-6          # fp32 accumulation over up to 1024 tokens per CTA
+    assert rel_l2(upd.unpack(), ref) < 6e-6
+    # determinism (no atomics): bit-identical on a second launch
+    upd_b, mask_b, upd32_b = ops.slot_attend_fused(x, qa, B, N, S, Din, ln_eps, eps, want_mask=True, want_fp32=True)
+    assert torch.equal(upd32, upd32_b) and torch.equal(mask, mask_b)
+
+
 def test_gru_gates(ops):
     R, D = 77, 192
     gi, gh, h = rnd(R, 3 * D, seed=38), rnd(R, 3 * D, seed=39), rnd(R, D, seed=40)
