@@ -186,6 +186,8 @@ int sdb_slot_attend_train(const float* kv, const float* q, float* seg_mask, void
  * packed GEMM operand [2][B*S][Din] (+ optional fp32 copy) and the seg mask [B,S,N] (optional).
  * Supported: Din in {128,192,256}, S <= 32 (sdb_slot_attend_fused_supported); work: _workspace() bytes. */
 int sdb_slot_attend_fused_supported(int64_t S, int64_t Din);
+/* debug aid: device buffer of 6*64 int64 receiving the per-role timeline (SM cycles) of CTA (0,0); NULL switches it off */
+int sdb_slot_attend_fused_debug(void* buf);
 int64_t sdb_slot_attend_fused_workspace(int64_t B, int64_t N, int64_t S, int64_t Din);
 int sdb_slot_attend_fused(const float* x, const float* qa, int64_t ldq, float* seg_mask, void* upd_packed,
                           float* upd32, float* work, int64_t B, int64_t N, int64_t S, int64_t Din, float ln_eps,

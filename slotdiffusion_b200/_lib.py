@@ -61,6 +61,7 @@ SIGNATURES = {
     'sdb_slot_attend_train': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                       c_int64, c_int64, c_int64, c_float, c_float, c_void_p]),
     'sdb_slot_attend_fused_supported': (c_int, [c_int64, c_int64]),
+    'sdb_slot_attend_fused_debug': (c_int, [c_void_p]),
     'sdb_slot_attend_fused_workspace': (c_int64, [c_int64, c_int64, c_int64, c_int64]),
     'sdb_slot_attend_fused': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                       c_int64, c_int64, c_int64, c_float, c_float, c_void_p]),

@@ -4,17 +4,21 @@
 //   logits[n,s] = scale * k[n] . q[s]          = n[n] . qa[s,:Din] + qa[s,Din]          (qa = LN_q(slots) W_qa^T, host-folded
 //                                                                                        W_qa = scale * diag(gamma) Wk^T Wq | beta row)
 //   updates[s]  = (sum_n a[n,s] v[n]) / sum_n a = (gamma * U[s] + beta) Wv^T,  U[s] = (sum_n a[n,s] n[n]) / sum_n a[n,s]
-// so one pass over the RAW features per iteration does LayerNorm statistics, both N x S contractions and the softmax:
+// so one pass over the RAW features per iteration does LayerNorm statistics, both N x S contractions and the softmax.
 //
-//   warp 13      TMA producer: cp.async.bulk of 32-token fp32 chunks straight into the operand slots (mbarrier full/empty)
-//   warps 4..11  converters: LayerNorm (8 lanes per token, warp-shuffle reductions) and fp16 hi/lo split IN PLACE: the
-//                6 KB of eight fp32 token rows become the 6 one-KB 128B-swizzled UMMA atoms (2 planes x Din/64 blocks)
-//                of the same eight tokens.  One operand tile [128 tokens][Din] serves BOTH contractions (K-major for
-//                the logits, MN-major for the weighted sum); tiles are double-buffered (two sets of four chunk slots)
-//   warp 12      MMA issuer (one thread): logits[128 x SP] = X Q^T, then U^T[Din x SP] += X^T A, tcgen05.mma kind::f16.
-//                fp32-faithful products hi*hi + lo*hi + hi*lo in TWO instructions per k-step: the hi and lo planes of
-//                the small operand are stacked along N (x_hi * [b_hi ; b_lo], then x_lo * b_hi) -- small MMAs are
-//                issue-bound (~51 cycles each, tools/probes/umma_probe.cu), so instruction count is what matters
+//   warp TMA     producer: cp.async.bulk of 32-token fp32 chunks straight into the operand slots (mbarrier completion),
+//                started before the rest of the prologue; L2 prefetch of the tile after next
+//   warps 4..4+CW-1  converters: LayerNorm (8 lanes per token, warp-shuffle reductions) and fp16 hi/lo split IN PLACE:
+//                the 6 KB of eight fp32 token rows become the 6 one-KB 128B-swizzled UMMA atoms (2 planes x Din/64
+//                blocks) of the same eight tokens.  ONE operand tile [128 tokens][Din] serves BOTH contractions
+//                (K-major for the logits, MN-major for the weighted sum); tiles are double-buffered.
+//                (A register-staged variant -- ld.global one tile ahead, no fp32 copy in shared memory -- was measured
+//                too and lost: see profiles/README.md.)
+//   warp G1      MMA issuer (one thread): logits[128 x SP] = X Q^T                      tcgen05.mma kind::f16
+//   warp G2      MMA issuer (one thread): U^T[Din x SP] += X^T A
+//                fp32-faithful products hi*hi + lo*hi + hi*lo (+ lo*lo) with the hi and lo planes STACKED inside one
+//                instruction (along N for the small operand, along M for the features in the second product): small
+//                MMAs are bound by their ~50-cycle issue cost (tools/probes/umma_probe.cu), not by the tensor pipe
 //   warps 0..3   softmax over slots (thread <-> token <-> TMEM lane), seg-mask store, a = softmax + eps as the B operand
 //                of the second contraction, column sums by warp shuffles; finally drain U from TMEM
 //
@@ -26,14 +30,13 @@
 namespace sdb {
 
 constexpr int SF_TILE = 128;          // tokens per tile (UMMA M of the logits product, K extent of the update product)
+constexpr int SF_GROUPS = SF_TILE / 8;
 constexpr int SF_CT = 32;             // tokens per TMA chunk
 constexpr int SF_CPT = SF_TILE / SF_CT;   // chunks per tile
 constexpr int SF_SOFT_WARPS = 4;
-constexpr int SF_CONV_WARPS = 8;
-constexpr int SF_MMA_WARP = SF_SOFT_WARPS + SF_CONV_WARPS;   // 12
-constexpr int SF_TMA_WARP = SF_MMA_WARP + 1;                 // 13
-constexpr int SF_THREADS = 32 * (SF_TMA_WARP + 1);           // 448
-constexpr int SF_TMEM_COLS = 256;     // logits set s at [64 s, 64 s + 2 SP) | U half h at [128 + 64 h, ... + 2 SP)
+// converter warps CW: 16 (one 8-token group per warp and tile) when the softmax warps fit 88 registers (SP = 16),
+// else 8.  Warps: 0..3 softmax, 4..4+CW-1 converters, then the two MMA issuers and the TMA producer.
+constexpr int SF_TMEM_COLS = 512;     // logits set s at [64 s, 64 s + 2 SP) | U block kb at [128 + 2 SP kb, ... + 2 SP)
 constexpr float SF_ASCALE = 4096.f;   // a = softmax + eps is scaled before the fp16 split (keeps 1e-6 out of fp16 subnormals)
 
 struct SfCtl {
@@ -50,17 +53,19 @@ struct SfCtl {
 template <int DIN, int SP>
 struct SfCfg {
   static constexpr int NKB = DIN / 64;                       // 64-channel blocks
-  static constexpr int GROUP_BYTES = 2 * NKB * 1024;         // 8 tokens: fp32 rows == 2 planes x NKB atoms of 1 KB
+  static constexpr int GROUP_BYTES = 2 * NKB * 1024;         // 8 tokens: fp32 rows == 2 planes x NKB swizzle atoms of 1 KB
   static constexpr int CHUNK_BYTES = (SF_CT / 8) * GROUP_BYTES;
-  static constexpr int TILE_BYTES = SF_CPT * CHUNK_BYTES;
+  static constexpr int TILE_BYTES = SF_GROUPS * GROUP_BYTES;
+  static_assert(GROUP_BYTES == 8 * DIN * 4, "in-place conversion needs equal fp32 and fp16x2 footprints");
   static constexpr int QBYTES = NKB * 2 * SP * 128;          // per k-block: [q_hi rows | q_lo rows] x 128 B
   static constexpr int ABYTES = (SF_TILE / 64) * 2 * SP * 128;   // per set: 2 token blocks x [a_hi rows | a_lo rows] x 128 B
   static constexpr int CTL = 1024;
   static constexpr int NSETS = (1024 + 2 * TILE_BYTES + QBYTES + 2 * ABYTES + CTL <= 227 * 1024) ? 2 : 1;
   static constexpr int SMEM = 1024 + NSETS * TILE_BYTES + QBYTES + NSETS * ABYTES + CTL;
-  static_assert(GROUP_BYTES == 8 * DIN * 4, "in-place conversion needs equal fp32 and fp16x2 footprints");
   static_assert(SMEM <= 227 * 1024, "slot_attend_fused: tile does not fit shared memory");
   static_assert(sizeof(SfCtl) <= CTL, "control block too large");
+  static_assert(NKB * 64 * SP * 4 <= TILE_BYTES, "epilogue scratch must fit an operand tile");
+  static_assert(128 + NKB * 2 * SP <= SF_TMEM_COLS, "TMEM columns");
 };
 
 // two fp32 -> (hi, lo) fp16 pairs; inputs are LayerNorm outputs / probabilities (bounded, no saturation needed)
@@ -112,22 +117,70 @@ __device__ __forceinline__ void tmem_ld_folded(uint32_t taddr, float (&out)[SP])
   }
 }
 
+// latency-critical single-thread wait (MMA issuers): non-blocking test_wait in a tight loop, bounded
+__device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  long long t0 = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(a), "r"(parity)
+        : "memory");
+    if (ok) return;
+    const long long now = clock64();
+    if (t0 == 0) t0 = now;
+    else if (now - t0 > 4000000000LL) {
+      printf("sdb200: mbarrier spin timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+      __trap();
+    }
+  }
+}
+
 // one lane polls, the warp follows (keeps hundreds of threads from hammering the barrier)
 __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int lane) {
-  if (lane == 0) mbar_wait(bar, parity);
+  if (lane == 0) {
+    long long t0 = 0;
+    while (!mbar_try_wait(bar, parity)) {     // try_wait itself blocks for a hardware-defined interval
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000LL) {
+        printf("sdb200: mbarrier wait timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+        __trap();
+      }
+    }
+  }
   __syncwarp();
   mbar_wait(bar, parity);   // already complete: one try_wait per thread = its own acquire
 }
 
-template <int DIN, int SP>
-__global__ void __launch_bounds__(SF_THREADS, 1)
+__device__ __forceinline__ void l2_prefetch(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(src)), "r"(bytes) : "memory");
+}
+
+template <int DIN, int SP, int CW>
+__global__ void __launch_bounds__(32 * (SF_SOFT_WARPS + CW + 3), 1)
 slot_attend_fused_kernel(const float* __restrict__ x, const float* __restrict__ qa, int ldq,
                          float* __restrict__ seg_mask, float* __restrict__ part_upd, float* __restrict__ part_cs,
-                         int N, int S, int chunks, float ln_eps, float eps) {
+                         int N, int S, int chunks, float ln_eps, float eps, long long* __restrict__ dbg) {
   using C = SfCfg<DIN, SP>;
+  // optional timeline of CTA (0,0) for tools/sa_timeline.py: dbg[role * 64 + tile * 4 + k] = cycles since kernel entry
+  const long long t_entry = clock64();
+#define SF_T(role, tile, k)                                                                     \
+  do {                                                                                          \
+    if (dbg && blockIdx.x == 0 && blockIdx.y == 0 && (tile) < 16) dbg[(role) * 64 + (tile) * 4 + (k)] = clock64() - t_entry; \
+  } while (0)
   constexpr int NKB = C::NKB;
   constexpr int NSETS = C::NSETS;
   constexpr int GB = C::GROUP_BYTES;
+  constexpr int SF_G1_WARP = SF_SOFT_WARPS + CW;
+  constexpr int SF_G2_WARP = SF_G1_WARP + 1;
+  constexpr int SF_TMA_WARP = SF_G2_WARP + 1;
+  constexpr int SF_THREADS = 32 * (SF_TMA_WARP + 1);
+  constexpr int NV = DIN / 32;                      // float4 per lane per token
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* xop = base;                              // NSETS tiles: [16 token groups][2 planes][NKB][8 tokens][128 B]
@@ -151,32 +204,53 @@ slot_attend_fused_kernel(const float* __restrict__ x, const float* __restrict__ 
     return;
   }
   const int ntiles = (ntok + SF_TILE - 1) / SF_TILE;
+
   const int nchunks = (ntok + SF_CT - 1) / SF_CT;
+  const bool is_conv = warp >= SF_SOFT_WARPS && warp < SF_G1_WARP;
+  const int cw = warp - SF_SOFT_WARPS, sub = lane >> 3, j = lane & 7;
+  // token of (round q, lane) within its 8-token group: a half-warp's two tokens land in disjoint halves of the bank space
+  auto tok_in_group = [&](int q) { return 4 * (sub & 1) + (sub >> 1) + 2 * q; };
 
   // ------------------------------------------------------------------ prologue
-  if (tid == 0) {
+  // TMA chunk loads of tile i into its set (+ L2 prefetch of the tile that will follow it into the same set)
+  auto issue_tile = [&](int i) {
+    const int set = i % NSETS;
+    for (int cc = 0; cc < SF_CPT; ++cc) {
+      const int c = i * SF_CPT + cc;
+      if (c >= nchunks) break;
+      const int rows = min(SF_CT, ntok - c * SF_CT);
+      const uint32_t bytes = (uint32_t)rows * DIN * 4;
+      uint64_t* bar = &ctl.sfull[set * SF_CPT + cc];
+      mbar_arrive_expect_tx(bar, bytes);
+      bulk_load(xop + set * C::TILE_BYTES + cc * C::CHUNK_BYTES, x + (b * N + n_begin + c * SF_CT) * DIN, bytes, bar);
+    }
+    const int nxt = (i + NSETS) * SF_TILE;
+    if (nxt < ntok) l2_prefetch(x + (b * N + n_begin + nxt) * DIN, (uint32_t)min(SF_TILE, ntok - nxt) * DIN * 4);
+  };
+  if (warp == SF_TMA_WARP && lane == 0) {
     for (int i = 0; i < 2 * SF_CPT; ++i) mbar_init(&ctl.sfull[i], 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&ctl.xfull[i], SF_CONV_WARPS);
+      mbar_init(&ctl.xfull[i], CW);
       mbar_init(&ctl.xempty[i], 1);
       mbar_init(&ctl.lfull[i], 1);
       mbar_init(&ctl.afull[i], SF_SOFT_WARPS);
     }
     mbar_init(&ctl.ufull, 1);
     fence_mbar_init();
+    for (int i = 0; i < NSETS && i < ntiles; ++i) issue_tile(i);   // the feature stream starts before the rest of the prologue
   }
-  if (warp == SF_MMA_WARP) {
+  if (warp == SF_G1_WARP) {
     tmem_alloc(&ctl.tmem_base, SF_TMEM_COLS);
     tmem_relinquish();
   }
   // slot-side operand of the logits product: qa[s, 0:DIN] split into fp16 planes stacked along N, K-major swizzled rows
   for (int i = tid; i < SP * (DIN / 4); i += SF_THREADS) {
     const int s = i / (DIN / 4), c = (i % (DIN / 4)) * 4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (s < S) v = *reinterpret_cast<const float4*>(qa + (b * S + s) * ldq + c);
+    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (s < S) w = *reinterpret_cast<const float4*>(qa + (b * S + s) * ldq + c);
     uint2 hi, lo;
-    split2(v.x, v.y, hi.x, lo.x);
-    split2(v.z, v.w, hi.y, lo.y);
+    split2(w.x, w.y, hi.x, lo.x);
+    split2(w.z, w.w, hi.y, lo.y);
     const int kb = c >> 6, cc = c & 63;
     const uint32_t off = kb * (2 * SP * 128) + (((cc >> 3) ^ (s & 7)) << 4) + (cc & 7) * 2;   // SP % 8 == 0: lo row has the same swizzle phase
     *reinterpret_cast<uint2*>(qop + off + s * 128) = hi;
@@ -187,125 +261,112 @@ slot_attend_fused_kernel(const float* __restrict__ x, const float* __restrict__ 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = ctl.tmem_base;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, ctl.tmem_base, 0);   // warp-uniform by construction
+  if (tid == 0) SF_T(5, 0, 2);   // prologue done
 
   if (warp == SF_TMA_WARP) {
     // ================================================================ TMA producer
     if (lane == 0) {
-      for (int i = 0; i < ntiles; ++i) {
+      for (int i = NSETS; i < ntiles; ++i) {
         const int set = i % NSETS;
         mbar_wait(&ctl.xempty[set], ((i / NSETS) & 1) ^ 1);    // the MMAs of the tile that used this set have retired
-        for (int cc = 0; cc < SF_CPT; ++cc) {
-          const int c = i * SF_CPT + cc;
-          if (c >= nchunks) break;
-          const int rows = min(SF_CT, ntok - c * SF_CT);
-          const uint32_t bytes = (uint32_t)rows * DIN * 4;
-          uint64_t* bar = &ctl.sfull[set * SF_CPT + cc];
-          mbar_arrive_expect_tx(bar, bytes);
-          bulk_load(xop + set * C::TILE_BYTES + cc * C::CHUNK_BYTES, x + (b * N + n_begin + c * SF_CT) * DIN, bytes, bar);
-        }
+        issue_tile(i);
       }
     }
     __syncwarp();
-  } else if (warp == SF_MMA_WARP) {
-    // ================================================================ MMA issuer
+  } else if (warp == SF_G1_WARP) {
+    // ================================================================ MMA issuer 1: logits product
+    // (two issuer warps with plain counted loops: every operand of tcgen05.mma stays warp-uniform, so the per-MMA
+    //  instruction stream is a handful of uniform-datapath adds -- small MMAs are bound by their issue overhead)
     if (lane == 0) {
-      const uint32_t id1w = umma_idesc_f16(SF_TILE, 2 * SP), id1n = umma_idesc_f16(SF_TILE, SP);   // A, B K-major
-      const uint32_t id2w = id1w | (1u << 15), id2n = id1n | (1u << 15);                          // A MN-major (features^T)
-      const uint32_t x0 = smem_u32(xop), q0 = smem_u32(qop), a0 = smem_u32(aop);
-      constexpr int NH = NKB > 2 ? 2 : 1;       // 128-channel halves of U (overlapping when DIN = 192)
-      int g1 = 0, g2 = 0;                       // next tile of the logits product / of the update product
-      long long t_idle = 0;
-      while (g2 < ntiles) {
-        bool progress = false;
-        if (g1 < ntiles && g1 - g2 < NSETS && mbar_try_wait(&ctl.xfull[g1 % NSETS], (g1 / NSETS) & 1)) {
-          // ---- logits[128 tokens x SP] = X[128 x DIN] * Qa[SP x DIN]^T       (cols [0,SP): hi*hi + lo*hi, [SP,2SP): hi*lo)
-          tc_fence_after();
-          const int set = g1 % NSETS;
-          const uint32_t xs = x0 + set * C::TILE_BYTES;
-          const uint32_t d_tmem = tmem + 64u * set;
+      const uint32_t id1 = umma_idesc_f16(SF_TILE, 2 * SP);   // A, B K-major
+      const uint32_t x0 = smem_u32(xop), q0 = smem_u32(qop);
+      for (int i = 0; i < ntiles; ++i) {
+        const int set = i % NSETS;
+        // logits[128 tokens x 2SP] = X[128 x DIN] * [Q_hi ; Q_lo]^T for X = hi plane, then lo plane:
+        //   cols [0,SP): x_hi q_hi + x_lo q_hi     cols [SP,2SP): x_hi q_lo + x_lo q_lo
+        mbar_spin(&ctl.xfull[set], (i / NSETS) & 1);
+        tc_fence_after();
+        SF_T(1, i, 0);
+        const uint32_t xs = x0 + set * C::TILE_BYTES;
+        const uint32_t d_tmem = tmem + 64u * set;
+        const uint64_t dxh0 = umma_desc_k_sw128(xs, GB), dxl0 = umma_desc_k_sw128(xs + NKB * 1024, GB);
+        const uint64_t dq0 = umma_desc_k_sw128(q0, 1024);
 #pragma unroll
-          for (int kb = 0; kb < NKB; ++kb) {
+        for (int kb = 0; kb < NKB; ++kb) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t adv = uint64_t((k * 32) >> 4);
-              const uint64_t dxh = umma_desc_k_sw128(xs + kb * 1024, GB) + adv;
-              const uint64_t dxl = umma_desc_k_sw128(xs + (NKB + kb) * 1024, GB) + adv;
-              const uint64_t dq = umma_desc_k_sw128(q0 + kb * (2 * SP * 128), 1024) + adv;
-              umma_f16(d_tmem, dxh, dq, id1w, (kb | k) ? 1u : 0u);
-              umma_f16(d_tmem, dxl, dq, id1n, 1u);
-            }
-          }
-          umma_commit(&ctl.lfull[set]);
-          ++g1;
-          progress = true;
-        }
-        if (g2 < g1 && mbar_try_wait(&ctl.afull[g2 % NSETS], (g2 / NSETS) & 1)) {
-          // ---- U^T[128 channels x SP] += X^T[channels x 128 tokens] * A[SP x 128 tokens]^T
-          tc_fence_after();
-          const int set = g2 % NSETS;
-          const uint32_t xs = x0 + set * C::TILE_BYTES;
-          const uint32_t as = a0 + set * C::ABYTES;
-#pragma unroll
-          for (int h = 0; h < NH; ++h) {
-            const int m0 = h == 0 ? 0 : NKB - 2;  // first 64-channel block of this half
-            const uint32_t d_tmem = tmem + 128u + 64u * h;
-#pragma unroll
-            for (int k2 = 0; k2 < SF_TILE / 16; ++k2) {
-              const uint64_t xadv = uint64_t((k2 * 2 * GB) >> 4);             // 16 tokens = two 8-token groups
-              const uint64_t dxh = umma_desc_mn_sw128(xs + m0 * 1024, 1024, GB) + xadv;
-              const uint64_t dxl = umma_desc_mn_sw128(xs + (NKB + m0) * 1024, 1024, GB) + xadv;
-              const uint64_t da = umma_desc_k_sw128(as + (k2 >> 2) * (2 * SP * 128), 1024) + uint64_t(((k2 & 3) * 32) >> 4);
-              umma_f16(d_tmem, dxh, da, id2w, (g2 | k2) ? 1u : 0u);
-              umma_f16(d_tmem, dxl, da, id2n, 1u);
-            }
-          }
-          umma_commit(&ctl.xempty[set]);    // operand tile, a tile and the logits columns of this set may be overwritten
-          ++g2;
-          progress = true;
-        }
-        if (progress) {
-          t_idle = 0;
-        } else {
-          const long long now = clock64();
-          if (t_idle == 0) t_idle = now;
-          else if (now - t_idle > 4000000000LL) {
-            printf("sdb200: slot_attend_fused MMA issuer stalled (block %d,%d g1 %d g2 %d)\n", blockIdx.x, blockIdx.y, g1, g2);
-            __trap();
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t xadv = uint64_t((kb * 1024 + k * 32) >> 4);
+            const uint64_t qadv = uint64_t((kb * (2 * SP * 128) + k * 32) >> 4);
+            umma_f16(d_tmem, dxh0 + xadv, dq0 + qadv, id1, (kb | k) ? 1u : 0u);
+            umma_f16(d_tmem, dxl0 + xadv, dq0 + qadv, id1, 1u);
           }
         }
+        umma_commit(&ctl.lfull[set]);
+        SF_T(1, i, 1);
+      }
+    }
+    __syncwarp();
+  } else if (warp == SF_G2_WARP) {
+    // ================================================================ MMA issuer 2: weighted-sum product
+    if (lane == 0) {
+      const uint32_t id2 = umma_idesc_f16(SF_TILE, 2 * SP) | (1u << 15);     // A MN-major (features^T), B K-major
+      const uint32_t x0 = smem_u32(xop), a0 = smem_u32(aop);
+      for (int i = 0; i < ntiles; ++i) {
+        const int set = i % NSETS;
+        // per 64-channel block kb: D_kb[128 x 2SP] += [X_hi^T ; X_lo^T][(64+64) x 128 tokens] * [A_hi ; A_lo]^T
+        //   (rows 0..63: hi plane of channels 64 kb.., rows 64..127: lo plane -- the two MN blocks of the A descriptor)
+        mbar_spin(&ctl.afull[set], (i / NSETS) & 1);
+        tc_fence_after();
+        SF_T(2, i, 0);
+        const uint32_t xs = x0 + set * C::TILE_BYTES;
+        const uint64_t da0 = umma_desc_k_sw128(a0 + set * C::ABYTES, 1024);
+        const uint64_t dx0 = umma_desc_mn_sw128(xs, NKB * 1024, GB);
+        const uint32_t first = i ? 1u : 0u;
+#pragma unroll
+        for (int kb = 0; kb < NKB; ++kb) {
+          const uint32_t d_tmem = tmem + 128u + uint32_t(2 * SP * kb);
+#pragma unroll
+          for (int k2 = 0; k2 < SF_TILE / 16; ++k2) {
+            const uint64_t xadv = uint64_t((kb * 1024 + k2 * 2 * GB) >> 4);   // 16 tokens = two 8-token groups
+            const uint64_t aadv = uint64_t(((k2 >> 2) * (2 * SP * 128) + (k2 & 3) * 32) >> 4);
+            umma_f16(d_tmem, dx0 + xadv, da0 + aadv, id2, k2 ? 1u : first);
+          }
+        }
+        umma_commit(&ctl.xempty[set]);    // operand tile, a tile and the logits columns of this set may be overwritten
+        SF_T(2, i, 1);
       }
       umma_commit(&ctl.ufull);
     }
     __syncwarp();
-  } else if (warp >= SF_SOFT_WARPS) {
+  } else if (is_conv) {
     // ================================================================ converters: LayerNorm + fp16 split, in place
-    // warp cw owns token group (cw & 3) of every second chunk; 8 lanes per token, two rounds of 4 tokens
-    const int cw = warp - SF_SOFT_WARPS, sub = lane >> 3, j = lane & 7;
-    const int g = cw & 3;
-    constexpr int NV = DIN / 32;                          // float4 per lane per token
+    // a warp owns whole 8-token groups (the unit of the in-place rewrite); 8 lanes per token, two rounds of 4 tokens
     for (int i = 0; i < ntiles; ++i) {
       const int set = i % NSETS;
-      for (int cc = cw >> 2; cc < SF_CPT; cc += 2) {
+      for (int gi = cw; gi < SF_GROUPS; gi += CW) {
+        const int cc = gi >> 2;
         const int c = i * SF_CPT + cc;
-        uint8_t* grp = xop + set * C::TILE_BYTES + cc * C::CHUNK_BYTES + g * GB;   // fp32 rows in, UMMA atoms out
+        uint8_t* grp = xop + set * C::TILE_BYTES + gi * GB;   // fp32 rows in, UMMA atoms out
         float4 v[2][NV];
-        bool valid[2];
         if (c < nchunks) mbar_wait_warp(&ctl.sfull[set * SF_CPT + cc], (i / NSETS) & 1, lane);   // CTA-uniform branch
         else mbar_wait_warp(&ctl.xempty[set], ((i / NSETS) & 1) ^ 1, lane);   // zero-filled chunk: the set must still be free
+        if (lane == 0 && gi == 0) SF_T(3, i, 0);
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-          const int tg = (sub & 1) + 4 * (sub >> 1) + 2 * q;          // token within the group: rows {0,1,4,5} / {2,3,6,7}
-          valid[q] = (c * SF_CT + g * 8 + tg) < ntok;
-          const float* row = reinterpret_cast<const float*>(grp) + tg * DIN;
+          const int tg = tok_in_group(q);
+          const bool valid = (i * SF_TILE + gi * 8 + tg) < ntok;
+          const float* row = reinterpret_cast<const float*>(grp) + tg * DIN + 4 * j;
 #pragma unroll
-          for (int k = 0; k < NV; ++k)
-            v[q][k] = valid[q] ? *reinterpret_cast<const float4*>(row + 4 * (j + 8 * k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int k = 0; k < NV; ++k) {
+            v[q][k] = *reinterpret_cast<const float4*>(row + 32 * k);   // stale bytes if !valid: zeroed below, no branch
+            if (!valid) v[q][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
         }
         __syncwarp();                                       // all fp32 rows of the group are in registers
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-          const int tg = (sub & 1) + 4 * (sub >> 1) + 2 * q;
+          const int tg = tok_in_group(q);
           float sum = 0.f;
 #pragma unroll
           for (int k = 0; k < NV; ++k) sum += (v[q][k].x + v[q][k].y) + (v[q][k].z + v[q][k].w);
@@ -322,28 +383,39 @@ slot_attend_fused_kernel(const float* __restrict__ x, const float* __restrict__ 
           sq += __shfl_xor_sync(0xffffffffu, sq, 1);
           sq += __shfl_xor_sync(0xffffffffu, sq, 2);
           sq += __shfl_xor_sync(0xffffffffu, sq, 4);
-          const float rstd = valid[q] ? 1.f / sqrtf(sq * (1.f / DIN) + ln_eps) : 0.f;
+          const float rstd = rsqrtf(sq * (1.f / DIN) + ln_eps);   // zero rows stay zero
+          // swizzled 16-B chunk of channel block (j >> 1) + 4 (k & 1) in row tg: (chunk ^ tg); the k parity only flips bit 6
+          const uint32_t o0 = tg * 128 + ((((j >> 1) ^ (tg & 3)) | ((tg >> 2) << 2)) << 4) + (j & 1) * 8;
+          uint8_t* w0 = grp + o0;
+          uint8_t* w1 = grp + (o0 ^ 64u);
 #pragma unroll
           for (int k = 0; k < NV; ++k) {
             uint2 hi, lo;
             split2(v[q][k].x * rstd, v[q][k].y * rstd, hi.x, lo.x);
             split2(v[q][k].z * rstd, v[q][k].w * rstd, hi.y, lo.y);
-            const int kb = k >> 1;
-            const int col16 = (j >> 1) + 4 * (k & 1);
-            const uint32_t off = kb * 1024 + tg * 128 + ((col16 ^ tg) << 4) + (j & 1) * 8;
-            *reinterpret_cast<uint2*>(grp + off) = hi;
-            *reinterpret_cast<uint2*>(grp + NKB * 1024 + off) = lo;
+            uint8_t* dst = ((k & 1) ? w1 : w0) + (k >> 1) * 1024;
+            *reinterpret_cast<uint2*>(dst) = hi;
+            *reinterpret_cast<uint2*>(dst + NKB * 1024) = lo;
           }
         }
       }
       fence_proxy_async_smem();
       __syncwarp();
+      if (lane == 0 && cw == 0) SF_T(3, i, 1);
+      if (lane == 0 && cw == CW - 1) SF_T(3, i, 3);
       if (lane == 0) mbar_arrive(&ctl.xfull[set]);
     }
   } else {
     // ================================================================ softmax over slots; thread <-> token <-> TMEM lane
     const int r = warp * 32 + lane;
     const uint32_t lane_addr = tmem + (uint32_t(warp * 32) << 16);
+    // a operand stores: tokens (2m, 2m+1) share a 32-bit word of a slot row; even lanes write slot rows s, odd lanes
+    // rows s + 4 (other half of the 128-B bank space) -> every 32-lane store is one conflict-free wavefront
+    const int col = r & 63, odd = lane & 1;
+    const uint32_t a_lane = (r >> 6) * (2 * SP * 128) + (odd ? 4 * 128 : 0) + (((col >> 3) ^ (odd ? 4 : 0)) << 4) +
+                            ((col & 7) >> 1) * 4;
+    const uint32_t sel_send = odd ? 0x5410u : 0x7632u;
+    const uint32_t sel_hi = odd ? 0x3254u : 0x5410u, sel_lo = odd ? 0x3276u : 0x7610u;
     float cs[SP];
 #pragma unroll
     for (int s = 0; s < SP; ++s) cs[s] = 0.f;
@@ -351,6 +423,7 @@ slot_attend_fused_kernel(const float* __restrict__ x, const float* __restrict__ 
       const int set = i % NSETS;
       mbar_wait_warp(&ctl.lfull[set], (i / NSETS) & 1, lane);
       tc_fence_after();
+      if (tid == 0) SF_T(4, i, 0);
       float l[SP];
       tmem_ld_folded<SP>(lane_addr + 64u * set, l);
       const int n = n_begin + i * SF_TILE + r;
@@ -368,54 +441,69 @@ slot_attend_fused_kernel(const float* __restrict__ x, const float* __restrict__ 
         sum += l[s];
       }
       const float inv = 1.f / sum;
-      const int kb = r >> 6, col = r & 63;
-      uint8_t* arow = aop + set * C::ABYTES + kb * (2 * SP * 128) + (col & 7) * 2;
+#pragma unroll
+      for (int s = 0; s < SP; ++s) l[s] *= inv;                     // softmax over slots
+      if (seg_mask && valid) {
+        float* mrow = seg_mask + (b * S) * N + n;
+#pragma unroll
+        for (int s = 0; s < SP; ++s)
+          if (s < S) mrow[(long long)s * N] = l[s];
+      }
 #pragma unroll
       for (int s = 0; s < SP; ++s) {
-        const float p = l[s] * inv;
-        if (seg_mask && valid && s < S) seg_mask[(b * S + s) * N + n] = p;
-        const float a = (valid && s < S) ? p + eps : 0.f;
-        cs[s] += a;
-        const float as = a * SF_ASCALE;
-        const __half h = __float2half_rn(as);
-        const __half lo = __float2half_rn(as - __half2float(h));
-        const uint32_t off = s * 128 + (((col >> 3) ^ (s & 7)) << 4);
-        *reinterpret_cast<__half*>(arow + off) = h;
-        *reinterpret_cast<__half*>(arow + SP * 128 + off) = lo;
+        l[s] = (valid && s < S) ? l[s] + eps : 0.f;                   // a = attn + eps (zero for padding slots / tokens)
+        cs[s] += l[s];
+      }
+      uint8_t* abase = aop + set * C::ABYTES;
+#pragma unroll
+      for (int pq = 0; pq < SP / 2; ++pq) {
+        const int s = (pq & 3) + 8 * (pq >> 2);                      // slots s and s + 4
+        uint32_t H, L;
+        split2(l[s] * SF_ASCALE, l[s + 4] * SF_ASCALE, H, L);
+        const uint32_t recv = __shfl_xor_sync(0xffffffffu, __byte_perm(H, L, sel_send), 1);
+        uint8_t* dst = abase + ((a_lane ^ ((s & 3) << 4)) + s * 128);
+        *reinterpret_cast<uint32_t*>(dst) = __byte_perm(H, recv, sel_hi);
+        *reinterpret_cast<uint32_t*>(dst + SP * 128) = __byte_perm(L, recv, sel_lo);
       }
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
+      if (tid == 0) SF_T(4, i, 1);
       if (lane == 0) mbar_arrive(&ctl.afull[set]);
     }
-    // ---- drain U^T (lane <-> channel, column <-> slot) and the column sums
+    // ---- drain U^T: block kb, TMEM lane r < 64: hi-plane part of channel 64 kb + r; lane 64 + r: its lo-plane part
     mbar_wait_warp(&ctl.ufull, 0, lane);
     tc_fence_after();
-    constexpr int NH = NKB > 2 ? 2 : 1;
+    if (tid == 0) SF_T(5, 0, 0);
+    float* scr = reinterpret_cast<float*>(xop);       // [NKB][SP][64] fp32; the operand tiles are dead now
 #pragma unroll
-    for (int h = 0; h < NH; ++h) {
-      const int ch = (h == 0 ? 0 : (NKB - 2) * 64) + r;
-      const bool need = h == 0 || ch >= 128;
+    for (int kb = 0; kb < NKB; ++kb) {
       float u[SP];
-      tmem_ld_folded<SP>(lane_addr + 128u + 64u * h, u);
-      if (need) {
+      tmem_ld_folded<SP>(lane_addr + 128u + uint32_t(2 * SP * kb), u);
+      if (r >= 64) {
+#pragma unroll
+        for (int s = 0; s < SP; ++s) scr[(kb * SP + s) * 64 + (r - 64)] = u[s];
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(SF_SOFT_WARPS * 32) : "memory");
+      if (r < 64) {
 #pragma unroll
         for (int s = 0; s < SP; ++s)
-          if (s < S) my_upd[s * DIN + ch] = u[s];
+          if (s < S) my_upd[s * DIN + kb * 64 + r] = u[s] + scr[(kb * SP + s) * 64 + r];
       }
     }
 #pragma unroll
     for (int s = 0; s < SP; ++s) {
-      const float v = warp_sum(cs[s]);
-      if (lane == 0) ctl.cs_scr[warp][s] = v;
+      const float w = warp_sum(cs[s]);
+      if (lane == 0) ctl.cs_scr[warp][s] = w;
     }
     asm volatile("bar.sync 1, %0;" ::"n"(SF_SOFT_WARPS * 32) : "memory");
     if (tid < S) my_cs[tid] = (ctl.cs_scr[0][tid] + ctl.cs_scr[1][tid]) + (ctl.cs_scr[2][tid] + ctl.cs_scr[3][tid]);
+    if (tid == 0) SF_T(5, 0, 1);
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == SF_MMA_WARP) {
+  if (warp == SF_G1_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem, SF_TMEM_COLS);
   }
@@ -453,16 +541,18 @@ static int sf_chunks(int64_t B, int64_t N) {
 
 template <int DIN, int SP>
 static int launch_fused(const float* x, const float* qa, int ldq, float* seg_mask, float* part_upd, float* part_cs,
-                        int64_t B, int N, int S, int chunks, float ln_eps, float eps, cudaStream_t st) {
+                        int64_t B, int N, int S, int chunks, float ln_eps, float eps, long long* dbg, cudaStream_t st) {
   using C = SfCfg<DIN, SP>;
-  auto kern = slot_attend_fused_kernel<DIN, SP>;
+  constexpr int CW = (SP == 16 && DIN <= 192) ? 16 : 8;
+  constexpr int SF_THREADS = 32 * (SF_SOFT_WARPS + CW + 3);
+  auto kern = slot_attend_fused_kernel<DIN, SP, CW>;
   static bool attr = false;
   if (!attr) {
     SDB_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     attr = true;
   }
   dim3 grid(chunks, (unsigned)B);
-  kern<<<grid, SF_THREADS, C::SMEM, st>>>(x, qa, ldq, seg_mask, part_upd, part_cs, N, S, chunks, ln_eps, eps);
+  kern<<<grid, SF_THREADS, C::SMEM, st>>>(x, qa, ldq, seg_mask, part_upd, part_cs, N, S, chunks, ln_eps, eps, dbg);
   SDB_LAUNCH_CHECK();
   return 0;
 }
@@ -470,6 +560,13 @@ static int launch_fused(const float* x, const float* qa, int ldq, float* seg_mas
 }  // namespace sdb
 
 using namespace sdb;
+
+static long long* g_sf_dbg = nullptr;
+/* debug: device buffer of 6*64 int64 that receives the timeline of CTA (0,0) of every following launch (NULL = off) */
+extern "C" int sdb_slot_attend_fused_debug(void* buf) {
+  g_sf_dbg = reinterpret_cast<long long*>(buf);
+  return 0;
+}
 
 extern "C" int sdb_slot_attend_fused_supported(int64_t S, int64_t Din) {
   if (S < 1 || S > 32) return 0;
@@ -503,9 +600,9 @@ extern "C" int sdb_slot_attend_fused(const float* x, const float* qa, int64_t ld
 #define SF_CASE(DD)                                                                                                  \
   if (Din == DD) {                                                                                                   \
     rc = (S <= 16) ? launch_fused<DD, 16>(x, qa, (int)ldq, seg_mask, part_upd, part_cs, B, (int)N, (int)S, chunks,   \
-                                          ln_eps, eps, st)                                                           \
+                                          ln_eps, eps, g_sf_dbg, st)                                                 \
                    : launch_fused<DD, 32>(x, qa, (int)ldq, seg_mask, part_upd, part_cs, B, (int)N, (int)S, chunks,   \
-                                          ln_eps, eps, st);                                                          \
+                                          ln_eps, eps, g_sf_dbg, st);                                                \
   }
   SF_CASE(128) else SF_CASE(192) else SF_CASE(256)
 #undef SF_CASE
