@@ -154,6 +154,11 @@ int sdb_timestep_embedding_pack(const float* t, void* out, int64_t B, int dim, v
  * out: packed [2][B*Lq][heads*d] (feeds to_out) */
 int sdb_attention_pack(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
                        void* out, int64_t B, int64_t Lq, int64_t Lk, int heads, int d, float scale, void* stream);
+/* same contract on the tensor cores (tcgen05, fp32-faithful split-fp16 products, online softmax over 64-key chunks);
+ * head dim 32 only (sdb_attention_tc_supported) */
+int sdb_attention_tc_supported(int64_t heads, int64_t d, int64_t ldq, int64_t ldk, int64_t ldv);
+int sdb_attention_tc(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv, void* out,
+                     int64_t B, int64_t Lq, int64_t Lk, int heads, int d, float scale, void* stream);
 
 /* ------------------------------------------------------------------ small-channel convolutions
  * input conv (unet.py:408): x NCHW [B,Cin,H,W] (Cin small, e.g. 3) -> NHWC fp32 [B,H,W,Cout], 3x3 pad 1 */

@@ -299,9 +299,17 @@ def groupnorm_finalize(gsum1, gsum2, C1, C2, B, HW, G, eps):
 
 
 # ---------------------------------------------------------------- attention / convs / slot attention / sampler
-def attention_pack(q, k, v, B, Lq, Lk, heads, d, scale):
+ATTENTION_TC = True   # tensor-core attention cores (csrc/attention_tc.cu) when the shape is supported
+
+
+def attention_pack(q, k, v, B, Lq, Lk, heads, d, scale, tc=None):
     """q/k/v: 2-D strided views [B*L, heads*d] (last dim contiguous) -> Packed [B*Lq, heads*d]."""
     out = Packed.empty(B * Lq, heads * d, q.device)
+    use_tc = ATTENTION_TC if tc is None else tc
+    if use_tc and lib().sdb_attention_tc_supported(heads, d, q.stride(0), k.stride(0), v.stride(0)):
+        check(lib().sdb_attention_tc(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out.t), B, Lq, Lk,
+                                     heads, d, scale, _stream()), 'sdb_attention_tc')
+        return out
     check(lib().sdb_attention_pack(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out.t), B, Lq, Lk,
                                    heads, d, scale, _stream()), 'sdb_attention_pack')
     return out

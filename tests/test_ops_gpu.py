@@ -256,20 +256,37 @@ def test_geglu_and_timestep(ops):
     assert (got - timestep_embedding(ti.cpu(), 128)).abs().max().item() < 2e-4
 
 
-@pytest.mark.parametrize('Lq,Lk,heads', [(256, 256, 8), (64, 64, 12), (16, 16, 16), (256, 11, 8), (100, 24, 4),
-                                         (784, 784, 2)])
-def test_attention(ops, Lq, Lk, heads):
+@pytest.mark.parametrize('tc', [True, False])
+@pytest.mark.parametrize('Lq,Lk,heads', [(256, 256, 8), (64, 64, 12), (16, 16, 16), (256, 11, 8), (64, 11, 12),
+                                          (16, 11, 16), (100, 37, 4), (1024, 1024, 4), (300, 130, 2), (256, 24, 8),
+                                          (3136, 7, 4)])
+def test_attention(ops, Lq, Lk, heads, tc):
+    """attention core through the tensor-core kernel (tc) and the CUDA-core kernel, vs fp64 torch math"""
     B, d = 2, 32
     C = heads * d
     qkv = rnd(B * Lq, 3 * C, seed=26)
     kv = rnd(B * Lk, 2 * C, seed=27)
     q = qkv[:, :C]
     k, v = kv[:, :C], kv[:, C:]
-    out = ops.attention_pack(q, k, v, B, Lq, Lk, heads, d, d ** -0.5).unpack()
+    out = ops.attention_pack(q, k, v, B, Lq, Lk, heads, d, d ** -0.5, tc=tc).unpack()
     qd = q.double().view(B, Lq, heads, d).transpose(1, 2)
     kd = k.double().view(B, Lk, heads, d).transpose(1, 2)
     vd = v.double().view(B, Lk, heads, d).transpose(1, 2)
     ref = (torch.softmax(qd @ kd.transpose(-1, -2) * d ** -0.5, -1) @ vd).transpose(1, 2).reshape(B * Lq, C)
+    assert rel_l2(out, ref) < 3e-6
+
+
+def test_attention_tc_peaked(ops):
+    """large logits (peaked softmax) and a self-attention view of a fused q|k|v projection"""
+    B, L, heads, d = 3, 256, 8, 32
+    C = heads * d
+    qkv = rnd(B * L, 3 * C, seed=50, scale=4.0)
+    q, k, v = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]
+    out = ops.attention_pack(q, k, v, B, L, L, heads, d, d ** -0.5, tc=True).unpack()
+    qd = q.double().view(B, L, heads, d).transpose(1, 2)
+    kd = k.double().view(B, L, heads, d).transpose(1, 2)
+    vd = v.double().view(B, L, heads, d).transpose(1, 2)
+    ref = (torch.softmax(qd @ kd.transpose(-1, -2) * d ** -0.5, -1) @ vd).transpose(1, 2).reshape(B * L, C)
     assert rel_l2(out, ref) < 3e-6
 
 
