@@ -464,6 +464,80 @@ __global__ void conv3_out_kernel(const float* __restrict__ h, const float* __res
   }
 }
 
+// Tiled form of the output head: a CTA owns R output rows of one image, evaluates SiLU(GN(h)) ONCE per input pixel of
+// the R + 2 rows it needs (zero border = the conv padding) into shared memory, then every warp computes 4 adjacent
+// output pixels at a time (lanes split the channels, float4 smem reads, weight reads shared by the 4 pixels).
+template <int COUT_MAX>
+__global__ void __launch_bounds__(256)
+conv3_out_tile_kernel(const float* __restrict__ h, const float* __restrict__ stats, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, const float* __restrict__ w, const float* __restrict__ bias,
+                      float* __restrict__ y, int H, int W, int C, int G, int Cout, int R) {
+  extern __shared__ __align__(16) float smem_f[];
+  float* sw = smem_f;                         // [Cout][9][C]
+  float* sa = smem_f + Cout * 9 * C;          // [R + 2][W + 2][C]
+  const int64_t b = blockIdx.y;
+  const int y0 = blockIdx.x * R;
+  const int Wp = W + 2, c4n = C / 4, cpg = C / G;
+  for (int i = threadIdx.x; i < Cout * 9 * C; i += blockDim.x) {
+    const int c = i % C, tap = (i / C) % 9, o = i / (9 * C);
+    sw[i] = w[(o * C + c) * 9 + tap];
+  }
+  for (int i = threadIdx.x; i < (R + 2) * Wp * c4n; i += blockDim.x) {
+    const int c = (i % c4n) * 4, xp = (i / c4n) % Wp, rr = i / (c4n * Wp);
+    const int yi = y0 - 1 + rr, xi = xp - 1;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (yi >= 0 && yi < H && xi >= 0 && xi < W) {
+      const float4 v = *reinterpret_cast<const float4*>(h + ((b * H + yi) * W + xi) * C + c);
+      const float4 ga = *reinterpret_cast<const float4*>(gamma + c), be = *reinterpret_cast<const float4*>(beta + c);
+      const int g = c / cpg;                  // C / G is a multiple of 4: the four channels share a group
+      const float mean = stats[(b * G + g) * 2], rstd = stats[(b * G + g) * 2 + 1];
+      a.x = silu_f((v.x - mean) * rstd * ga.x + be.x);
+      a.y = silu_f((v.y - mean) * rstd * ga.y + be.y);
+      a.z = silu_f((v.z - mean) * rstd * ga.z + be.z);
+      a.w = silu_f((v.w - mean) * rstd * ga.w + be.w);
+    }
+    *reinterpret_cast<float4*>(sa + (rr * Wp + xp) * C + c) = a;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int rows = min(R, H - y0);
+  const int quads = rows * (W / 4);
+  for (int qd = warp; qd < quads; qd += nwarps) {
+    const int yr = qd / (W / 4), x0 = (qd % (W / 4)) * 4;
+    float acc[4][COUT_MAX];
+#pragma unroll
+    for (int px = 0; px < 4; ++px)
+#pragma unroll
+      for (int o = 0; o < COUT_MAX; ++o) acc[px][o] = 0.f;
+    for (int c = lane * 4; c < C; c += 128) {
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int ky = tap / 3, kx = tap % 3;
+        float4 wv[COUT_MAX];
+#pragma unroll
+        for (int o = 0; o < COUT_MAX; ++o)
+          wv[o] = o < Cout ? *reinterpret_cast<const float4*>(sw + (o * 9 + tap) * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int px = 0; px < 4; ++px) {
+          const float4 a = *reinterpret_cast<const float4*>(sa + ((yr + ky) * Wp + x0 + px + kx) * C + c);
+#pragma unroll
+          for (int o = 0; o < COUT_MAX; ++o)
+            acc[px][o] += (a.x * wv[o].x + a.y * wv[o].y) + (a.z * wv[o].z + a.w * wv[o].w);
+        }
+      }
+    }
+#pragma unroll
+    for (int px = 0; px < 4; ++px)
+#pragma unroll
+      for (int o = 0; o < COUT_MAX; ++o) {
+        if (o < Cout) {
+          const float sum = warp_sum(acc[px][o]);
+          if (lane == 0) y[((b * Cout + o) * H + y0 + yr) * W + x0 + px] = sum + bias[o];
+        }
+      }
+  }
+}
+
 // ------------------------------------------------------------------ DPM-Solver glue
 // x0 = (x - sigma*eps)/alpha, then nearest codebook row.  One thread per latent pixel; codebook in smem.
 __global__ void dpm_x0_kernel(const float* __restrict__ x, const float* __restrict__ eps, float alpha, float sigma,
@@ -637,6 +711,23 @@ extern "C" int sdb_conv3_out(const float* h, const float* stats, const float* ga
   SDB_REQUIRE(Cout >= 1 && Cout <= 4 && C % G == 0, "sdb_conv3_out: Cout=%lld must be in 1..4", (long long)Cout);
   const size_t smem = (size_t)Cout * 9 * C * 4;
   SDB_REQUIRE(smem <= 48 * 1024, "sdb_conv3_out: C=%lld too large", (long long)C);
+  // tiled kernel: 2 output rows per CTA when the shapes allow it (activation tile + weights in shared memory)
+  const int R = 2;
+  const size_t smem_t = smem + (size_t)(R + 2) * (W + 2) * C * 4;
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  if (W % 4 == 0 && C % 4 == 0 && (C / G) % 4 == 0 && smem_t <= 110 * 1024 && B <= 65535 && al16(h) && al16(gamma) &&
+      al16(beta)) {
+    static size_t attr = 0;
+    if (smem_t > attr) {
+      SDB_CHECK(cudaFuncSetAttribute(conv3_out_tile_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+      attr = smem_t;
+    }
+    dim3 grid((unsigned)cdiv(H, R), (unsigned)B);
+    conv3_out_tile_kernel<4><<<grid, 256, smem_t, as_stream(stream)>>>(h, stats, gamma, beta, w, bias, y, (int)H, (int)W,
+                                                                       (int)C, G, (int)Cout, R);
+    SDB_LAUNCH_CHECK();
+    return 0;
+  }
   conv3_out_kernel<4><<<grid_for(B * H * W, 8, 4), 256, smem, as_stream(stream)>>>(h, stats, gamma, beta, w, bias, y, B,
                                                                                   (int)H, (int)W, (int)C, G, (int)Cout);
   SDB_LAUNCH_CHECK();

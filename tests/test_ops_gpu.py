@@ -290,8 +290,8 @@ def test_attention_tc_peaked(ops):
     assert rel_l2(out, ref) < 3e-6
 
 
-def test_conv_in_out(ops):
-    B, H, W = 3, 32, 32
+@pytest.mark.parametrize('B,H,W', [(3, 32, 32), (2, 7, 8), (1, 56, 56)])
+def test_conv_in_out(ops, B, H, W):
     x = rnd(B, 3, H, W, seed=28)
     w, b = rnd(128, 3, 3, 3, seed=29, scale=0.2), rnd(128, seed=30)
     y = ops.conv3_in(x, w, b)

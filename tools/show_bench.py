@@ -1,5 +1,7 @@
 import sys, json
-for l in sys.stdin:
+# usage: python tools/show_bench.py < bench.json   (or pass the file name)
+src = open(sys.argv[1]) if len(sys.argv) > 1 else sys.stdin
+for l in src:
     l = l.strip()
     if l.startswith('{'):
         d = json.loads(l)
