@@ -610,7 +610,7 @@ def main():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--batch', type=int, default=64, help='per-GPU batch')
+    ap.add_argument('--batch', type=int, default=256, help='per-GPU batch of the sampling workload')
     ap.add_argument('--train-batch', type=int, default=64, help='per-GPU batch of the training-step measurement')
     ap.add_argument('--train-steps', type=int, default=5)
     ap.add_argument('--no-train', action='store_true', help='skip the training-step measurement')

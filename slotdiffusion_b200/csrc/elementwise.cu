@@ -582,6 +582,74 @@ __global__ void dpm_x0_kernel(const float* __restrict__ x, const float* __restri
   }
 }
 
+// Three-channel latents (every shipped VQ-VAE, quantize.py:80-94): register-blocked nearest-code search.  A block stages
+// the codebook as (e0, e1, e2, |e|^2) float4 rows in shared memory once; every thread scores PX pixels against each
+// broadcast row (one LDS.128 feeds PX * 5 FMA-pipe operations), strict '<' in increasing code order = argmin's first
+// minimum.  Same expanded distance |z|^2 + |e|^2 - 2 z.e as the reference, with the contraction order pinned by fmaf.
+constexpr int VQ_PX = 4;
+constexpr int VQ_THREADS = 128;
+__global__ void __launch_bounds__(VQ_THREADS)
+dpm_x0_vq3_kernel(const float* __restrict__ x, const float* __restrict__ eps, float alpha, float sigma,
+                  const float* __restrict__ codebook, int ncodes, float* __restrict__ x0, int* __restrict__ idx,
+                  int64_t B, int64_t HW) {
+  extern __shared__ __align__(16) float4 scb4[];   // [ncodes]
+  for (int i = threadIdx.x; i < ncodes; i += VQ_THREADS) {
+    const float e0 = codebook[i * 3], e1 = codebook[i * 3 + 1], e2 = codebook[i * 3 + 2];
+    float nrm = 0.f;
+    nrm += e0 * e0;
+    nrm += e1 * e1;
+    nrm += e2 * e2;
+    scb4[i] = make_float4(e0, e1, e2, nrm);
+  }
+  __syncthreads();
+  const int64_t total = B * HW;
+  const int64_t p0 = (int64_t)blockIdx.x * (VQ_THREADS * VQ_PX) + threadIdx.x;
+  float z0[VQ_PX], z1[VQ_PX], z2[VQ_PX], zz[VQ_PX], best[VQ_PX];
+  int bi[VQ_PX];
+#pragma unroll
+  for (int i = 0; i < VQ_PX; ++i) {
+    const int64_t p = p0 + (int64_t)i * VQ_THREADS;
+    z0[i] = z1[i] = z2[i] = 0.f;
+    if (p < total) {
+      const int64_t b = p / HW, q = p % HW;
+      const int64_t o = b * 3 * HW + q;
+      z0[i] = (x[o] - sigma * eps[o]) / alpha;
+      z1[i] = (x[o + HW] - sigma * eps[o + HW]) / alpha;
+      z2[i] = (x[o + 2 * HW] - sigma * eps[o + 2 * HW]) / alpha;
+    }
+    float t = 0.f;
+    t += z0[i] * z0[i];
+    t += z1[i] * z1[i];
+    t += z2[i] * z2[i];
+    zz[i] = t;
+    best[i] = INFINITY;
+    bi[i] = 0;
+  }
+#pragma unroll 4
+  for (int j = 0; j < ncodes; ++j) {
+    const float4 e = scb4[j];
+#pragma unroll
+    for (int i = 0; i < VQ_PX; ++i) {
+      const float dot = fmaf(z2[i], e.z, fmaf(z1[i], e.y, z0[i] * e.x));
+      const float d = fmaf(-2.f, dot, zz[i] + e.w);
+      if (d < best[i]) { best[i] = d; bi[i] = j; }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < VQ_PX; ++i) {
+    const int64_t p = p0 + (int64_t)i * VQ_THREADS;
+    if (p < total) {
+      const int64_t b = p / HW, q = p % HW;
+      const int64_t o = b * 3 * HW + q;
+      const float4 e = scb4[bi[i]];
+      x0[o] = e.x;
+      x0[o + HW] = e.y;
+      x0[o + 2 * HW] = e.z;
+      if (idx) idx[p] = bi[i];
+    }
+  }
+}
+
 __global__ void lincomb_kernel(float* __restrict__ out, const float* __restrict__ x, const float* __restrict__ m0,
                                const float* __restrict__ m1, float a, float b, float c, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -737,6 +805,20 @@ extern "C" int sdb_conv3_out(const float* h, const float* stats, const float* ga
 extern "C" int sdb_dpm_x0(const float* x, const float* eps, float alpha, float sigma, const float* codebook,
                           int64_t ncodes, float* x0, int32_t* idx, int64_t B, int64_t C, int64_t HW, void* stream) {
   SDB_REQUIRE(x && eps && x0 && B > 0 && C > 0 && C <= 8 && HW > 0, "sdb_dpm_x0: bad args (C <= 8)");
+  if (codebook && C == 3 && ncodes > 0 && (size_t)ncodes * 16 <= 200 * 1024) {
+    const size_t smem4 = (size_t)ncodes * 16;
+    static size_t attr4 = 0;
+    if (smem4 > 48 * 1024 && smem4 > attr4) {
+      SDB_CHECK(cudaFuncSetAttribute(dpm_x0_vq3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+      attr4 = smem4;
+    }
+    const int64_t blocks = cdiv(B * HW, VQ_THREADS * VQ_PX);
+    SDB_REQUIRE(blocks < (1ll << 31), "sdb_dpm_x0: grid too large");
+    dpm_x0_vq3_kernel<<<(unsigned)blocks, VQ_THREADS, smem4, as_stream(stream)>>>(x, eps, alpha, sigma, codebook,
+                                                                                 (int)ncodes, x0, idx, B, HW);
+    SDB_LAUNCH_CHECK();
+    return 0;
+  }
   size_t smem = codebook ? (size_t)ncodes * (C + 1) * 4 : 0;
   SDB_REQUIRE(smem <= 200 * 1024, "sdb_dpm_x0: codebook too large for shared memory");
   static size_t attr = 0;
