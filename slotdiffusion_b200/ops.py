@@ -60,6 +60,22 @@ class Packed:
         return t[0] + t[1]
 
 
+def slot_attention_fold_math(wq, wk, wv, gamma, beta, w_ih, b_ih, scale):
+    """fp64 algebra of the Slot-Attention weight fold (pure torch, any device; unit-tested on CPU against the oracle):
+    returns (W_qa [Din+4, D], W_iv [3D, Din], b_iv [3D]) such that with n = LayerNorm-without-affine(inputs),
+      logits = n @ W_qa[:Din] @ LN_q(slots)^T + W_qa[Din] @ LN_q(slots)^T      ( = scale * k q^T of slot_attention.py:84)
+      gi     = U @ W_iv^T + b_iv,  U = (a^T n) / sum_n a                        ( = GRU input projection of updates, :91-97)"""
+    wq, wk, wv, g, b, wih, bih = [t.double() for t in (wq, wk, wv, gamma, beta, w_ih, b_ih)]
+    Din = wk.shape[1]
+    wqk = (wk.t() @ wq) * scale                               # [Din, D]
+    wqa = torch.zeros(Din + 4, wq.shape[1], dtype=torch.float64, device=wq.device)
+    wqa[:Din] = wqk * g[:, None]
+    wqa[Din] = b @ wqk
+    wiv = (wih @ wv) * g[None, :]                             # [3D, Din]
+    biv = wih @ (wv @ b) + bih
+    return wqa, wiv, biv
+
+
 # ---------------------------------------------------------------- weights (cached per parameter version)
 class WeightCache:
     """Packed copies of parameters, re-packed when the parameter storage or version changes
@@ -102,14 +118,7 @@ class WeightCache:
               mod.norm_inputs.bias, mod.gru.weight_ih, mod.gru.bias_ih)
 
         def make():
-            wq, wk, wv, g, b, wih, bih = [p.detach().double() for p in ps]
-            Din = wk.shape[1]
-            wqk = (wk.t() @ wq) * mod.attn_scale                      # [Din, D]
-            wqa = torch.zeros(Din + 4, wq.shape[1], dtype=torch.float64, device=wq.device)
-            wqa[:Din] = wqk * g[:, None]
-            wqa[Din] = b @ wqk
-            wiv = (wih @ wv) * g[None, :]                             # [3D, Din]
-            biv = wih @ (wv @ b) + bih
+            wqa, wiv, biv = slot_attention_fold_math(*[p.detach() for p in ps], mod.attn_scale)
             return dict(w_qa=pack_weight(wqa.float().contiguous()), w_iv=pack_weight(wiv.float().contiguous()),
                         b_iv=biv.float().contiguous())
         return self._get('sa_fold', ps, make)

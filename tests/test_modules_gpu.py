@@ -141,6 +141,47 @@ def test_unet_batch64_properties():
     assert rel_l2(y[10:12], ref) < TIGHT
 
 
+def test_unet_coco_latent56_ctx256_matches_oracle():
+    """BASELINE configs[4] geometry (DINOSAUR+SlotDiffusion COCO): 56x56 latents, 7 slots of size 256 -- non-power-of-2
+    widths (56/28/14/7) through the implicit-GEMM convolutions and 3136/784/196/49-token attention."""
+    cfg_over = dict(context_dim=256)
+    net, sd, cfg = make_unet(cfg_over, seed=33)
+    x, ctx = seeded((1, 3, 56, 56), 81).cuda(), seeded((1, 7, 256), 82).cuda()
+    t = torch.tensor([421.5]).cuda()
+    with torch.no_grad():
+        y = net(x, t, context=ctx)
+    ref = unet_ref.unet_forward(sd, x.cpu(), t.cpu(), ctx.cpu(), cfg)
+    assert rel_l2(y, ref) < TIGHT
+
+
+def test_unet_movie_24slots_matches_oracle():
+    """BASELINE configs[3] geometry (MOVi-E): 24 slots of size 192 as cross-attention context."""
+    net, sd, cfg = make_unet(seed=34)
+    x, ctx = seeded((2, 3, 32, 32), 83).cuda(), seeded((2, 24, 192), 84).cuda()
+    t = torch.tensor([3, 977]).cuda()
+    with torch.no_grad():
+        y = net(x, t, context=ctx)
+    ref = unet_ref.unet_forward(sd, x.cpu(), t.cpu(), ctx.cpu(), cfg)
+    assert rel_l2(y, ref) < TIGHT
+
+
+def test_savi_per_frame_driver_matches_oracle():
+    """a6 (savi_diffusion.py:183-196): the module is called once per frame with the previous frame's slots; T = 3 frames,
+    15 slots, 2 iterations (the shipped MOVi config)."""
+    mod, p, x, s0, gw, iters = make_sa('sa_vid_movid')
+    T = 3
+    frames = [seeded(tuple(x.shape), 90 + f) for f in range(T)]
+    slots, ref = s0.cuda(), s0.double()
+    with torch.no_grad():
+        for f in range(T):
+            slots, mask = mod(frames[f].cuda(), slots)
+            ref, ref_m = sa_ref.slot_attention_forward(p, frames[f].double(), ref, iters)
+            assert rel_l2(slots, ref) < TIGHT
+            margin = ref_m.topk(2, dim=1).values
+            real, near = argmax_mismatch(mask, ref_m.argmax(1).numpy(), (margin[:, 0] - margin[:, 1]).numpy(), 1e-5)
+            assert real == 0, (f, real, near)
+
+
 def test_dpm_sampler_matches_reference_golden():
     from slotdiffusion_b200.dpm_solver import DPMSolverSampler
     g = golden('dpm')
