@@ -656,14 +656,29 @@ extern "C" int sdb_gemm(const SdbGemm* p, void* stream) {
   const bool wgrad_mode = (p->mode == SDB_A_WGRAD || p->mode == SDB_A_WGRAD_S2);
   if (wgrad_mode) g.bn = pick_bn(p->N, 128 * cg, 64 * cg);   // each CTA stages whole 64-column (128-byte) blocks of dY
   else g.bn = (cg == 2) ? pick_bn(p->N, 256, 32) : pick_bn(p->N, 128, geglu ? 32 : 16);
-  g.bnl = g.bn / cg;
   g.n_tiles_m = (int)cdiv(n_tiles_m1, cg);
-  g.n_tiles_n = (int)cdiv(p->N, g.bn);
   const int ksteps = g.kblocks * g.ntaps;
   const int units = sms / cg;
+  const bool can_split = !p->relu && !p->out_packed && !p->gsum;   // those epilogues need the complete sum
+  if (!wgrad_mode && !can_split && env_int("SDB_GEMM_NARROW", 1)) {
+    // under-filled grid that cannot use split-K (the GroupNorm-sum / packed / ReLU epilogues need complete sums): narrower
+    // N tiles put more SMs to work.  Cost model: waves * (bn + fixed per-tile overhead worth ~64 columns).
+    const int step = (cg == 2) ? 32 : (geglu ? 32 : 16);
+    long long best_cost = -1;
+    int best_bn = g.bn;
+    for (int bn = g.bn; bn >= 32 * cg && bn >= step; bn /= 2) {
+      if (bn % step) break;
+      const long long t = (long long)g.n_tiles_m * cdiv(p->N, bn);
+      const long long waves = cdiv(t, units);
+      const long long cost = waves * (bn + 64);
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_bn = bn; }
+    }
+    g.bn = best_bn;
+  }
+  g.bnl = g.bn / cg;
+  g.n_tiles_n = (int)cdiv(p->N, g.bn);
   const long long tiles = (long long)g.n_tiles_m * g.n_tiles_n;
   g.splits = 1;
-  const bool can_split = !p->relu && !p->out_packed && !p->gsum;   // those epilogues need the complete sum
   if (can_split && tiles * 4 < (long long)units * 3 && ksteps >= 8) {
     long long s = units / tiles;
     if (s > ksteps / 4) s = ksteps / 4;
