@@ -14,6 +14,8 @@
 //   all threads   o += O_c[:, :32] + O_c[:, 32:]
 // The output is written in packed GEMM-operand format for to_out.  72 KB of shared memory and 128 TMEM columns per
 // CTA: three CTAs per SM overlap each other's load / MMA / softmax phases (the phases of one CTA are serial).
+#include <type_traits>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -200,31 +202,50 @@ attention_tc_kernel(const float* __restrict__ q, int64_t ldq, const float* __res
       tmem_ld_32x32(lane_addr, s0);
       tmem_ld_32x32(lane_addr + 32, s1);
       tmem_ld_wait();
+      // full chunk of a single-pair tile (the common case of the L = 256 / 64 self-attention cores): no key masks
+      const bool full = (G == 1) && (jhi - jlo == AT_KC);
       float cmax = -INFINITY;
+      if (full) {
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;   // four independent max chains
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        if (j >= jlo && j < jhi) cmax = fmaxf(cmax, __uint_as_float(s0[j]));
-        if (32 + j >= jlo && 32 + j < jhi) cmax = fmaxf(cmax, __uint_as_float(s1[j]));
+        for (int j = 0; j < 32; j += 2) {
+          m0 = fmaxf(m0, __uint_as_float(s0[j]));
+          m1 = fmaxf(m1, __uint_as_float(s0[j + 1]));
+          m2 = fmaxf(m2, __uint_as_float(s1[j]));
+          m3 = fmaxf(m3, __uint_as_float(s1[j + 1]));
+        }
+        cmax = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (j >= jlo && j < jhi) cmax = fmaxf(cmax, __uint_as_float(s0[j]));
+          if (32 + j >= jlo && 32 + j < jhi) cmax = fmaxf(cmax, __uint_as_float(s1[j]));
+        }
       }
       const float mnew = fmaxf(mrun, cmax);
       const float corr = __expf(mrun - mnew);            // exp(-inf) = 0 on the first chunk
       mrun = mnew;
       float psum = 0.f;
+      auto probs = [&](auto fullc) {
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {                       // 8 keys per 16-byte chunk
-        float pv[8];
+        for (int c = 0; c < 8; ++c) {                     // 8 keys per 16-byte chunk
+          float pv[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int j = c * 8 + e;
-          const float sv = __uint_as_float(j < 32 ? s0[j] : s1[j - 32]);
-          pv[e] = (j >= jlo && j < jhi) ? __expf(sv - mnew) : 0.f;
-          psum += pv[e];
+          for (int e = 0; e < 8; ++e) {
+            const int j = c * 8 + e;
+            const float sv = __uint_as_float(j < 32 ? s0[j] : s1[j - 32]);
+            if constexpr (decltype(fullc)::value) pv[e] = __expf(sv - mnew);
+            else pv[e] = (j >= jlo && j < jhi) ? __expf(sv - mnew) : 0.f;
+          }
+          psum += ((pv[0] + pv[1]) + (pv[2] + pv[3])) + ((pv[4] + pv[5]) + (pv[6] + pv[7]));
+          uint4 hi, lo;
+          split8(make_float4(pv[0], pv[1], pv[2], pv[3]), make_float4(pv[4], pv[5], pv[6], pv[7]), hi, lo);
+          *sw_chunk(sm.p[0], r, c) = hi;
+          *sw_chunk(sm.p[1], r, c) = lo;
         }
-        uint4 hi, lo;
-        split8(make_float4(pv[0], pv[1], pv[2], pv[3]), make_float4(pv[4], pv[5], pv[6], pv[7]), hi, lo);
-        *sw_chunk(sm.p[0], r, c) = hi;
-        *sw_chunk(sm.p[1], r, c) = lo;
-      }
+      };
+      if (full) probs(std::true_type{});
+      else probs(std::false_type{});
       lrun = lrun * corr + psum;
 #pragma unroll
       for (int i = 0; i < AT_D; ++i) o[i] *= corr;
