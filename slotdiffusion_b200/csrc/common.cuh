@@ -41,19 +41,21 @@ __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
   lo = __float2half_rn(x - __half2float(hi));
 }
 
+// packed form: two elements per conversion instruction (F2FP.PACK_AB / HADD2.F32); same roundings as split_f16
+__device__ __forceinline__ void split_f16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  a = fminf(fmaxf(a, -65504.f), 65504.f);
+  b = fminf(fmaxf(b, -65504.f), 65504.f);
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
 __device__ __forceinline__ void store_split4(__half* hi, __half* lo, long long idx, float4 v) {
-  __half h0, h1, h2, h3, l0, l1, l2, l3;
-  split_f16(v.x, h0, l0);
-  split_f16(v.y, h1, l1);
-  split_f16(v.z, h2, l2);
-  split_f16(v.w, h3, l3);
-  __half2 a = __halves2half2(h0, h1), b = __halves2half2(h2, h3);
-  __half2 c = __halves2half2(l0, l1), d = __halves2half2(l2, l3);
   uint2 ph, pl;
-  ph.x = *reinterpret_cast<uint32_t*>(&a);
-  ph.y = *reinterpret_cast<uint32_t*>(&b);
-  pl.x = *reinterpret_cast<uint32_t*>(&c);
-  pl.y = *reinterpret_cast<uint32_t*>(&d);
+  split_f16x2(v.x, v.y, ph.x, pl.x);
+  split_f16x2(v.z, v.w, ph.y, pl.y);
   *reinterpret_cast<uint2*>(hi + idx) = ph;
   *reinterpret_cast<uint2*>(lo + idx) = pl;
 }
@@ -95,8 +97,10 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
-__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + __expf(-x)); }
+// x * sigmoid(x) with the fast reciprocal (MUFU.RCP, <= 2 ulp): these run once per activation element in the
+// memory-bound operand producers, where the IEEE division was a third of the instruction stream (profiles/README 9)
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.f + __expf(-x)); }
+__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 
 // counter-based dropout mask: keep-scale (1/(1-p)) or 0 for element `idx` of the tensor identified by `seed`

@@ -306,6 +306,33 @@ __global__ void pack_nhwc_kernel(const float* __restrict__ x1, int C1, const flo
   const int Wo = (mode == SDB_PACK_UP2) ? 2 * W : W;
   const int64_t total = B * Ho * Wo * c4n;     // iterate over OUTPUT elements
   const int64_t plane = B * (int64_t)Ho * Wo * C;
+  if (total < (1ll << 31)) {
+    // 32-bit index arithmetic (64-bit div/mod was most of this kernel's instruction stream)
+    const unsigned tot = (unsigned)total, stride = gridDim.x * blockDim.x;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += stride) {
+      const unsigned pq = i / (unsigned)c4n;
+      const int c = int(i - pq * (unsigned)c4n) * 4;
+      const unsigned pr = pq / (unsigned)Wo;
+      const int xo = int(pq - pr * (unsigned)Wo);
+      const unsigned bb = pr / (unsigned)Ho;
+      const int yo = int(pr - bb * (unsigned)Ho);
+      int yi = yo, xi = xo;
+      if (mode == SDB_PACK_UP2) { yi = yo >> 1; xi = xo >> 1; }
+      const int64_t src = ((int64_t)bb * H + yi) * W + xi;
+      float4 v = (c < C1) ? *reinterpret_cast<const float4*>(x1 + src * C1 + c)
+                          : *reinterpret_cast<const float4*>(x2 + src * C2 + (c - C1));
+      int64_t dst;
+      if (mode == SDB_PACK_PHASE2) {
+        const int ph = (yo & 1) * 2 + (xo & 1);
+        dst = ((((int64_t)bb * 4 + ph) * (H / 2) + (yo >> 1)) * (W / 2) + (xo >> 1)) * C + c;
+      } else {
+        dst = (((int64_t)bb * Ho + yo) * Wo + xo) * C + c;
+      }
+      store_split4(out, out + plane, dst, v);
+      if (ycat) *reinterpret_cast<float4*>(ycat + src * C + c) = v;
+    }
+    return;
+  }
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = int(i % c4n) * 4;
     int64_t p = i / c4n;
