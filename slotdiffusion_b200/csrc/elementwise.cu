@@ -424,19 +424,22 @@ __global__ void conv3_in_kernel(const float* __restrict__ x, const float* __rest
   const int o4n = Cout / 4;
   const int64_t total = B * H * W * o4n;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int o = int(i % o4n) * 4;
-    int64_t p = i / o4n;
-    const int xo = int(p % W);
-    p /= W;
-    const int yo = int(p % H);
-    const int64_t b = p / H;
+    // pixel / channel decomposition in 32-bit arithmetic (B*H*W < 2^31 is checked by the launcher)
+    const unsigned pq = (unsigned)(i / o4n);
+    const int o = int(i - (int64_t)pq * o4n) * 4;
+    const unsigned pr = pq / (unsigned)W;
+    const int xo = int(pq - pr * (unsigned)W);
+    const unsigned bb = pr / (unsigned)H;
+    const int yo = int(pr - bb * (unsigned)H);
+    const int64_t b = bb;
     float4 acc = *reinterpret_cast<const float4*>(bias + o);
     for (int c = 0; c < Cin; ++c) {
+      const float* xc = x + (b * Cin + c) * (int64_t)H * W;
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap) {
         const int yi = yo + tap / 3 - 1, xi = xo + tap % 3 - 1;
         if (yi < 0 || yi >= H || xi < 0 || xi >= W) continue;
-        const float v = x[((b * Cin + c) * H + yi) * W + xi];
+        const float v = xc[yi * W + xi];
         const float4 ww = *reinterpret_cast<const float4*>(sw + (c * 9 + tap) * Cout + o);
         acc.x += v * ww.x; acc.y += v * ww.y; acc.z += v * ww.z; acc.w += v * ww.w;
       }
@@ -785,6 +788,7 @@ extern "C" int sdb_gru_gates(const float* gi, const float* gh, const float* h, f
 extern "C" int sdb_conv3_in(const float* x, const float* w, const float* bias, float* y, int64_t B, int64_t Cin,
                             int64_t H, int64_t W, int64_t Cout, void* stream) {
   SDB_REQUIRE(x && w && bias && y && B > 0, "sdb_conv3_in: null argument");
+  SDB_REQUIRE(B * H * W < (1ll << 31), "sdb_conv3_in: B*H*W must be below 2^31");
   SDB_REQUIRE(Cout % 4 == 0 && Cin * 9 * Cout * 4 <= 96 * 1024, "sdb_conv3_in: Cin=%lld Cout=%lld unsupported",
               (long long)Cin, (long long)Cout);
   const size_t smem = (size_t)Cin * 9 * Cout * 4;
