@@ -123,6 +123,10 @@ int sdb_groupnorm_apply_pack_fused(const float* x1, int64_t C1, const float* gsu
 int sdb_groupnorm_apply_pack_dropout(const float* x1, int64_t C1, const float* x2, int64_t C2, const float* stats,
                                      const float* gamma, const float* beta, void* out, int64_t B, int64_t HW, int G,
                                      int silu, float drop_p, uint64_t seed, const uint64_t* seed_dev, void* stream);
+/* per-(sample, 4-channel block) [sum, sum of squares] of an NHWC activation x [B*HW, C], ACCUMULATED into gsum
+ * [B, C/4, 2] (zero it first) -- the same partial sums sdb_gemm's `gsum` epilogue emits, for activations that no GEMM
+ * produced (output of sdb_conv3_in, unet.py:408), so their GroupNorm consumers can use the fused statistics path */
+int sdb_channel_block_sums(const float* x, int64_t C, float* gsum, int64_t B, int64_t HW, void* stream);
 /* partial sums -> stats [B,G,2] (mean, rstd) */
 int sdb_groupnorm_finalize(const float* gsum1, int64_t C1, const float* gsum2, int64_t C2, float* stats, int64_t B,
                            int64_t HW, int G, float eps, void* stream);

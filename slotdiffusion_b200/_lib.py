@@ -42,6 +42,7 @@ SIGNATURES = {
     'sdb_groupnorm_apply_pack_fused': (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
                                                c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_int,
                                                c_void_p]),
+    'sdb_channel_block_sums': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p]),
     'sdb_groupnorm_finalize': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int,
                                        c_float, c_void_p]),
     'sdb_pack_weight_geglu': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),

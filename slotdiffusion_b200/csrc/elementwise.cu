@@ -258,6 +258,39 @@ groupnorm_apply_pack_fused_kernel(const float* __restrict__ x1, int C1, const fl
   }
 }
 
+// GroupNorm partial sums of an activation that no GEMM epilogue produced (the 3 -> C input convolution): per (sample,
+// 4-channel block) sum and sum of squares in the `gsum` format, so every consumer takes the fused statistics path
+// instead of a full two-pass statistics kernel each.  Grid (chunks, B); thread owns 4 channels and strides over rows.
+__global__ void __launch_bounds__(256)
+channel_block_sums_kernel(const float* __restrict__ x, int C, float* __restrict__ gsum, int HW, int rows_per_chunk) {
+  __shared__ float red[256][2];
+  const int c4n = C >> 2;
+  const int64_t b = blockIdx.y;
+  const int tx = threadIdx.x % c4n, ty = threadIdx.x / c4n, rpb = blockDim.x / c4n;
+  float s = 0.f, ss = 0.f;
+  if (ty < rpb) {
+    const int r_begin = blockIdx.x * rows_per_chunk, r_end = min(HW, r_begin + rows_per_chunk);
+#pragma unroll 4
+    for (int r = r_begin + ty; r < r_end; r += rpb) {
+      const float4 v = *reinterpret_cast<const float4*>(x + (b * HW + r) * C + tx * 4);
+      s += (v.x + v.y) + (v.z + v.w);
+      ss += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+    }
+  }
+  red[threadIdx.x][0] = s;
+  red[threadIdx.x][1] = ss;
+  __syncthreads();
+  if (threadIdx.x < c4n) {
+    for (int y = 1; y < rpb; ++y) {
+      s += red[y * c4n + threadIdx.x][0];
+      ss += red[y * c4n + threadIdx.x][1];
+    }
+    float* p = gsum + (b * c4n + threadIdx.x) * 2;
+    atomicAdd(p, s);
+    atomicAdd(p + 1, ss);
+  }
+}
+
 // partial sums -> [B,G,2] (mean, rstd) for consumers that want final statistics (output head)
 __global__ void groupnorm_finalize_kernel(const float* __restrict__ gsum1, int C1, const float* __restrict__ gsum2,
                                           int C2, float* __restrict__ stats, int64_t B, int HW, int G, float eps) {
@@ -919,6 +952,23 @@ extern "C" int sdb_groupnorm_apply_pack_dropout(const float* x1, int64_t C1, con
   g_drop_p = 0.f;
   g_drop_seed_dev = nullptr;
   return rc;
+}
+
+extern "C" int sdb_channel_block_sums(const float* x, int64_t C, float* gsum, int64_t B, int64_t HW, void* stream) {
+  SDB_REQUIRE(x && gsum && B > 0 && HW > 0, "sdb_channel_block_sums: null argument");
+  SDB_REQUIRE(C % 4 == 0 && C >= 4 && C <= 1024 && B <= 65535 && (reinterpret_cast<uintptr_t>(x) & 15) == 0,
+              "sdb_channel_block_sums: C=%lld unsupported", (long long)C);
+  const int c4n = (int)(C / 4);
+  const int rpb = 256 / c4n > 0 ? 256 / c4n : 1;
+  int64_t chunks = cdiv((int64_t)num_sms() * 4, B);
+  if (chunks > cdiv(HW, rpb)) chunks = cdiv(HW, rpb);
+  if (chunks < 1) chunks = 1;
+  const int rows_per_chunk = (int)cdiv(HW, chunks);
+  chunks = cdiv(HW, rows_per_chunk);
+  dim3 grid((unsigned)chunks, (unsigned)B);
+  channel_block_sums_kernel<<<grid, c4n * rpb, 0, as_stream(stream)>>>(x, (int)C, gsum, (int)HW, rows_per_chunk);
+  SDB_LAUNCH_CHECK();
+  return 0;
 }
 
 extern "C" int sdb_groupnorm_finalize(const float* gsum1, int64_t C1, const float* gsum2, int64_t C2, float* stats,

@@ -172,6 +172,7 @@ class DPMSolverSampler:
         conv_in = net.input_blocks[0][0]
         from .unet_exec import Act
         h = Act(ops.conv3_in(x, conv_in.weight, conv_in.bias), H, W, net.model_channels)
+        ex.input_conv_sums(h, B)
         hs = [h]
         bcast = _RowBroadcast(emb_all)
         for block in list(net.input_blocks)[1:]:

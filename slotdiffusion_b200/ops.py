@@ -300,6 +300,13 @@ def groupnorm_pack_fused(x1, x2, gamma, beta, B, HW, G=32, eps=1e-5, silu=True, 
     return out
 
 
+def channel_block_sums(x, gsum, B, HW):
+    """Accumulate GroupNorm partial sums [B, C/4, 2] of the NHWC rows x [B*HW, C] into the (zeroed) buffer gsum."""
+    C = x.shape[-1]
+    check(lib().sdb_channel_block_sums(_p(x), C, _p(gsum), B, HW, _stream()), 'sdb_channel_block_sums')
+    return gsum
+
+
 def groupnorm_finalize(gsum1, gsum2, C1, C2, B, HW, G, eps):
     stats = torch.empty(B, G, 2, dtype=torch.float32, device=gsum1.device)
     check(lib().sdb_groupnorm_finalize(_p(gsum1), C1, _p(gsum2), C2, _p(stats), B, HW, G, eps, _stream()),

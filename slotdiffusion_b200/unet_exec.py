@@ -71,6 +71,13 @@ class UNetExecutor:
         self._gs_off += n
         return v
 
+    def input_conv_sums(self, h, B):
+        """The input convolution is not a GEMM, so nothing accumulated GroupNorm sums for its output; it feeds three
+        GroupNorms (first ResBlock + two skip concats): one pass over it replaces three exact-statistics kernels."""
+        gs = self._gs(B, h.H * h.W, h.C)
+        if gs is not None:
+            h.gs = ops.channel_block_sums(h.t, gs, B, h.H * h.W)
+
     def group_norm(self, x1, x2, gn, B, HW, silu):
         """GroupNorm(+SiLU) -> packed operand; statistics from the producers' epilogue sums when available."""
         x2t = x2.t if x2 is not None else None
@@ -215,6 +222,7 @@ class UNetExecutor:
             ctx_kv = self.context_kv(context)
         conv_in = net.input_blocks[0][0]
         h = Act(ops.conv3_in(x.float(), conv_in.weight, conv_in.bias), H, W, net.model_channels)   # unet.py:408
+        self.input_conv_sums(h, B)
         hs = [h]
         for block in list(net.input_blocks)[1:]:                                                   # unet.py:566-568
             h = self.run_block(block, h, None, emb_all, ctx_kv, B, S)
