@@ -227,7 +227,7 @@ def run_ours(args):
                          'gemm_share_of_unet_time': roof['ms'] / (ms / args.steps / NFE), 'launches': roof['launches'],
                          'how': 'all %d GEMM launches of one UNet evaluation replayed from a CUDA graph, CUDA events' % roof['launches']},
             'roofline_slot_attention': sa_stat['attend_kernel'],
-            'cpu_baseline': cpu_baseline(sample_nfe=NFE, batch=4),
+            'cpu_baseline': cpu_baseline(sample_nfe=NFE, batch=4) if world == 1 else None,   # rank 0, N=1 only
             'train': train,
         }
         print(json.dumps(line))
