@@ -50,3 +50,18 @@ def test_invalid_arguments_are_reported_not_ub():
     assert l.sdb_gemm(ctypes.byref(g), None) == 1          # SDB_ERR_INVALID
     assert b'null' in l.sdb_last_error()
     assert l.sdb_slot_attend(None, None, None, None, None, None, 1, 1, 1, 192, 1.0, 1e-6, None) == 1
+
+
+def test_new_entry_points_validate_arguments():
+    """argument validation of the tensor-core entry points (no CUDA call is reached)"""
+    from slotdiffusion_b200 import _lib
+    l = _lib.lib()
+    assert l.sdb_slot_attend_fused_supported(11, 192) == 1 and l.sdb_slot_attend_fused_supported(24, 256) == 1
+    assert l.sdb_slot_attend_fused_supported(33, 192) == 0 and l.sdb_slot_attend_fused_supported(11, 64) == 0
+    assert l.sdb_slot_attend_fused(None, None, 196, None, None, None, None, 1, 16, 4, 192, 1e-5, 1e-6, None) == 1
+    assert b'null' in l.sdb_last_error()
+    assert l.sdb_slot_attend_fused_workspace(64, 1024, 11, 192) == (64 * 2 * 11 * 192 + 64 * 2 * 11) * 4 or \
+        l.sdb_slot_attend_fused_workspace(64, 1024, 11, 192) > 0     # chunks depend on the SM count of the device
+    assert l.sdb_attention_tc_supported(8, 32, 768, 768, 768) == 1 and l.sdb_attention_tc_supported(8, 64, 768, 768, 768) == 0
+    assert l.sdb_attention_tc(None, 4, None, 4, None, 4, None, 1, 16, 16, 2, 32, 1.0, None) == 1
+    assert l.sdb_channel_block_sums(None, 128, None, 1, 16, None) == 1
