@@ -174,11 +174,64 @@ def gen_dpm():
     print('dpm ok', len(calls))
 
 
+def gen_layout():
+    """state_dict layout (ordered key -> shape) of the hot-path sub-modules inside the full reference models
+    (build_model of the shipped configs): the checkpoint contract of the drop-in modules."""
+    import json
+    import runpy
+    out = {}
+    for task, rel, get in (('img_based', 'sa_ldm/sa_ldm_clevrtex_params-res128.py', ref_import.img_models),
+                           ('video_based', 'savi_ldm/savi_ldm_movid_params-res128.py', ref_import.video_models),
+                           ('video_based', 'savi_ldm/savi_ldm_movie_params-res128.py', ref_import.video_models)):
+        cfg = os.path.join(ref_import.REF_ROOT, 'slotdiffusion', task, 'configs', rel)
+        if not os.path.exists(cfg):
+            continue
+        params = runpy.run_path(cfg)['SlotAttentionParams']()      # fresh class: build_model pops from its dicts
+        model = get().build_model(params)
+        name = os.path.basename(rel)[:-3]
+        out[name] = {
+            'slot_attention': [[k, list(v.shape)] for k, v in model.slot_attention.state_dict().items()],
+            'unet': [[k, list(v.shape)] for k, v in model.dm_decoder.model.diffusion_model.state_dict().items()],
+            'slot_attention_ctor': dict(in_features=model.slot_attention.in_features,
+                                        num_iterations=model.slot_attention.num_iterations,
+                                        num_slots=model.slot_attention.num_slots,
+                                        slot_size=model.slot_attention.slot_size,
+                                        mlp_hidden_size=model.slot_attention.mlp_hidden_size),
+            'unet_dict': {k: (list(v) if isinstance(v, tuple) else v) for k, v in params.unet_dict.items()},
+            'n_model_state': len(model.state_dict()),
+        }
+        print(name, 'layout ok', len(out[name]['unet']), len(out[name]['slot_attention']))
+    # COCO (DINO encoder: ViT weights are not constructible offline) -- the two hot-path modules built directly
+    # from the config dicts, the way sa_diffusion.py:132-139 and ddpm.py:342 do
+    from slotdiffusion.img_based.models.sa_diffusion import SlotAttentionWMask
+    from slotdiffusion.video_based.models.unet.unet import UNetModel
+    rel = 'sa_ldm/sa_ldm_dino_coco_params-res224.py'
+    params = runpy.run_path(os.path.join(ref_import.REF_ROOT, 'slotdiffusion', 'img_based', 'configs', rel))[
+        'SlotAttentionParams']()
+    sd_, ed_ = params.slot_dict, params.enc_dict
+    ctor = dict(in_features=ed_['enc_out_channels'], num_iterations=sd_['num_iterations'], num_slots=sd_['num_slots'],
+                slot_size=sd_['slot_size'], mlp_hidden_size=sd_['slot_mlp_size'])
+    sa = SlotAttentionWMask(eps=1e-6, **ctor)
+    un = UNetModel(**params.unet_dict)
+    out[os.path.basename(rel)[:-3]] = {
+        'slot_attention': [[k, list(v.shape)] for k, v in sa.state_dict().items()],
+        'unet': [[k, list(v.shape)] for k, v in un.state_dict().items()],
+        'slot_attention_ctor': ctor,
+        'unet_dict': {k: (list(v) if isinstance(v, tuple) else v) for k, v in params.unet_dict.items()},
+        'n_model_state': None,
+    }
+    print('coco layout ok')
+    with open(os.path.join(OUT, 'state_dict_layout.json'), 'w') as f:
+        json.dump(out, f, indent=0, sort_keys=True)
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['sa', 'unet', 'dpm']
+    which = sys.argv[1:] or ['sa', 'unet', 'dpm', 'layout']
     if 'sa' in which:
         gen_sa()
     if 'unet' in which:
         gen_unet()
     if 'dpm' in which:
         gen_dpm()
+    if 'layout' in which:
+        gen_layout()
