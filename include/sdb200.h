@@ -201,6 +201,51 @@ int64_t sdb_slot_attend_fused_workspace(int64_t B, int64_t N, int64_t S, int64_t
 int sdb_slot_attend_fused(const float* x, const float* qa, int64_t ldq, float* seg_mask, void* upd_packed,
                           float* upd32, float* work, int64_t B, int64_t N, int64_t S, int64_t Din, float ln_eps,
                           float eps, void* stream);
+/* The attend kernel alone: leaves its per-chunk partial sums in `work` for sdb_slot_update (no finalize launch).
+ * work = part_upd [B, chunks, S, Din] (= ascale * sum_n a[n,s] n[n,:]) | part_cs [B, chunks, S] (= sum_n a[n,s]) with
+ * chunks = sdb_slot_attend_fused_chunks(B, N), ascale = sdb_slot_attend_fused_ascale(). */
+int64_t sdb_slot_attend_fused_chunks(int64_t B, int64_t N);
+float sdb_slot_attend_fused_ascale(void);
+int sdb_slot_attend_fused_partials(const float* x, const float* qa, int64_t ldq, float* seg_mask, float* work,
+                                   int64_t B, int64_t N, int64_t S, int64_t Din, float ln_eps, float eps, void* stream);
+
+/* ------------------------------------------------------------------ slot update: everything of one Slot-Attention
+ * iteration that is not the token contraction, in ONE launch (slot_attention.py:82 and :97-102):
+ *   U      = sum_chunks part_upd / (ascale * sum_chunks part_cs)          (finalize of the attend kernel)
+ *   h'     = GRUCell(updates, slots_in)   with gi = U W_iv^T + b_iv  (W_iv = W_ih Wv diag(gamma), b_iv = W_ih Wv beta + b_ih)
+ *   slots  = h' + W_2 relu(W_1 LN_m(h') + b_1) + b_2                       -> slots_out [rows, D]
+ *   qa     = LN_q(slots) W_qa^T  (next iteration's folded slot-side operand, sdb_slot_attend_fused) -> qa_out [rows, ldq]
+ * do_update = 0: only the last line, applied to slots_in (the projection of the initial slots).
+ * All weights fp32 and TRANSPOSED (input-major, [K][N] contiguous in N): w_ivT [Din][3D], w_hhT [D][3D], w1T [D][M],
+ * w2T [M][D], w_qaT [D][ldq] (column Din = logit bias row, columns > Din ignored).  rows = B * S.
+ * Plain fp32 FMA arithmetic (no operand splitting); intended for rows <~ 1k where the tail is launch-latency bound. */
+typedef struct SdbSlotUpdate {
+  const float* part_upd;
+  const float* part_cs;
+  const float* slots_in;
+  const float* w_ivT;
+  const float* b_iv;
+  const float* w_hhT;
+  const float* b_hh;
+  const float* ln_m_g;
+  const float* ln_m_b;
+  const float* w1T;
+  const float* b1;
+  const float* w2T;
+  const float* b2;
+  const float* ln_q_g;
+  const float* ln_q_b;
+  const float* w_qaT;
+  float* slots_out;
+  float* qa_out;          /* NULL: no projection (last iteration) */
+  int64_t rows;
+  int32_t S, Din, D, M, ldq, chunks;
+  float ascale, ln_m_eps, ln_q_eps;
+  int32_t do_update;
+} SdbSlotUpdate;
+int sdb_slot_update_supported(int64_t S, int64_t Din, int64_t D, int64_t M);
+int sdb_slot_update(const SdbSlotUpdate* args, void* stream);
+
 /* GRUCell pointwise part (PyTorch gate order r,z,n; slot_attention.py:97-100): gi = x W_ih^T + b_ih and
  * gh = h W_hh^T + b_hh come from sdb_gemm; h_new = (1-z) n + z h.  All [R, 3D] / [R, D]. */
 int sdb_gru_gates(const float* gi, const float* gh, const float* h, float* h_new, int64_t R, int64_t D,

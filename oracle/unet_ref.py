@@ -27,7 +27,7 @@ DEFAULT_CFG = dict(  # img_based/configs/sa_ldm/sa_ldm_clevrtex_params-res128.py
 def timestep_embedding(t, dim, max_period=10000.0):
     # utils.py:79-86: freqs in fp32, [cos, sin] order; t may be fractional
     half = dim // 2
-    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32) / half)
+    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32, device=t.device) / half)
     args = t[:, None].float() * freqs[None]
     return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
 

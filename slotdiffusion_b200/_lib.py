@@ -24,6 +24,14 @@ class SdbGemm(Structure):
     ]
 
 
+class SdbSlotUpdate(Structure):
+    _fields_ = [(n, c_void_p) for n in (
+        'part_upd', 'part_cs', 'slots_in', 'w_ivT', 'b_iv', 'w_hhT', 'b_hh', 'ln_m_g', 'ln_m_b', 'w1T', 'b1', 'w2T', 'b2',
+        'ln_q_g', 'ln_q_b', 'w_qaT', 'slots_out', 'qa_out')] + [
+        ('rows', c_int64), ('S', c_int32), ('Din', c_int32), ('D', c_int32), ('M', c_int32), ('ldq', c_int32),
+        ('chunks', c_int32), ('ascale', c_float), ('ln_m_eps', c_float), ('ln_q_eps', c_float), ('do_update', c_int32)]
+
+
 # name -> (restype, argtypes); must list every symbol declared in include/sdb200.h
 SIGNATURES = {
     'sdb_version': (c_int, []),
@@ -69,6 +77,12 @@ SIGNATURES = {
     'sdb_slot_attend_fused_workspace': (c_int64, [c_int64, c_int64, c_int64, c_int64]),
     'sdb_slot_attend_fused': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                       c_int64, c_int64, c_int64, c_float, c_float, c_void_p]),
+    'sdb_slot_attend_fused_chunks': (c_int64, [c_int64, c_int64]),
+    'sdb_slot_attend_fused_ascale': (c_float, []),
+    'sdb_slot_attend_fused_partials': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64,
+                                               c_int64, c_int64, c_float, c_float, c_void_p]),
+    'sdb_slot_update_supported': (c_int, [c_int64, c_int64, c_int64, c_int64]),
+    'sdb_slot_update': (c_int, [POINTER(SdbSlotUpdate), c_void_p]),
     'sdb_groupnorm_apply_pack_dropout': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
                                                  c_void_p, c_int64, c_int64, c_int, c_int, c_float, c_uint64, c_void_p, c_void_p]),
     'sdb_grad_pack': (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64,

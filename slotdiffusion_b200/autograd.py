@@ -8,12 +8,19 @@ hand-written kernels:
   per iteration: LayerNorm+pack -> Wq GEMM -> fused attend (TMA-staged, one pass over k|v)
                  -> W_ih / W_hh GEMMs -> GRU gates -> LayerNorm+pack -> MLP GEMMs (+ReLU, +residual)
 """
+import os
+
 import torch
 
 from . import ops
 
 
 FUSED_ATTEND = True   # inference: tensor-core attend over the raw features (no k / v tensors)
+# One-launch slot update (csrc/slot_update.cuh) instead of the ten-launch GEMM tail, for B*S <= FUSED_TAIL_MAX_ROWS.
+# Opt-in (SDB_SA_FUSED_TAIL=1) until it has been timed on the B200: written when the round's GPU budget was spent;
+# its arithmetic is checked on the CPU through the host emulation (tests/test_slot_update_emulation_cpu.py).
+FUSED_TAIL = os.environ.get('SDB_SA_FUSED_TAIL', '0') == '1'
+FUSED_TAIL_MAX_ROWS = 1024
 
 
 def _needs_grad(*ts):
@@ -29,6 +36,8 @@ def slot_attention_forward(mod, inputs, slots, want_mask, save=None):
     inputs = inputs.contiguous().float()
     slots = slots.contiguous().float().reshape(B * S, D)
     if save is None and FUSED_ATTEND and ops.slot_attend_fused_supported(S, Din):
+        if FUSED_TAIL and B * S <= FUSED_TAIL_MAX_ROWS and ops.slot_update_supported(S, Din, D, mod.mlp_hidden_size):
+            return slot_attention_forward_fused_tail(mod, inputs, slots, want_mask, B, N, Din, S, D)
         return _slot_attention_forward_fused(mod, inputs, slots, want_mask, B, N, Din, S, D)
 
     # k | v projection of LayerNorm(inputs)                                  (slot_attention.py:68-72)
@@ -97,6 +106,26 @@ def _slot_attention_forward_fused(mod, inputs, slots, want_mask, B, N, Din, S, D
         hn = ops.layernorm_pack(h, mod.mlp[0].weight, mod.mlp[0].bias, mod.mlp[0].eps)
         _, y1p = ops.gemm(hn, w_1, bias=mod.mlp[1].bias, relu=True, pack_out='none', keep_c=False)
         slots, hp = ops.gemm(y1p, w_2, bias=mod.mlp[3].bias, residual=h, pack_out='none')
+    return slots.view(B, S, D), mask
+
+
+def slot_attention_forward_fused_tail(mod, inputs, slots, want_mask, B, N, Din, S, D, attend=None, update=None):
+    """Inference path with the one-launch slot update: 1 + 2 * iterations launches per forward
+    (projection of the initial slots; then attend, update+projection per iteration).
+    attend / update default to the CUDA entry points; the CPU emulation test passes host stand-ins with the same
+    signatures, so this sequencing is what both run."""
+    attend = attend or ops.slot_attend_fused_partials
+    update = update or ops.slot_update
+    w = mod._wcache.slot_update_weights(mod)
+    M = mod.mlp_hidden_size
+    mask = None
+    _, qa = update(w, None, slots, S, Din, D, M, True)                       # :82 of iteration 0 (+ k-side fold of :84)
+    for it in range(mod.num_iterations):
+        last = it == mod.num_iterations - 1
+        parts, m = attend(inputs, qa, B, N, S, Din, mod.norm_inputs.eps, mod.eps, want_mask and last)   # :68-72, :84-91
+        if want_mask and last:
+            mask = m
+        slots, qa = update(w, parts, slots, S, Din, D, M, not last)          # :91 (v side), :97-102, next :82
     return slots.view(B, S, D), mask
 
 

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libsdb200.so')
 STAMP = os.path.join(HERE, '.libsdb200.stamp')
-SOURCES = ['api.cu', 'gemm.cu', 'elementwise.cu', 'attention.cu', 'attention_tc.cu', 'slot_attention.cu', 'slot_attention_fused.cu', 'backward.cu']
+SOURCES = ['api.cu', 'gemm.cu', 'elementwise.cu', 'attention.cu', 'attention_tc.cu', 'slot_attention.cu', 'slot_attention_fused.cu', 'slot_update.cu', 'backward.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '--use_fast_math=false']
 

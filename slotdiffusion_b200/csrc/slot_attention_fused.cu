@@ -580,10 +580,11 @@ extern "C" int64_t sdb_slot_attend_fused_workspace(int64_t B, int64_t N, int64_t
   return (B * chunks * S * Din + B * chunks * S) * (int64_t)sizeof(float);
 }
 
-extern "C" int sdb_slot_attend_fused(const float* x, const float* qa, int64_t ldq, float* seg_mask, void* upd_packed,
-                                     float* upd32, float* work, int64_t B, int64_t N, int64_t S, int64_t Din,
-                                     float ln_eps, float eps, void* stream) {
-  SDB_REQUIRE(x && qa && upd_packed && work, "sdb_slot_attend_fused: null argument");
+// finalize = 0: leave the per-chunk partial sums in `work` (sdb_slot_update consumes them)
+static int sf_run(const float* x, const float* qa, int64_t ldq, float* seg_mask, void* upd_packed, float* upd32,
+                  float* work, int64_t B, int64_t N, int64_t S, int64_t Din, float ln_eps, float eps, void* stream,
+                  int finalize) {
+  SDB_REQUIRE(x && qa && work && (upd_packed || !finalize), "sdb_slot_attend_fused: null argument");
   SDB_REQUIRE(B > 0 && B <= 65535 && N > 0 && N < (1 << 24), "sdb_slot_attend_fused: bad B=%lld N=%lld", (long long)B,
               (long long)N);
   SDB_REQUIRE(sdb_slot_attend_fused_supported(S, Din), "sdb_slot_attend_fused: unsupported num_slots=%lld in_features=%lld",
@@ -606,9 +607,26 @@ extern "C" int sdb_slot_attend_fused(const float* x, const float* qa, int64_t ld
   }
   SF_CASE(128) else SF_CASE(192) else SF_CASE(256)
 #undef SF_CASE
-  if (rc) return rc;
+  if (rc || !finalize) return rc;
   slot_attend_fused_finalize_kernel<<<(unsigned)(B * S), 64, 0, st>>>(part_upd, part_cs, (__half*)upd_packed, upd32,
                                                                       B * S, (int)S, (int)Din, chunks, SF_ASCALE);
   SDB_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int sdb_slot_attend_fused(const float* x, const float* qa, int64_t ldq, float* seg_mask, void* upd_packed,
+                                     float* upd32, float* work, int64_t B, int64_t N, int64_t S, int64_t Din,
+                                     float ln_eps, float eps, void* stream) {
+  return sf_run(x, qa, ldq, seg_mask, upd_packed, upd32, work, B, N, S, Din, ln_eps, eps, stream, 1);
+}
+
+/* token chunks per sample the attend kernel uses for (B, N) on this device, and the scale of its partial sums:
+ * work = part_upd [B, chunks, S, Din] (= ascale * sum_n a[n,s] n[n,:]) followed by part_cs [B, chunks, S] (= sum_n a) */
+extern "C" int64_t sdb_slot_attend_fused_chunks(int64_t B, int64_t N) { return sf_chunks(B, N); }
+extern "C" float sdb_slot_attend_fused_ascale(void) { return SF_ASCALE; }
+
+extern "C" int sdb_slot_attend_fused_partials(const float* x, const float* qa, int64_t ldq, float* seg_mask, float* work,
+                                              int64_t B, int64_t N, int64_t S, int64_t Din, float ln_eps, float eps,
+                                              void* stream) {
+  return sf_run(x, qa, ldq, seg_mask, nullptr, nullptr, work, B, N, S, Din, ln_eps, eps, stream, 0);
 }

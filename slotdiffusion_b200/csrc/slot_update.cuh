@@ -1,0 +1,229 @@
+// Slot update ("tail" of a Slot-Attention iteration) as ONE kernel: partial-sum finalize -> GRU input/hidden
+// projections -> GRU gates -> LayerNorm -> MLP (+ residual) -> LayerNorm_q -> folded slot-side projection of the NEXT
+// iteration (slot_attention.py:82, :97-102 of the reference; weight fold in ops.slot_attention_fold_math).
+//
+// Written as a sequence of PHASES separated by CTA barriers; phase(ph, t, ...) is what thread t does in phase ph and
+// touches shared scratch only through the Lay offsets below.  The same function is compiled
+//   * by nvcc into slot_update_kernel (slot_update.cu): for (ph) { phase(ph, threadIdx.x, ...); __syncthreads(); }
+//   * by g++ into the host emulation used by tests/test_slot_update_emulation_cpu.py: for (ph) for (t) phase(ph, t, ...)
+// so the index arithmetic and the fp32 operation order (explicit fmaf, fixed summation orders) of the kernel are
+// checked against the oracle on the CPU; no warp-level primitives are used on purpose.
+//
+// Arithmetic is plain fp32 FMA on the CUDA cores: with rows = B*S <= ~1k the ~0.8 MFLOP/row of the tail are launch-
+// and latency-bound as ten separate tensor-core launches (profiles/README.md section 4: ~9 us floor per small GEMM);
+// one CTA per RT rows streams the 1.6 MB of transposed weights from L2 once and reuses each element RT times.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/sdb200.h"
+
+#ifdef __CUDACC__
+#define SU_HD __host__ __device__ __forceinline__
+#else
+#define SU_HD inline
+#endif
+
+namespace sdb {
+namespace su {
+
+constexpr int NUM_PHASES = 17;
+
+struct Lay {   // float offsets into the CTA's scratch; every array starts 16-byte aligned
+  int u, h, gi, gh, hn, ln, y1, so, stat, red, total;
+};
+
+SU_HD Lay layout(int RT, int Din, int D, int M, int nt) {
+  Lay l;
+  int o = 0;
+  l.u = o;    o += RT * Din;     // normalised weighted feature means U (GRU input before the folded projection)
+  l.h = o;    o += RT * D;       // previous slots
+  l.gi = o;   o += RT * 3 * D;   // GRU input projection  (r | z | n)
+  l.gh = o;   o += RT * 3 * D;   // GRU hidden projection (r | z | n)
+  l.hn = o;   o += RT * D;       // GRU output
+  l.ln = o;   o += RT * D;       // LayerNorm output (MLP input, later the q-projection input)
+  l.y1 = o;   o += RT * M;       // MLP hidden
+  l.so = o;   o += RT * D;       // new slots
+  l.stat = o; o += 2 * RT;       // (mean, rstd) per row
+  l.red = o;  o += (nt + 3) / 4 * 4;   // per-thread partials of the row reductions
+  l.total = o;
+  return l;
+}
+
+struct F4 { float x, y, z, w; };
+SU_HD F4 ld4(const float* p) {
+#ifdef __CUDA_ARCH__
+  const float4 v = *reinterpret_cast<const float4*>(p);
+  return F4{v.x, v.y, v.z, v.w};
+#else
+  return F4{p[0], p[1], p[2], p[3]};
+#endif
+}
+
+// out[r][j] = act(bias[j] + sum_k x[r][k] * wT[k][j] (+ resid[r][j])), j = t, t + nt, ...; rows r < nr are stored.
+// x: scratch [RT][K] (K % 4 == 0); wT: global, row stride ldw, consecutive j contiguous (coalesced across threads).
+template <int RT>
+SU_HD void matvec(int t, int nt, int nr, const float* x, int K, const float* wT, int ldw, int N, const float* bias,
+                  float* out, int64_t ldo, const float* resid, int ldres, bool relu) {
+  for (int j = t; j < N; j += nt) {
+    float acc[RT];
+    const float b = bias ? bias[j] : 0.f;
+#pragma unroll
+    for (int r = 0; r < RT; ++r) acc[r] = b;
+    const float* w = wT + j;
+    for (int k = 0; k < K; k += 4) {
+      const float w0 = w[(int64_t)(k + 0) * ldw], w1 = w[(int64_t)(k + 1) * ldw];
+      const float w2 = w[(int64_t)(k + 2) * ldw], w3 = w[(int64_t)(k + 3) * ldw];
+#pragma unroll
+      for (int r = 0; r < RT; ++r) {
+        const F4 xv = ld4(x + r * K + k);
+        acc[r] = fmaf(xv.x, w0, acc[r]);
+        acc[r] = fmaf(xv.y, w1, acc[r]);
+        acc[r] = fmaf(xv.z, w2, acc[r]);
+        acc[r] = fmaf(xv.w, w3, acc[r]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+      if (r < nr) {
+        float v = acc[r];
+        if (resid) v += resid[r * ldres + j];
+        if (relu) v = fmaxf(v, 0.f);
+        out[(int64_t)r * ldo + j] = v;
+      }
+    }
+  }
+}
+
+// Row reductions for LayerNorm over src[RT][D], two-pass (mean, then centred squares), nt % RT == 0:
+// thread t owns row t % RT and the columns d = t / RT, t / RT + nt / RT, ...; partials are combined in slice order.
+template <int RT>
+SU_HD void ln_partial(int t, int nt, const float* src, int D, const float* stat, float* red, bool centred) {
+  const int r = t % RT, s0 = t / RT, ns = nt / RT;
+  const float mean = centred ? stat[2 * r] : 0.f;
+  float a = 0.f;
+  for (int d = s0; d < D; d += ns) {
+    const float v = src[r * D + d] - mean;
+    a += centred ? v * v : v;
+  }
+  red[t] = a;
+}
+template <int RT>
+SU_HD void ln_combine(int t, int nt, int D, float* stat, const float* red, bool centred, float eps) {
+  if (t >= RT) return;
+  const int ns = nt / RT;
+  float a = 0.f;
+  for (int s = 0; s < ns; ++s) a += red[s * RT + t];
+  if (!centred) stat[2 * t] = a / (float)D;
+  else stat[2 * t + 1] = 1.f / sqrtf(a / (float)D + eps);
+}
+template <int RT>
+SU_HD void ln_apply(int t, int nt, const float* src, int D, const float* stat, const float* g, const float* b,
+                    float* dst) {
+  for (int i = t; i < RT * D; i += nt) {
+    const int r = i / D, d = i % D;
+    dst[i] = (src[i] - stat[2 * r]) * stat[2 * r + 1] * g[d] + b[d];
+  }
+}
+
+// What thread t of the CTA that owns rows [tile * RT, tile * RT + RT) does in phase ph.  sm: the CTA's scratch.
+template <int RT>
+SU_HD void phase(int ph, int t, int nt, int64_t tile, const SdbSlotUpdate& p, float* sm) {
+  const int Din = p.Din, D = p.D, M = p.M, S = p.S;
+  const Lay l = layout(RT, Din, D, M, nt);
+  const int64_t r0 = tile * RT;
+  const int nr = (int)((p.rows - r0) < RT ? (p.rows - r0) : RT);
+  float *u = sm + l.u, *h = sm + l.h, *gi = sm + l.gi, *gh = sm + l.gh, *hn = sm + l.hn, *ln = sm + l.ln;
+  float *y1 = sm + l.y1, *so = sm + l.so, *stat = sm + l.stat, *red = sm + l.red;
+  const bool upd = p.do_update != 0, wq = p.qa_out != nullptr;
+  switch (ph) {
+    case 0: {   // previous slots; U = sum_chunks part_upd / (ascale * sum_chunks part_cs)   (finalize of the attend kernel)
+      for (int i = t; i < RT * D; i += nt) {
+        const int r = i / D;
+        const float v = r < nr ? p.slots_in[(r0 + r) * D + (i % D)] : 0.f;
+        h[i] = v;
+        if (!upd) so[i] = v;       // q-only call: project the given slots
+      }
+      if (upd) {
+        for (int i = t; i < RT * Din; i += nt) {
+          const int r = i / Din, c = i % Din;
+          float v = 0.f;
+          if (r < nr) {
+            const int64_t row = r0 + r, b = row / S, s = row % S;
+            float cs = 0.f;
+            for (int ch = 0; ch < p.chunks; ++ch) cs += p.part_cs[(b * p.chunks + ch) * S + s];
+            const float inv = 1.f / (cs * p.ascale);
+            for (int ch = 0; ch < p.chunks; ++ch) v += p.part_upd[((b * p.chunks + ch) * S + s) * Din + c];
+            v *= inv;
+          }
+          u[i] = v;
+        }
+      }
+    } break;
+    case 1:     // gi = U W_iv^T + b_iv (v projection and norm_inputs affine folded in), gh = h W_hh^T + b_hh
+      if (upd) {
+        matvec<RT>(t, nt, RT, u, Din, p.w_ivT, 3 * D, 3 * D, p.b_iv, gi, 3 * D, nullptr, 0, false);
+        matvec<RT>(t, nt, RT, h, D, p.w_hhT, 3 * D, 3 * D, p.b_hh, gh, 3 * D, nullptr, 0, false);
+      }
+      break;
+    case 2:     // GRUCell gates, PyTorch order (r, z, n)
+      if (upd) {
+        for (int i = t; i < RT * D; i += nt) {
+          const int r = i / D, d = i % D;
+          const float* a = gi + r * 3 * D;
+          const float* b = gh + r * 3 * D;
+          const float rg = 1.f / (1.f + expf(-(a[d] + b[d])));
+          const float zg = 1.f / (1.f + expf(-(a[D + d] + b[D + d])));
+          const float ng = tanhf(a[2 * D + d] + rg * b[2 * D + d]);
+          hn[i] = (1.f - zg) * ng + zg * h[i];
+        }
+      }
+      break;
+    case 3: if (upd) ln_partial<RT>(t, nt, hn, D, stat, red, false); break;
+    case 4: if (upd) ln_combine<RT>(t, nt, D, stat, red, false, p.ln_m_eps); break;
+    case 5: if (upd) ln_partial<RT>(t, nt, hn, D, stat, red, true); break;
+    case 6: if (upd) ln_combine<RT>(t, nt, D, stat, red, true, p.ln_m_eps); break;
+    case 7: if (upd) ln_apply<RT>(t, nt, hn, D, stat, p.ln_m_g, p.ln_m_b, ln); break;
+    case 8:     // MLP hidden: relu(LN(h') W_1^T + b_1)
+      if (upd) matvec<RT>(t, nt, RT, ln, D, p.w1T, M, M, p.b1, y1, M, nullptr, 0, true);
+      break;
+    case 9:     // slots = h' + y1 W_2^T + b_2  -> scratch (for the q projection) and global
+      if (upd) {
+        matvec<RT>(t, nt, RT, y1, M, p.w2T, D, D, p.b2, so, D, hn, D, false);
+      }
+      break;
+    case 10:
+      if (upd) {
+        for (int i = t; i < nr * D; i += nt) p.slots_out[r0 * D + i] = so[i];
+      }
+      if (wq) ln_partial<RT>(t, nt, so, D, stat, red, false);
+      break;
+    case 11: if (wq) ln_combine<RT>(t, nt, D, stat, red, false, p.ln_q_eps); break;
+    case 12: if (wq) ln_partial<RT>(t, nt, so, D, stat, red, true); break;
+    case 13: if (wq) ln_combine<RT>(t, nt, D, stat, red, true, p.ln_q_eps); break;
+    case 14: if (wq) ln_apply<RT>(t, nt, so, D, stat, p.ln_q_g, p.ln_q_b, ln); break;
+    case 15:    // qa[:, :Din] = LN_q(slots) W_qa^T; the logit-bias column Din is a split-K reduction over all threads
+      if (wq) {
+        matvec<RT>(t, nt, nr, ln, D, p.w_qaT, p.ldq, Din, nullptr, p.qa_out + r0 * p.ldq, p.ldq, nullptr, 0, false);
+        const int r = t % RT, s0 = t / RT, ns = nt / RT;
+        float a = 0.f;
+        for (int k = s0; k < D; k += ns) a = fmaf(ln[r * D + k], p.w_qaT[(int64_t)k * p.ldq + Din], a);
+        red[t] = a;
+      }
+      break;
+    case 16:
+      if (wq && t < nr) {
+        const int ns = nt / RT;
+        float a = 0.f;
+        for (int s = 0; s < ns; ++s) a += red[s * RT + t];
+        float* q = p.qa_out + (r0 + t) * p.ldq;
+        q[Din] = a;
+        for (int c = Din + 1; c < p.ldq; ++c) q[c] = 0.f;
+      }
+      break;
+    default: break;
+  }
+}
+
+}  // namespace su
+}  // namespace sdb

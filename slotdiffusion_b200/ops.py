@@ -10,7 +10,7 @@ import torch
 
 from . import _lib
 from ._lib import (SDB_A_CONV3, SDB_A_CONV3S2, SDB_A_PLAIN, SDB_PACK_PHASE2, SDB_PACK_PLAIN, SDB_PACK_UP2,
-                   SdbGemm, check, lib)
+                   SdbGemm, SdbSlotUpdate, check, lib)
 
 _PASSES = 3   # 3: hi*hi + lo*hi + hi*lo (fp32-faithful, default); 1: single fp16 pass
 
@@ -122,6 +122,27 @@ class WeightCache:
             return dict(w_qa=pack_weight(wqa.float().contiguous()), w_iv=pack_weight(wiv.float().contiguous()),
                         b_iv=biv.float().contiguous())
         return self._get('sa_fold', ps, make)
+
+    def slot_update_weights(self, mod):
+        """fp32 TRANSPOSED ([K][N]) weights of the one-launch slot update (csrc/slot_update.cuh): the same fold as
+        slot_attention_fold (fp64 algebra, once per parameter version), then input-major copies so that consecutive
+        threads of the kernel read consecutive output columns."""
+        ps = (mod.project_q[1].weight, mod.project_k.weight, mod.project_v.weight, mod.norm_inputs.weight,
+              mod.norm_inputs.bias, mod.gru.weight_ih, mod.gru.bias_ih)
+        rest = (mod.gru.weight_hh, mod.gru.bias_hh, mod.mlp[0].weight, mod.mlp[0].bias, mod.mlp[1].weight,
+                mod.mlp[1].bias, mod.mlp[3].weight, mod.mlp[3].bias, mod.project_q[0].weight, mod.project_q[0].bias)
+
+        def make():
+            wqa, wiv, biv = slot_attention_fold_math(*[p.detach() for p in ps], mod.attn_scale)
+            whh, bhh, gm, bm, w1, b1, w2, b2, gq, bq = [p.detach().float() for p in rest]
+
+            def T(w):
+                return w.float().t().contiguous()
+            return dict(w_ivT=T(wiv), b_iv=biv.float().contiguous(), w_hhT=T(whh), b_hh=bhh.contiguous(),
+                        ln_m_g=gm.contiguous(), ln_m_b=bm.contiguous(), w1T=T(w1), b1=b1.contiguous(), w2T=T(w2),
+                        b2=b2.contiguous(), ln_q_g=gq.contiguous(), ln_q_b=bq.contiguous(), w_qaT=T(wqa),
+                        ldq=int(wqa.shape[0]), ln_m_eps=float(mod.mlp[0].eps), ln_q_eps=float(mod.project_q[0].eps))
+        return self._get('sa_update', ps + rest, make)
 
     def cat(self, key, *vs):
         """Concatenation of fp32 vectors (fused biases)."""
@@ -376,6 +397,55 @@ def slot_attend_fused(x, qa, B, N, S, Din, ln_eps, eps, want_mask, want_fp32=Fal
     check(lib().sdb_slot_attend_fused(_p(x), _p(qa), qa.stride(0), _p(mask), _p(upd.t), _p(upd32), _p(work), B, N, S,
                                       Din, ln_eps, eps, _stream()), 'sdb_slot_attend_fused')
     return upd, mask, upd32
+
+
+def slot_attend_fused_partials(x, qa, B, N, S, Din, ln_eps, eps, want_mask):
+    """The attend kernel without its finalize launch.  Returns ((part_upd, part_cs, chunks, ascale), mask): the
+    per-chunk partial sums that sdb_slot_update consumes."""
+    _f32(x), _f32(qa)
+    assert x.is_contiguous() and qa.stride(1) == 1
+    ws = lib().sdb_slot_attend_fused_workspace(B, N, S, Din)
+    chunks = int(lib().sdb_slot_attend_fused_chunks(B, N))
+    work = torch.empty(ws // 4, dtype=torch.float32, device=x.device)
+    mask = torch.empty(B, S, N, dtype=torch.float32, device=x.device) if want_mask else None
+    check(lib().sdb_slot_attend_fused_partials(_p(x), _p(qa), qa.stride(0), _p(mask), _p(work), B, N, S, Din, ln_eps,
+                                               eps, _stream()), 'sdb_slot_attend_fused_partials')
+    n_upd = B * chunks * S * Din
+    return (work[:n_upd], work[n_upd:n_upd + B * chunks * S], chunks, float(lib().sdb_slot_attend_fused_ascale())), mask
+
+
+def slot_update_supported(S, Din, D, M):
+    return bool(lib().sdb_slot_update_supported(S, Din, D, M))
+
+
+def slot_update_args(w, parts, slots_in, slots_out, qa_out, S, Din, D, M):
+    """SdbSlotUpdate for one call (device-agnostic: only data_ptr()s; the CPU emulation test fills the same struct).
+    parts = (part_upd, part_cs, chunks, ascale) or None for the projection of the initial slots."""
+    def ptr(t):
+        return t.data_ptr() if t is not None else None
+    a = SdbSlotUpdate()
+    if parts is not None:
+        a.part_upd, a.part_cs, a.chunks, a.ascale = ptr(parts[0]), ptr(parts[1]), int(parts[2]), float(parts[3])
+    for k in ('w_ivT', 'b_iv', 'w_hhT', 'b_hh', 'ln_m_g', 'ln_m_b', 'w1T', 'b1', 'w2T', 'b2', 'ln_q_g', 'ln_q_b',
+              'w_qaT'):
+        setattr(a, k, ptr(w[k]))
+    a.slots_in, a.slots_out, a.qa_out = ptr(slots_in), ptr(slots_out), ptr(qa_out)
+    a.rows, a.S, a.Din, a.D, a.M, a.ldq = slots_in.shape[0], S, Din, D, M, w['ldq']
+    a.ln_m_eps, a.ln_q_eps = w['ln_m_eps'], w['ln_q_eps']
+    a.do_update = 1 if parts is not None else 0
+    return a
+
+
+def slot_update(w, parts, slots_in, S, Din, D, M, want_q):
+    """One launch: (optional) GRU + MLP update of slots_in [B*S, D] from the attend partials, and (optional) the
+    folded slot-side projection qa [B*S, ldq] of the result.  Returns (slots_out or slots_in, qa or None)."""
+    _f32(slots_in)
+    rows = slots_in.shape[0]
+    slots_out = torch.empty_like(slots_in) if parts is not None else None
+    qa = torch.empty(rows, w['ldq'], dtype=torch.float32, device=slots_in.device) if want_q else None
+    a = slot_update_args(w, parts, slots_in, slots_out, qa, S, Din, D, M)
+    check(lib().sdb_slot_update(ctypes.byref(a), _stream()), 'sdb_slot_update')
+    return (slots_out if parts is not None else slots_in), qa
 
 
 def gru_gates(gi, gh, h):

@@ -10,6 +10,9 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')
+    config.addinivalue_line('markers', 'gpu_next: GPU test of a code path written after the round\'s GPU budget was '
+                            'spent -- not yet run on hardware, opt-in product path; run with -m gpu_next, promote to '
+                            'gpu once green (tools/gpu_round2_first.sh)')
 
 
 def pytest_collection_modifyitems(config, items):
@@ -18,5 +21,5 @@ def pytest_collection_modifyitems(config, items):
         return
     skip = pytest.mark.skip(reason='no CUDA device')
     for it in items:
-        if 'gpu' in it.keywords:
+        if 'gpu' in it.keywords or 'gpu_next' in it.keywords:
             it.add_marker(skip)

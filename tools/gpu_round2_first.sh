@@ -1,0 +1,10 @@
+#!/bin/bash
+# First GPU call of the next round: run what was written blind at the end of round 1 (marker gpu_next), then time it.
+#   gpurun --timeout 900 -- 'bash tools/gpu_round2_first.sh'
+mkdir -p gpurun_out
+echo "=== gpu_next tests (one-launch slot update)"
+timeout 300 python -m pytest tests -q -m gpu_next 2>&1 | tail -20 | tee gpurun_out/gpu_next_tests.log
+echo "=== Slot Attention module timing: GEMM tail vs one-launch tail"
+timeout 300 python tools/sa_bench.py --batch 4 16 64 256 2>&1 | tail -8 | tee gpurun_out/sa_bench_tail.log
+echo "=== eager PyTorch bar on the same GPU (oracle arithmetic on CUDA; TF32 off / on)"
+timeout 600 python tools/eager_gpu_bar.py 2>&1 | tail -6 | tee gpurun_out/eager_gpu_bar.log

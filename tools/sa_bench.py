@@ -68,6 +68,13 @@ def main():
                 autograd.FUSED_ATTEND = fused
                 res[fused] = graph_time(lambda: mod(x, s0), flush=flush)
             autograd.FUSED_ATTEND = True
+            # one-launch slot update instead of the GEMM tail (opt-in path; forced here whatever the row count)
+            t_tail = None
+            if ops.slot_update_supported(S, D, D, 2 * D):
+                saved = autograd.FUSED_TAIL, autograd.FUSED_TAIL_MAX_ROWS
+                autograd.FUSED_TAIL, autograd.FUSED_TAIL_MAX_ROWS = True, 1 << 30
+                t_tail = graph_time(lambda: mod(x, s0), flush=flush)
+                autograd.FUSED_TAIL, autograd.FUSED_TAIL_MAX_ROWS = saved
             # attend kernel alone (one iteration): cold (L2 flushed) and warm
             qa = torch.randn(B * S, D + 4, device=dev) * D ** -0.5
             t_cold = graph_time(lambda: ops.slot_attend_fused(x, qa, B, N, S, D, 1e-5, 1e-6, True), flush=flush)
@@ -80,6 +87,7 @@ def main():
         print(json.dumps({
             'B': B, 'N': N, 'S': S, 'D': D, 'iters': args.iters,
             'module_us_fused': round(res[True], 1), 'module_us_kv_path': round(res[False], 1),
+            'module_us_fused_one_launch_tail': None if t_tail is None else round(t_tail, 1),
             'module_hbm_frac_fused': round(mod_bytes / res[True] / 1e3 / hbm, 4),
             'attend_us_cold': round(t_cold, 1), 'attend_us_warm': round(t_warm, 1), 'attend_us_old_kernel_cold': round(t_old, 1),
             'attend_GBps_cold': round(it_bytes / t_cold / 1e3, 1), 'attend_hbm_frac_cold': round(it_bytes / t_cold / 1e3 / hbm, 4),
