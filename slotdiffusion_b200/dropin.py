@@ -89,8 +89,6 @@ def _make_adapters(ref_dpm):
         configuration (DPM-Solver++ singlestep order 3, time_uniform, noise model, guidance scale 1, no x0/xt
         correctors other than vq_denoised); anything else goes through the inherited reference loop."""
 
-        _samplers = {}       # (id(unet), steps, order, vq, device) -> DPMSolverSampler
-
         def __init__(self, model_fn, noise_schedule, algorithm_type='dpmsolver++', correcting_x0_fn=None, **kw):
             super().__init__(model_fn, noise_schedule, algorithm_type=algorithm_type,
                              correcting_x0_fn=correcting_x0_fn, **kw)
@@ -145,15 +143,22 @@ def _make_adapters(ref_dpm):
                 vae = mf.model.vae
                 emb = vae.vqvae.quantize.embedding.weight.detach()
                 codebook = (emb / float(getattr(vae, 'scale_factor', 1.))).float().contiguous()
-            key = (id(unet), steps, order, bool(self.vq_denoised), str(x.device))
-            smp = self._samplers.get(key)
+            # samplers (and their CUDA graphs) live on the UNet they drive, so they die with it
+            cache = unet.__dict__.setdefault('_sdb_samplers', {})
+            key = (steps, order, bool(self.vq_denoised), str(x.device))
+            smp = cache.get(key)
             if smp is None:
-                smp = self._samplers[key] = _ds.DPMSolverSampler(unet, mf.noise_schedule.sdb_betas, codebook=codebook,
-                                                             steps=steps, order=order)
-            elif codebook is not None:
-                smp.codebook = codebook.to(x.device)
-            if smp.codebook is not None and smp.codebook.device != x.device:
-                smp.codebook = smp.codebook.to(x.device)
+                smp = cache[key] = _ds.DPMSolverSampler(unet, mf.noise_schedule.sdb_betas, codebook=codebook,
+                                                        steps=steps, order=order)
+            if codebook is not None:
+                # the VQ-VAE may have been reloaded since the last call; captured graphs hold the buffer's address,
+                # so refresh it in place (or drop the graphs if it has to be replaced)
+                cur = smp.codebook
+                if cur is not None and cur.shape == codebook.shape and cur.device == x.device:
+                    cur.copy_(codebook)
+                else:
+                    smp.codebook = codebook.to(x.device)
+                    getattr(smp, '_graphs', {}).clear()
             return smp.sample(x, mf.condition)
 
     return NoiseScheduleVP, model_wrapper, DPM_Solver
