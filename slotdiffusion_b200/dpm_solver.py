@@ -134,10 +134,21 @@ class DPMSolverSampler:
         self.use_cuda_graph = use_cuda_graph
         self._graphs = {}
         self._t_all = {}
+        self._sig = None
 
     @property
     def nfe(self):
         return len(self.t_model)
+
+    def _param_signature(self):
+        """Changes whenever a UNet parameter is updated in place (optimizer step, load_state_dict: `_version`) or
+        re-allocated (`.to()`, `.data = ...`: `data_ptr`).  A captured graph holds the addresses of the PACKED weights
+        of the parameter version it was captured with (ops.WeightCache re-packs into new buffers afterwards)."""
+        v, a = 0, 0
+        for p in self.unet.parameters():
+            v += p._version
+            a ^= p.data_ptr()
+        return v, a
 
     def _run(self, x, context):
         """Enqueue the whole sampling loop on the current stream; returns the final latents."""
@@ -190,6 +201,10 @@ class DPMSolverSampler:
         context = context.contiguous().float()
         if not self.use_cuda_graph:
             return self._run(x_T, context)
+        sig = self._param_signature()
+        if sig != self._sig:            # train-then-sample (method.py logs samples every epoch): stale graphs go
+            self._graphs.clear()
+            self._sig = sig
         key = (tuple(x_T.shape), tuple(context.shape), x_T.device.index, ops.get_passes())
         g = self._graphs.get(key)
         if g is None:

@@ -158,3 +158,22 @@ def test_generate_imgs_use_dpm_routes_to_the_b200_sampler(dropin, monkeypatch):
     with pytest.warns(UserWarning, match='outside the B200 plan'):
         with pytest.raises(RuntimeError, match='CUDA'):
             solver.sample(torch.randn(2, 3, 32, 32), steps=10, order=2, method='multistep')
+
+
+def test_sampler_graph_cache_is_invalidated_by_parameter_updates():
+    """train-then-sample: a captured graph reads the packed weights of the parameter version it was captured with"""
+    from slotdiffusion_b200.dpm_solver import DPMSolverSampler
+    from slotdiffusion_b200.unet import UNetModel
+    from oracle import dpm_ref
+    net = UNetModel(3, 32, 3, 1, (2,), channel_mult=(1, 2), num_head_channels=32, context_dim=32)
+    smp = DPMSolverSampler(net, dpm_ref.ddpm_buffers(dpm_ref.linear_betas())['betas'])
+    s0 = smp._param_signature()
+    assert smp._param_signature() == s0
+    opt = torch.optim.SGD(net.parameters(), lr=0.1)
+    for p in net.parameters():
+        p.grad = torch.ones_like(p)
+    opt.step()
+    s1 = smp._param_signature()
+    assert s1 != s0
+    net.load_state_dict(net.state_dict())
+    assert smp._param_signature() != s1
