@@ -44,6 +44,15 @@ class SlotAttention(nn.Module):
         )
         self._wcache = ops.WeightCache()
 
+    def __getstate__(self):          # deepcopy / pickle: the packed-weight cache is derived state
+        d = self.__dict__.copy()
+        d.pop('_wcache', None)
+        return d
+
+    def __setstate__(self, d):
+        super().__setstate__(d)
+        self._wcache = ops.WeightCache()
+
     def _run(self, inputs, slots, want_mask):
         if not inputs.is_cuda:
             raise RuntimeError('slotdiffusion_b200.SlotAttention runs on CUDA (sm_100a) only; no CPU fallback')

@@ -217,6 +217,19 @@ class UNetModel(nn.Module):
         from .unet_exec import UNetExecutor
         self._exec = UNetExecutor(self)
 
+    # copy.deepcopy / pickle (EMA copies, torch.save(model)): the kernel schedule, its packed-weight cache and any
+    # captured sampler graphs are derived state -- dropped here and rebuilt for the copy
+    def __getstate__(self):
+        d = self.__dict__.copy()
+        d.pop('_exec', None)
+        d.pop('_sdb_samplers', None)
+        return d
+
+    def __setstate__(self, d):
+        super().__setstate__(d)
+        from .unet_exec import UNetExecutor
+        self._exec = UNetExecutor(self)
+
     def forward(self, x, timesteps=None, context=None, **kwargs):
         """x [N,C,h,w], timesteps [N] (int or fractional float), context [N,S,Dc] -> [N,C,h,w]."""
         if not x.is_cuda:

@@ -177,3 +177,24 @@ def test_sampler_graph_cache_is_invalidated_by_parameter_updates():
     assert s1 != s0
     net.load_state_dict(net.state_dict())
     assert smp._param_signature() != s1
+
+
+def test_modules_survive_deepcopy_and_pickle():
+    """EMA copies / torch.save(model): derived state (kernel schedule, packed-weight cache) is rebuilt for the copy"""
+    import copy
+    import io
+    from slotdiffusion_b200.slot_attention import SlotAttentionWMask
+    from slotdiffusion_b200.unet import UNetModel
+    net = UNetModel(3, 32, 3, 1, (2,), channel_mult=(1, 2), num_head_channels=32, context_dim=32)
+    buf = io.BytesIO()
+    torch.save(net, buf)
+    buf.seek(0)
+    for c in (copy.deepcopy(net), torch.load(buf, weights_only=False)):
+        assert c._exec.net is c and c._exec is not net._exec
+        ids = {id(m) for m in c.modules()}
+        assert all(k in ids for k in c._exec.emb_off) and all(k in ids for k in c._exec.kv_off)
+        assert [(k, v.shape) for k, v in c.state_dict().items()] == [(k, v.shape) for k, v in net.state_dict().items()]
+        assert all(torch.equal(a, b) for a, b in zip(c.state_dict().values(), net.state_dict().values()))
+    sa = SlotAttentionWMask(192, 3, 11, 192, 384)
+    c = copy.deepcopy(sa)
+    assert c._wcache is not sa._wcache and torch.equal(c.project_k.weight, sa.project_k.weight)
