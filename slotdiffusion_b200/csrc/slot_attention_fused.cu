@@ -117,10 +117,14 @@ __device__ __forceinline__ void tmem_ld_folded(uint32_t taddr, float (&out)[SP])
   }
 }
 
-// latency-critical single-thread wait (MMA issuers): non-blocking test_wait in a tight loop, bounded
+// latency-critical single-thread wait (MMA issuers): non-blocking test_wait in a tight loop, bounded.
+// The clock is read once per 4096 polls: with a clock64() compare on every poll the wait loops of this kernel were
+// 38 % of all executed warp instructions (ncu source counters, profiles/README.md section 12) and compete for issue
+// slots with the converter warps of the same scheduler.
 __device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity) {
   const uint32_t a = smem_u32(bar);
   long long t0 = 0;
+  uint32_t polls = 0;
   for (;;) {
     uint32_t ok;
     asm volatile(
@@ -131,11 +135,13 @@ __device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity) {
         : "r"(a), "r"(parity)
         : "memory");
     if (ok) return;
-    const long long now = clock64();
-    if (t0 == 0) t0 = now;
-    else if (now - t0 > 4000000000LL) {
-      printf("sdb200: mbarrier spin timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
-      __trap();
+    if ((++polls & 0xfffu) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000LL) {
+        printf("sdb200: mbarrier spin timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+        __trap();
+      }
     }
   }
 }
@@ -144,12 +150,15 @@ __device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int lane) {
   if (lane == 0) {
     long long t0 = 0;
-    while (!mbar_try_wait(bar, parity)) {     // try_wait itself blocks for a hardware-defined interval
-      const long long now = clock64();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 4000000000LL) {
-        printf("sdb200: mbarrier wait timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
-        __trap();
+    uint32_t polls = 0;
+    while (!mbar_try_wait(bar, parity)) {     // try_wait itself blocks for a hardware-defined interval (~200 cycles)
+      if ((++polls & 0xffu) == 0) {           // bounded wait: look at the clock every 256 polls
+        const long long now = clock64();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 4000000000LL) {
+          printf("sdb200: mbarrier wait timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+          __trap();
+        }
       }
     }
   }
