@@ -361,15 +361,24 @@ slot_attend_fused_kernel(const float* __restrict__ x, const float* __restrict__ 
         if (c < nchunks) mbar_wait_warp(&ctl.sfull[set * SF_CPT + cc], (i / NSETS) & 1, lane);   // CTA-uniform branch
         else mbar_wait_warp(&ctl.xempty[set], ((i / NSETS) & 1) ^ 1, lane);   // zero-filled chunk: the set must still be free
         if (lane == 0 && gi == 0) SF_T(3, i, 0);
+        // every token of the group inside the sample (warp-uniform; false only in the last group of a ragged N):
+        // skips the 48 selects per lane that zero the rows beyond the end (8 % of the converter's instruction stream,
+        // which is issue-bound: ncu `stall_not_selected` is its top stall reason, profiles/README.md section 12)
+        const bool group_full = (i * SF_TILE + gi * 8 + 8) <= ntok;
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           const int tg = tok_in_group(q);
-          const bool valid = (i * SF_TILE + gi * 8 + tg) < ntok;
           const float* row = reinterpret_cast<const float*>(grp) + tg * DIN + 4 * j;
 #pragma unroll
-          for (int k = 0; k < NV; ++k) {
-            v[q][k] = *reinterpret_cast<const float4*>(row + 32 * k);   // stale bytes if !valid: zeroed below, no branch
-            if (!valid) v[q][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int k = 0; k < NV; ++k) v[q][k] = *reinterpret_cast<const float4*>(row + 32 * k);
+        }
+        if (!group_full) {
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const bool valid = (i * SF_TILE + gi * 8 + tok_in_group(q)) < ntok;   // stale bytes beyond the end -> zeros
+#pragma unroll
+            for (int k = 0; k < NV; ++k)
+              if (!valid) v[q][k] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
         __syncwarp();                                       // all fp32 rows of the group are in registers
