@@ -65,3 +65,22 @@ def test_new_entry_points_validate_arguments():
     assert l.sdb_attention_tc_supported(8, 32, 768, 768, 768) == 1 and l.sdb_attention_tc_supported(8, 64, 768, 768, 768) == 0
     assert l.sdb_attention_tc(None, 4, None, 4, None, 4, None, 1, 16, 16, 2, 32, 1.0, None) == 1
     assert l.sdb_channel_block_sums(None, 128, None, 1, 16, None) == 1
+
+
+def test_every_entry_point_rejects_null_and_zero_arguments():
+    """SURVEY 8b 'shape/alignment violations are reported, never UB': each compute entry point called with NULL
+    pointers and zero sizes returns SDB_ERR_INVALID with a message (no CUDA call is reached, runs without a GPU)."""
+    from slotdiffusion_b200 import _lib
+    l = _lib.lib()
+    queries = {'sdb_version', 'sdb_last_error', 'sdb_launch_count', 'sdb_attention_tc_supported',
+               'sdb_slot_attend_workspace', 'sdb_slot_attend_fused_supported', 'sdb_slot_attend_fused_debug',
+               'sdb_slot_attend_fused_workspace', 'sdb_slot_attend_fused_chunks', 'sdb_slot_attend_fused_ascale',
+               'sdb_slot_update_supported'}
+    for name, (res, args) in _lib.SIGNATURES.items():
+        if name in queries:
+            continue
+        vals = [1.0 if a is ctypes.c_float else (0 if a in (ctypes.c_int, ctypes.c_int32, ctypes.c_int64, ctypes.c_uint64) else None)
+                for a in args]
+        rc = getattr(l, name)(*vals)
+        assert rc == 1, (name, rc)
+        assert len(l.sdb_last_error()) > 0, name
