@@ -8,3 +8,8 @@ echo "=== Slot Attention module timing: GEMM tail vs one-launch tail"
 timeout 300 python tools/sa_bench.py --batch 4 16 64 256 2>&1 | tail -8 | tee gpurun_out/sa_bench_tail.log
 echo "=== eager PyTorch bar on the same GPU (oracle arithmetic on CUDA; TF32 off / on)"
 timeout 600 python tools/eager_gpu_bar.py 2>&1 | tail -6 | tee gpurun_out/eager_gpu_bar.log
+echo "=== probe: fp16 main term + e4m3 correction terms vs three fp16 passes (DESIGN 8.0)"
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I slotdiffusion_b200/csrc tools/probes/umma_f8_probe.cu -o tools/probes/umma_f8_probe.bin \
+  && timeout 120 ./tools/probes/umma_f8_probe.bin 2>&1 | tee gpurun_out/umma_f8_probe.log
+echo "=== fused attend timeline at B=256 (which stage is long under full-chip load?)"
+SA_B=256 timeout 120 python tools/sa_timeline.py 2>&1 | tail -40 | tee gpurun_out/sa_timeline_b256.log
