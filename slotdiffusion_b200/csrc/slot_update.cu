@@ -37,7 +37,7 @@ static int launch_slot_update(const SdbSlotUpdate& p, cudaStream_t st) {
 using namespace sdb;
 
 extern "C" int sdb_slot_update_supported(int64_t S, int64_t Din, int64_t D, int64_t M) {
-  if (S < 1 || Din < 4 || Din % 4 || M < 4 || M % 4) return 0;
+  if (S < 1 || Din < 16 || Din % 16 || M < 16 || M % 16) return 0;   // K loops run in chunks of 8 / 16
   if (!(D == 128 || D == 192 || D == 256)) return 0;      // block size = D, a multiple of the row tile
   const su::Lay l = su::layout(8, (int)Din, (int)D, (int)M, (int)D);
   return (size_t)l.total * sizeof(float) <= 200 * 1024 ? 1 : 0;

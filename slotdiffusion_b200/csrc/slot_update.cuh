@@ -60,39 +60,69 @@ SU_HD F4 ld4(const float* p) {
 #endif
 }
 
-// out[r][j] = act(bias[j] + sum_k x[r][k] * wT[k][j] (+ resid[r][j])), j = t, t + nt, ...; rows r < nr are stored.
-// x: scratch [RT][K] (K % 4 == 0); wT: global, row stride ldw, consecutive j contiguous (coalesced across threads).
-template <int RT>
-SU_HD void matvec(int t, int nt, int nr, const float* x, int K, const float* wT, int ldw, int N, const float* bias,
-                  float* out, int64_t ldo, const float* resid, int ldres, bool relu) {
-  for (int j = t; j < N; j += nt) {
-    float acc[RT];
-    const float b = bias ? bias[j] : 0.f;
+// out[r][j] = act(bias[j] + sum_k x[r][k] * wT[k][j] (+ resid[r][j])) for the columns j this thread owns; rows r < nr are
+// stored.  x: scratch [RT][K]; wT: global, row stride ldw, consecutive j contiguous (coalesced across threads).
+// A thread owns NC columns (j0, j0 + nt, ...) and walks K in chunks of KU: all NC * KU weight loads of a chunk are issued
+// before the first FMA, so a thread keeps 16-24 L2 requests in flight (the kernel lives on L2 latency: 1.6 MB of weights per
+// CTA), and one broadcast LDS.128 of x feeds 4 * NC FMAs.  Accumulation order per output is k ascending whatever NC / KU.
+template <int RT, int NC, int KU>
+SU_HD void matvec_nc(int t, int nt, int nr, const float* x, int K, const float* wT, int ldw, int N, const float* bias,
+                     float* out, int64_t ldo, const float* resid, int ldres, bool relu) {
+  for (int j0 = t; j0 < N; j0 += NC * nt) {
+    float acc[NC][RT];
+    bool ok[NC];
 #pragma unroll
-    for (int r = 0; r < RT; ++r) acc[r] = b;
-    const float* w = wT + j;
-    for (int k = 0; k < K; k += 4) {
-      const float w0 = w[(int64_t)(k + 0) * ldw], w1 = w[(int64_t)(k + 1) * ldw];
-      const float w2 = w[(int64_t)(k + 2) * ldw], w3 = w[(int64_t)(k + 3) * ldw];
+    for (int c = 0; c < NC; ++c) {
+      ok[c] = j0 + c * nt < N;
+      const float b = (bias && ok[c]) ? bias[j0 + c * nt] : 0.f;
 #pragma unroll
-      for (int r = 0; r < RT; ++r) {
-        const F4 xv = ld4(x + r * K + k);
-        acc[r] = fmaf(xv.x, w0, acc[r]);
-        acc[r] = fmaf(xv.y, w1, acc[r]);
-        acc[r] = fmaf(xv.z, w2, acc[r]);
-        acc[r] = fmaf(xv.w, w3, acc[r]);
+      for (int r = 0; r < RT; ++r) acc[c][r] = b;
+    }
+    for (int k = 0; k < K; k += KU) {
+      float w[NC][KU];
+#pragma unroll
+      for (int c = 0; c < NC; ++c)
+#pragma unroll
+        for (int u = 0; u < KU; ++u) w[c][u] = ok[c] ? wT[(int64_t)(k + u) * ldw + j0 + c * nt] : 0.f;
+#pragma unroll
+      for (int u = 0; u < KU; u += 4) {
+#pragma unroll
+        for (int r = 0; r < RT; ++r) {
+          const F4 xv = ld4(x + r * K + k + u);
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            acc[c][r] = fmaf(xv.x, w[c][u + 0], acc[c][r]);
+            acc[c][r] = fmaf(xv.y, w[c][u + 1], acc[c][r]);
+            acc[c][r] = fmaf(xv.z, w[c][u + 2], acc[c][r]);
+            acc[c][r] = fmaf(xv.w, w[c][u + 3], acc[c][r]);
+          }
+        }
       }
     }
 #pragma unroll
-    for (int r = 0; r < RT; ++r) {
-      if (r < nr) {
-        float v = acc[r];
-        if (resid) v += resid[r * ldres + j];
-        if (relu) v = fmaxf(v, 0.f);
-        out[(int64_t)r * ldo + j] = v;
+    for (int c = 0; c < NC; ++c) {
+      if (!ok[c]) continue;
+      const int j = j0 + c * nt;
+#pragma unroll
+      for (int r = 0; r < RT; ++r) {
+        if (r < nr) {
+          float v = acc[c][r];
+          if (resid) v += resid[r * ldres + j];
+          if (relu) v = fmaxf(v, 0.f);
+          out[(int64_t)r * ldo + j] = v;
+        }
       }
     }
   }
+}
+
+// K % 16 == 0 (checked by the entry point)
+template <int RT>
+SU_HD void matvec(int t, int nt, int nr, const float* x, int K, const float* wT, int ldw, int N, const float* bias,
+                  float* out, int64_t ldo, const float* resid, int ldres, bool relu) {
+  if (N > 2 * nt) matvec_nc<RT, 3, 8>(t, nt, nr, x, K, wT, ldw, N, bias, out, ldo, resid, ldres, relu);
+  else if (N > nt) matvec_nc<RT, 2, 8>(t, nt, nr, x, K, wT, ldw, N, bias, out, ldo, resid, ldres, relu);
+  else matvec_nc<RT, 1, 16>(t, nt, nr, x, K, wT, ldw, N, bias, out, ldo, resid, ldres, relu);
 }
 
 // Row reductions for LayerNorm over src[RT][D], two-pass (mean, then centred squares), nt % RT == 0:
