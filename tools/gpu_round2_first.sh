@@ -13,3 +13,5 @@ nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I slotdiffusion_b20
   && timeout 120 ./tools/probes/umma_f8_probe.bin 2>&1 | tee gpurun_out/umma_f8_probe.log
 echo "=== fused attend timeline at B=256 (which stage is long under full-chip load?)"
 SA_B=256 timeout 120 python tools/sa_timeline.py 2>&1 | tail -40 | tee gpurun_out/sa_timeline_b256.log
+# second call (separate, ~6 GPU-min): source-level ncu reports to read offline with tools/ncu_wait_share.py / ncu_stalls.py
+#   gpurun --timeout 900 -- 'bash tools/gpu_profile.sh r2a "gemm_kernel" 6; SA_B=256 bash tools/gpu_sa_profile.sh sa_b256'
