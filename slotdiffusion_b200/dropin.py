@@ -86,7 +86,7 @@ def _make_adapters(ref_dpm):
 
     class DPM_Solver(ref_dpm.DPM_Solver):
         """dpm_solver.py:419-1328.  sample() runs the CUDA-graph B200 sampler when the request is the repo's own
-        configuration (DPM-Solver++ singlestep order 3, time_uniform, noise model, guidance scale 1, no x0/xt
+        configuration (DPM-Solver++ singlestep, orders 1-3, any step count, time_uniform, noise model, guidance scale 1, no x0/xt
         correctors other than vq_denoised); anything else goes through the inherited reference loop."""
 
         def __init__(self, model_fn, noise_schedule, algorithm_type='dpmsolver++', correcting_x0_fn=None, **kw):
@@ -115,7 +115,7 @@ def _make_adapters(ref_dpm):
             if self.algorithm_type != 'dpmsolver++' or self.correcting_x0_fn is not None or \
                     self.correcting_xt_fn is not None:
                 return 'algorithm_type / correcting functions'
-            if method != 'singlestep' or order != 3 or skip_type != 'time_uniform' or denoise_to_zero:
+            if method != 'singlestep' or order not in (1, 2, 3) or skip_type != 'time_uniform' or denoise_to_zero:
                 return f'method={method!r} order={order} skip_type={skip_type!r}'
             if t_start is not None or t_end is not None or return_intermediate:
                 return 't_start / t_end / return_intermediate'

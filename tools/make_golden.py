@@ -174,6 +174,49 @@ def gen_dpm():
     print('dpm ok', len(calls))
 
 
+PLAN_CASES = [(20, 3), (10, 3), (15, 3), (21, 3), (22, 3), (50, 3), (7, 3), (12, 2), (9, 2), (6, 1)]   # (steps, order)
+
+
+def toy_eps(x, t_model, cond):
+    """cheap analytic stand-in for the UNet (tests/test_dpm_plan_cpu.py uses the same function)"""
+    return 0.3 * torch.sin(1.7 * x + cond.mean(dim=(1, 2)).view(-1, 1, 1, 1)) + 1e-4 * t_model.view(-1, 1, 1, 1) * x.roll(1, -1)
+
+
+def gen_dpm_plan():
+    """Reference DPM_Solver.sample (singlestep, dpmsolver++) for several (steps, order) with a toy noise model:
+    pins the host-precomputed plan of slotdiffusion_b200.dpm_solver.build_plan for more than the 20-step case."""
+    from slotdiffusion.video_based.models.ddpm.dpm_solver import NoiseScheduleVP, model_wrapper, DPM_Solver
+    betas = dpm_ref.ddpm_buffers(dpm_ref.linear_betas())['betas']
+    ns = NoiseScheduleVP(betas=betas)
+    cb = seeded((64, 3), 58)
+
+    class Toy(torch.nn.Module):
+        def forward(self, x, t, context=None, quantize=False):
+            return toy_eps(x, t, context)
+    model = Toy()
+
+    class VAE:
+        def quantize(self, h):
+            from slotdiffusion.video_based.models.vqvae.quantize import VectorQuantizer2     # the reference's quantiser
+            vq = VectorQuantizer2(64, 3, beta=0.25)
+            vq.embedding.weight.data.copy_(cb)
+            return vq(h)[0]
+    model.vae = VAE()
+    ctx = seeded((2, 11, 192), 56)
+    xT = seeded((2, 3, 16, 16), 57)
+    out = {}
+    for steps, order in PLAN_CASES:
+        for vq in (False, True):
+            fn = model_wrapper(model=model, noise_schedule=ns, model_type='noise', guidance_type='classifier-free',
+                               condition=ctx)
+            solver = DPM_Solver(fn, ns, algorithm_type='dpmsolver++', correcting_x0_fn=False, vq_denoised=vq)
+            with torch.no_grad():
+                y = solver.sample(xT, steps=steps, order=order, method='singlestep')
+            out[f's{steps}_o{order}_{"vq" if vq else "novq"}'] = y.numpy()
+    np.savez_compressed(os.path.join(OUT, 'dpm_plan.npz'), **out)
+    print('dpm_plan ok', len(out))
+
+
 def gen_layout():
     """state_dict layout (ordered key -> shape) of the hot-path sub-modules inside the full reference models
     (build_model of the shipped configs): the checkpoint contract of the drop-in modules."""
@@ -226,7 +269,7 @@ def gen_layout():
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['sa', 'unet', 'dpm', 'layout']
+    which = sys.argv[1:] or ['sa', 'unet', 'dpm', 'layout', 'dpm_plan']
     if 'sa' in which:
         gen_sa()
     if 'unet' in which:
@@ -235,3 +278,5 @@ if __name__ == '__main__':
         gen_dpm()
     if 'layout' in which:
         gen_layout()
+    if 'dpm_plan' in which:
+        gen_dpm_plan()
