@@ -108,7 +108,85 @@ __global__ void probe(int N, int units, int scheme, long long* out, float* vals)
   if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
+// ---- layout check: e4m3 operand tiles written by threads with the swizzle formulas a GEMM producer / TMA would use ----
+// sw = 128: 128-byte rows (K = 128 e4m3), 8-row atoms of 1024 B;  sw = 64: 64-byte rows (K = 64), 8-row atoms of 512 B.
+// A[r][k] = (r + 2k) % 7 - 3, B[n][k] = (3n + k) % 5 - 2 (exact in e4m3), D = A B^T must match the host sum exactly.
+__device__ __forceinline__ uint8_t e4m3_small(int v) {   // -3..3
+  const uint8_t mag[4] = {0x00, 0x38, 0x40, 0x44};
+  return (uint8_t)(mag[v < 0 ? -v : v] | (v < 0 ? 0x80 : 0));
+}
+__device__ __forceinline__ uint64_t desc_k_sw(uint32_t addr, int sw) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;                                   // LBO: unused for swizzled K-major
+  d |= (uint64_t)((sw == 128 ? 1024 : 512) >> 4) << 32;     // SBO: 8 rows
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(sw == 128 ? 2 : 4) << 61;                 // layout type: SWIZZLE_128B = 2, SWIZZLE_64B = 4
+  return d;
+}
+__global__ void layout_check(int sw, float* dout) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* base = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tm;
+  const int K = sw, N = 64;
+  uint8_t* a = base;
+  uint8_t* b = base + 128 * sw;
+  for (int i = threadIdx.x; i < (128 + N) * K; i += blockDim.x) {
+    const bool isb = i >= 128 * K;
+    const int e = isb ? i - 128 * K : i, r = e / K, k = e % K;
+    const int v = isb ? (3 * r + k) % 5 - 2 : (r + 2 * k) % 7 - 3;
+    const int chunk = k / 16, x = sw == 128 ? (r % 8) : ((r % 8) / 2);
+    const int off = (r / 8) * (8 * sw) + (r % 8) * sw + ((chunk ^ x) * 16) + k % 16;
+    (isb ? b : a)[off] = e4m3_small(v);
+  }
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (threadIdx.x < 32) { tmem_alloc(&tm, 64); tmem_relinquish(); }
+  fence_proxy_async_smem();
+  tc_fence_before(); __syncthreads(); tc_fence_after();
+  const uint32_t tmem = __shfl_sync(0xffffffffu, tm, 0);
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = umma_idesc_f16(128, N);
+    for (int k = 0; k < K / 32; ++k)
+      umma_f8(tmem, desc_k_sw(smem_u32(a), sw) + (uint64_t)((k * 32) >> 4), desc_k_sw(smem_u32(b), sw) + (uint64_t)((k * 32) >> 4),
+              idesc, k ? 1u : 0u);
+    umma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after();
+  const int warp = threadIdx.x >> 5;
+  for (int c0 = 0; c0 < N; c0 += 32) {
+    uint32_t r[32];
+    tmem_ld_32x32(tmem + ((uint32_t)(warp * 32) << 16) + c0, r);
+    tmem_ld_wait();
+    for (int c = 0; c < 32; ++c) dout[threadIdx.x * N + c0 + c] = __uint_as_float(r[c]);
+  }
+  tc_fence_before(); __syncthreads();
+  if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc(tmem, 64); }
+}
+
+static int run_layout_check(int sw) {
+  float* dd; cudaMalloc(&dd, 128 * 64 * 4);
+  cudaFuncSetAttribute(layout_check, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  layout_check<<<1, 128, 64 * 1024>>>(sw, dd);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("layout check sw %d: %s\n", sw, cudaGetErrorString(e)); return 1; }
+  static float h[128 * 64];
+  cudaMemcpy(h, dd, sizeof(h), cudaMemcpyDeviceToHost);
+  int bad = 0;
+  for (int r = 0; r < 128; ++r)
+    for (int n = 0; n < 64; ++n) {
+      float want = 0.f;
+      for (int k = 0; k < sw; ++k) want += (float)((r + 2 * k) % 7 - 3) * (float)((3 * n + k) % 5 - 2);
+      if (h[r * 64 + n] != want && bad++ < 4) printf("  sw %d D[%d][%d] = %g, expected %g\n", sw, r, n, h[r * 64 + n], want);
+    }
+  printf("layout check e4m3 K-major SWIZZLE_%dB (K = %d, 128 x 64): %s (%d mismatches)\n", sw, sw, bad ? "FAILED" : "ok", bad);
+  return 0;
+}
+
 int main() {
+  run_layout_check(128);
+  run_layout_check(64);
   long long* d; float* v;
   cudaMalloc(&d, 16); cudaMalloc(&v, 8);
   cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
