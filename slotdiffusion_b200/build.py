@@ -17,6 +17,9 @@ STAMP = os.path.join(HERE, '.libsdb200.stamp')
 SOURCES = ['api.cu', 'gemm.cu', 'elementwise.cu', 'attention.cu', 'attention_tc.cu', 'slot_attention.cu', 'slot_attention_fused.cu', 'slot_update.cu', 'backward.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '--use_fast_math=false']
+# kernel changes made without GPU access stay behind a macro until they have been run (csrc/slot_attention_fused.cu)
+if os.environ.get('SDB_SF_EXPERIMENTAL', '0') == '1':
+    NVCC_FLAGS.append('-DSDB_SF_EXPERIMENTAL=1')
 
 
 def _nvcc():

@@ -117,10 +117,20 @@ __device__ __forceinline__ void tmem_ld_folded(uint32_t taddr, float (&out)[SP])
   }
 }
 
-// latency-critical single-thread wait (MMA issuers): non-blocking test_wait in a tight loop, bounded.
-// The clock is read once per 4096 polls: with a clock64() compare on every poll the wait loops of this kernel were
-// 38 % of all executed warp instructions (ncu source counters, profiles/README.md section 12) and compete for issue
-// slots with the converter warps of the same scheduler.
+// Two changes derived offline from the ncu source page of this kernel (profiles/README.md section 12) were made after the
+// round's GPU budget was spent.  They are compiled in only with -DSDB_SF_EXPERIMENTAL=1 (SDB_SF_EXPERIMENTAL=1 python -m
+// slotdiffusion_b200.build) until tools/gpu_round2_first.sh has run the parity tests and timed both builds:
+//   * bounded-wait loops read the clock once per 256 / 4096 polls instead of on each one (poll loops were 40 % of the
+//     executed warp instructions: 18 -> 8 instructions per poll);
+//   * the converters zero rows beyond the end of a sample only in the partial last group (48 FSELs of 611 instructions).
+#ifndef SDB_SF_EXPERIMENTAL
+#define SDB_SF_EXPERIMENTAL 0
+#endif
+#if SDB_SF_EXPERIMENTAL
+constexpr uint32_t SF_SPIN_CLOCK_MASK = 0xfffu;   // read the clock when (polls & mask) == 0
+constexpr uint32_t SF_WAIT_CLOCK_MASK = 0xffu;
+
+// latency-critical single-thread wait (MMA issuers): non-blocking test_wait in a tight loop, bounded
 __device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity) {
   const uint32_t a = smem_u32(bar);
   long long t0 = 0;
@@ -135,7 +145,7 @@ __device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity) {
         : "r"(a), "r"(parity)
         : "memory");
     if (ok) return;
-    if ((++polls & 0xfffu) == 0) {
+    if ((++polls & SF_SPIN_CLOCK_MASK) == 0) {
       const long long now = clock64();
       if (t0 == 0) t0 = now;
       else if (now - t0 > 4000000000LL) {
@@ -152,7 +162,7 @@ __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, i
     long long t0 = 0;
     uint32_t polls = 0;
     while (!mbar_try_wait(bar, parity)) {     // try_wait itself blocks for a hardware-defined interval (~200 cycles)
-      if ((++polls & 0xffu) == 0) {           // bounded wait: look at the clock every 256 polls
+      if ((++polls & SF_WAIT_CLOCK_MASK) == 0) {
         const long long now = clock64();
         if (t0 == 0) t0 = now;
         else if (now - t0 > 4000000000LL) {
@@ -165,6 +175,49 @@ __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, i
   __syncwarp();
   mbar_wait(bar, parity);   // already complete: one try_wait per thread = its own acquire
 }
+
+#else   // the GPU-verified wait loops, verbatim
+// latency-critical single-thread wait (MMA issuers): non-blocking test_wait in a tight loop, bounded
+__device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  long long t0 = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(a), "r"(parity)
+        : "memory");
+    if (ok) return;
+    const long long now = clock64();
+    if (t0 == 0) t0 = now;
+    else if (now - t0 > 4000000000LL) {
+      printf("sdb200: mbarrier spin timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+      __trap();
+    }
+  }
+}
+
+// one lane polls, the warp follows (keeps hundreds of threads from hammering the barrier)
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int lane) {
+  if (lane == 0) {
+    long long t0 = 0;
+    while (!mbar_try_wait(bar, parity)) {     // try_wait itself blocks for a hardware-defined interval
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000LL) {
+        printf("sdb200: mbarrier wait timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+        __trap();
+      }
+    }
+  }
+  __syncwarp();
+  mbar_wait(bar, parity);   // already complete: one try_wait per thread = its own acquire
+}
+
+#endif
 
 __device__ __forceinline__ void l2_prefetch(const void* src, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(src)), "r"(bytes) : "memory");
@@ -361,9 +414,10 @@ slot_attend_fused_kernel(const float* __restrict__ x, const float* __restrict__ 
         if (c < nchunks) mbar_wait_warp(&ctl.sfull[set * SF_CPT + cc], (i / NSETS) & 1, lane);   // CTA-uniform branch
         else mbar_wait_warp(&ctl.xempty[set], ((i / NSETS) & 1) ^ 1, lane);   // zero-filled chunk: the set must still be free
         if (lane == 0 && gi == 0) SF_T(3, i, 0);
+#if SDB_SF_EXPERIMENTAL
         // every token of the group inside the sample (warp-uniform; false only in the last group of a ragged N):
         // skips the 48 selects per lane that zero the rows beyond the end (8 % of the converter's instruction stream,
-        // which is issue-bound: ncu `stall_not_selected` is its top stall reason, profiles/README.md section 12)
+        // which is issue-bound: ncu `stall_not_selected` is its top stall reason, profiles/README.md section 12).
         const bool group_full = (i * SF_TILE + gi * 8 + 8) <= ntok;
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
@@ -381,6 +435,19 @@ slot_attend_fused_kernel(const float* __restrict__ x, const float* __restrict__ 
               if (!valid) v[q][k] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
+#else   // GPU-verified form
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int tg = tok_in_group(q);
+          const bool valid = (i * SF_TILE + gi * 8 + tg) < ntok;
+          const float* row = reinterpret_cast<const float*>(grp) + tg * DIN + 4 * j;
+#pragma unroll
+          for (int k = 0; k < NV; ++k) {
+            v[q][k] = *reinterpret_cast<const float4*>(row + 32 * k);   // stale bytes if !valid: zeroed below, no branch
+            if (!valid) v[q][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+#endif
         __syncwarp();                                       // all fp32 rows of the group are in registers
 #pragma unroll
         for (int q = 0; q < 2; ++q) {

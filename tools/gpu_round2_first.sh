@@ -13,5 +13,10 @@ nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I slotdiffusion_b20
   && timeout 120 ./tools/probes/umma_f8_probe.bin 2>&1 | tee gpurun_out/umma_f8_probe.log
 echo "=== fused attend timeline at B=256 (which stage is long under full-chip load?)"
 SA_B=256 timeout 120 python tools/sa_timeline.py 2>&1 | tail -40 | tee gpurun_out/sa_timeline_b256.log
+echo "=== fused attend: experimental build (cheaper mbarrier polls, tail selects only in the partial group) -- parity, then timing"
+SDB_SF_EXPERIMENTAL=1 python -m slotdiffusion_b200.build --force > /dev/null 2>&1
+SDB_SF_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_modules_gpu.py tests/test_ops_gpu.py -q -m gpu -k "slot_att" 2>&1 | tail -4 | tee gpurun_out/sf_experimental_tests.log
+SDB_SF_EXPERIMENTAL=1 timeout 300 python tools/sa_bench.py --batch 64 256 2>&1 | tail -2 | tee gpurun_out/sa_bench_experimental.log
+python -m slotdiffusion_b200.build --force > /dev/null 2>&1    # back to the default build
 # second call (separate, ~6 GPU-min): source-level ncu reports to read offline with tools/ncu_wait_share.py / ncu_stalls.py
 #   gpurun --timeout 900 -- 'bash tools/gpu_profile.sh r2a "gemm_kernel" 6; SA_B=256 bash tools/gpu_sa_profile.sh sa_b256'
