@@ -152,6 +152,11 @@ int sdb_geglu_pack(const float* u, void* out, int64_t M, int64_t F, void* stream
 /* sinusoidal timestep embedding, [cos | sin] order, fp32 freqs (unet/utils.py:79-86) -> packed [2][B][dim] */
 int sdb_timestep_embedding_pack(const float* t, void* out, int64_t B, int dim, void* stream);
 
+/* Diagnostic (only in a library built with SDB_GEMM_TIMING=1; otherwise SDB_ERR_UNSUPPORTED): where the MMA-issuing
+ * thread of sdb_gemm waits.  out4 = {cycles waiting for operand stages, cycles waiting for a free accumulator, issuer
+ * lifetime cycles, tiles issued}, summed over CTAs and launches since the last reset.  Synchronises the device. */
+int sdb_gemm_timing(uint64_t* out4, int reset);
+
 /* ------------------------------------------------------------------ attention core (attention.py:188-205)
  * out[b, i, h*d:(h+1)*d] = softmax_j(scale * q[b,i,h,:] . k[b,j,h,:]) v[b,j,h,:],   d = head dim (32)
  * q [B,Lq,*] with row stride ldq, k/v [B,Lk,*] with row strides ldk/ldv (views into fused projections).

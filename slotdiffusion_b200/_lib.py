@@ -38,6 +38,7 @@ SIGNATURES = {
     'sdb_last_error': (c_char_p, []),
     'sdb_launch_count': (c_int64, []),
     'sdb_gemm': (c_int, [POINTER(SdbGemm), c_void_p]),
+    'sdb_gemm_timing': (c_int, [c_void_p, c_int]),
     'sdb_pack_weight': (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     'sdb_pack_weight_conv3': (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     'sdb_pack_rows': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_void_p]),

@@ -20,6 +20,9 @@ NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', 
 # kernel changes made without GPU access stay behind a macro until they have been run (csrc/slot_attention_fused.cu)
 if os.environ.get('SDB_SF_EXPERIMENTAL', '0') == '1':
     NVCC_FLAGS.append('-DSDB_SF_EXPERIMENTAL=1')
+# diagnostic build: the GEMM's issuer accounts its mbarrier wait cycles (csrc/gemm.cu, sdb_gemm_timing)
+if os.environ.get('SDB_GEMM_TIMING', '0') == '1':
+    NVCC_FLAGS.append('-DSDB_GEMM_TIMING=1')
 
 
 def _nvcc():

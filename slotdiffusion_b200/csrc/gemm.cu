@@ -18,6 +18,17 @@
 
 namespace sdb {
 
+// Issuer wait accounting, compiled in only with -DSDB_GEMM_TIMING=1 (SDB_GEMM_TIMING=1 python -m slotdiffusion_b200.build):
+// cycles the MMA-issuing thread spends waiting for operands (full[stage]: TMA / L2 fill) and for a free accumulator
+// (acc_empty: epilogue), summed over all CTAs and launches since the last reset; read with sdb_gemm_timing().
+// The default build contains none of it.
+#ifndef SDB_GEMM_TIMING
+#define SDB_GEMM_TIMING 0
+#endif
+#if SDB_GEMM_TIMING
+__device__ unsigned long long g_gemm_timing[4];   // wait full | wait acc_empty | issuer lifetime | tiles issued
+#endif
+
 constexpr int BM = 128;          // rows of A per CTA (UMMA M = 128 * CG)
 constexpr int BK = 64;           // fp16 elements per stage row = 128 B = one swizzle-128B row
 constexpr int UK = 16;           // UMMA K for 16-bit operands
@@ -237,17 +248,33 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+#if SDB_GEMM_TIMING
+      long long tw_full = 0, tw_acc = 0;
+      const long long t_begin = clock64();
+#endif
       for (int item = group; item < num_items; item += ngroups, ++it) {
         const int tile = item / g.splits, split = item - tile * g.splits;
         const int ks_begin = (int)((long long)ksteps * split / g.splits);
         const int ks_end = (int)((long long)ksteps * (split + 1) / g.splits);
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
+#if SDB_GEMM_TIMING
+        const long long ta = clock64();
+#endif
         mbar_wait(&ctl.acc_empty[as], aphase ^ 1);
+#if SDB_GEMM_TIMING
+        tw_acc += clock64() - ta;
+#endif
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * ACC_COLS;
         for (int ks = ks_begin; ks < ks_end; ++ks) {
+#if SDB_GEMM_TIMING
+          const long long tf = clock64();
+#endif
           mbar_wait(&ctl.full[stage], phase);
+#if SDB_GEMM_TIMING
+          tw_full += clock64() - tf;
+#endif
           tc_fence_after();
           const uint32_t a_hi = smem_u32(ring + (size_t)stage * g.stage_bytes);
           const uint32_t a_lo = a_hi + TILE_A_BYTES;
@@ -282,6 +309,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
         }
         if (CG == 2) umma_commit_pair(&ctl.acc_full[as]); else umma_commit(&ctl.acc_full[as]);   // accumulator complete
       }
+#if SDB_GEMM_TIMING
+      atomicAdd(&g_gemm_timing[0], (unsigned long long)tw_full);
+      atomicAdd(&g_gemm_timing[1], (unsigned long long)tw_acc);
+      atomicAdd(&g_gemm_timing[2], (unsigned long long)(clock64() - t_begin));
+      atomicAdd(&g_gemm_timing[3], (unsigned long long)it);
+#endif
     }
   } else {
     // ===================== epilogue warps (both CTAs: each drains its own 128 TMEM lanes) =====================
@@ -749,4 +782,27 @@ extern "C" int sdb_gemm(const SdbGemm* p, void* stream) {
                    : launch_gemm<1, EPI_GEGLU>(ma_hi, ma_lo, mb_hi, mb_lo, g, groups, smem, st);
   return cg == 2 ? launch_gemm<2, EPI_F32>(ma_hi, ma_lo, mb_hi, mb_lo, g, groups, smem, st)
                  : launch_gemm<1, EPI_F32>(ma_hi, ma_lo, mb_hi, mb_lo, g, groups, smem, st);
+}
+
+/* issuer wait accounting of the SDB_GEMM_TIMING build: out4 = {cycles waiting for operands, cycles waiting for a free
+ * accumulator, issuer lifetime cycles, tiles issued} summed over CTAs and launches since the last reset (synchronises the
+ * device).  Default build: returns SDB_ERR_UNSUPPORTED and zeros. */
+extern "C" int sdb_gemm_timing(uint64_t* out4, int reset) {
+  SDB_REQUIRE(out4, "sdb_gemm_timing: null argument");
+  for (int i = 0; i < 4; ++i) out4[i] = 0;
+#if SDB_GEMM_TIMING
+  unsigned long long h[4] = {0, 0, 0, 0};
+  SDB_CHECK(cudaDeviceSynchronize());
+  SDB_CHECK(cudaMemcpyFromSymbol(h, sdb::g_gemm_timing, sizeof(h)));
+  for (int i = 0; i < 4; ++i) out4[i] = h[i];
+  if (reset) {
+    const unsigned long long z[4] = {0, 0, 0, 0};
+    SDB_CHECK(cudaMemcpyToSymbol(sdb::g_gemm_timing, z, sizeof(z)));
+  }
+  return 0;
+#else
+  (void)reset;
+  sdb::set_error("sdb_gemm_timing: library built without SDB_GEMM_TIMING=1");
+  return SDB_ERR_UNSUPPORTED;
+#endif
 }

@@ -20,3 +20,5 @@ SDB_SF_EXPERIMENTAL=1 timeout 300 python tools/sa_bench.py --batch 64 256 2>&1 |
 python -m slotdiffusion_b200.build --force > /dev/null 2>&1    # back to the default build
 # second call (separate, ~6 GPU-min): source-level ncu reports to read offline with tools/ncu_wait_share.py / ncu_stalls.py
 #   gpurun --timeout 900 -- 'bash tools/gpu_profile.sh r2a "gemm_kernel" 6; SA_B=256 bash tools/gpu_sa_profile.sh sa_b256'
+#   third (GEMM issuer wait split):
+#   gpurun --timeout 600 -- 'SDB_GEMM_TIMING=1 python -m slotdiffusion_b200.build --force >/dev/null; SDB_GEMM_TIMING=1 python tools/gemm_wait_split.py | tee gpurun_out/gemm_wait_split.log'
