@@ -7,7 +7,9 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_uint64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libsdb200.so')
+# SDB_LIB selects a build variant of the same sources (slotdiffusion_b200/build.py: experimental / diagnostic macros);
+# unset = the product build
+LIB_PATH = os.environ.get('SDB_LIB') or os.path.join(HERE, 'libsdb200.so')
 
 SDB_A_PLAIN, SDB_A_CONV3, SDB_A_CONV3S2, SDB_A_WGRAD, SDB_A_WGRAD_S2 = 0, 1, 2, 3, 4
 SDB_PACK_PLAIN, SDB_PACK_UP2, SDB_PACK_PHASE2 = 0, 1, 2

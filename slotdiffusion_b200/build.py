@@ -12,17 +12,23 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
-LIB = os.path.join(HERE, 'libsdb200.so')
-STAMP = os.path.join(HERE, '.libsdb200.stamp')
 SOURCES = ['api.cu', 'gemm.cu', 'elementwise.cu', 'attention.cu', 'attention_tc.cu', 'slot_attention.cu', 'slot_attention_fused.cu', 'slot_update.cu', 'backward.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '--use_fast_math=false']
+# Build variants live next to the product library under their own names (they travel to the GPU box with it and are
+# selected at run time with SDB_LIB=<path>, see _lib.py); the product build is always libsdb200.so.
+VARIANT = ''
 # kernel changes made without GPU access stay behind a macro until they have been run (csrc/slot_attention_fused.cu)
 if os.environ.get('SDB_SF_EXPERIMENTAL', '0') == '1':
     NVCC_FLAGS.append('-DSDB_SF_EXPERIMENTAL=1')
+    VARIANT += '_sfexp'
 # diagnostic build: the GEMM's issuer accounts its mbarrier wait cycles (csrc/gemm.cu, sdb_gemm_timing)
 if os.environ.get('SDB_GEMM_TIMING', '0') == '1':
     NVCC_FLAGS.append('-DSDB_GEMM_TIMING=1')
+    VARIANT += '_gtiming'
+LIB = os.path.join(HERE, f'libsdb200{VARIANT}.so')
+STAMP = os.path.join(HERE, f'.libsdb200{VARIANT}.stamp')
+BUILD_DIR = os.path.join(HERE, 'build' + VARIANT)
 
 
 def _nvcc():
@@ -51,13 +57,13 @@ def build(force=False, verbose=True):
         return LIB
     objs = []
     procs = []
-    os.makedirs(os.path.join(HERE, 'build'), exist_ok=True)
+    os.makedirs(BUILD_DIR, exist_ok=True)
     flags = [f for f in NVCC_FLAGS if not f.startswith('--use_fast_math')]
     for src in SOURCES:
         sp = os.path.join(CSRC, src)
         if not os.path.exists(sp):
             continue
-        obj = os.path.join(HERE, 'build', src.replace('.cu', '.o'))
+        obj = os.path.join(BUILD_DIR, src.replace('.cu', '.o'))
         objs.append(obj)
         cmd = [_nvcc()] + flags + ['-c', sp, '-o', obj]
         if verbose:

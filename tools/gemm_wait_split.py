@@ -1,9 +1,8 @@
 #!/usr/bin/env python
 """Where does the GEMM's MMA-issuing thread wait?  Needs the diagnostic build:
 
-    SDB_GEMM_TIMING=1 python -m slotdiffusion_b200.build --force
-    SDB_GEMM_TIMING=1 python tools/gemm_wait_split.py [--batch 256]
-    python -m slotdiffusion_b200.build --force            # back to the product build
+    SDB_GEMM_TIMING=1 python -m slotdiffusion_b200.build          # -> slotdiffusion_b200/libsdb200_gtiming.so (next to the product .so)
+    SDB_LIB=$PWD/slotdiffusion_b200/libsdb200_gtiming.so python tools/gemm_wait_split.py [--batch 256]
 
 Per shape: share of the issuer's lifetime spent waiting for operand stages (full[stage]: TMA / L2 fill behind), waiting
 for a free accumulator (acc_empty: epilogue behind), and issuing (the rest ~ tensor pipe busy or issue-bound).
