@@ -25,3 +25,5 @@ TIM=$PWD/slotdiffusion_b200/libsdb200_gtiming.so
 SDB_LIB=$TIM timeout 300 python tools/gemm_wait_split.py 2>&1 | tail -10 | tee gpurun_out/gemm_wait_split.log
 # second call (separate, ~6 GPU-min): source-level ncu reports to read offline with tools/ncu_wait_share.py / ncu_stalls.py
 #   gpurun --timeout 900 -- 'bash tools/gpu_profile.sh r2a "gemm_kernel" 6; SA_B=256 bash tools/gpu_sa_profile.sh sa_b256'
+#   sanitizer pass over the new kernel (memcheck + racecheck on the smallest cases; slow, keep it to a few tests):
+#   gpurun --timeout 900 -- 'compute-sanitizer --tool memcheck python -m pytest tests/test_slot_update_gpu.py -q -m gpu_next -k "op_matches or ragged" 2>&1 | tail -15; compute-sanitizer --tool racecheck python -m pytest tests/test_slot_update_gpu.py -q -m gpu_next -k "op_matches" 2>&1 | tail -15'
