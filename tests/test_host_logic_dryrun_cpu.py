@@ -158,3 +158,33 @@ def test_shipped_unet_geometries_forward_and_backward(dry, name, hw, S, dc):
     assert all(p.grad is not None for p in net.parameters()) and ctx.grad.shape == ctx.shape
     with torch.no_grad():
         assert net.eval()._exec(x, torch.tensor([12.5]), ctx.detach()).shape == x.shape
+
+
+def test_full_model_training_chain_wires_up(dry):
+    """tools/full_model_train_bench.py in miniature: eager-PyTorch encoder -> Slot Attention (tape) -> UNet (tape) -> loss;
+    gradients reach the encoder through both hand-written backward passes"""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tools'))
+    from full_model_parts import ImageEncoder, VQVAEEncoder
+    from slotdiffusion_b200 import autograd
+    from slotdiffusion_b200.slot_attention import SlotAttentionWMask
+    B, S, D = 2, 4, 64
+    enc = ImageEncoder((32, 32), D).train()
+    vae = VQVAEEncoder().eval().requires_grad_(False)
+    sa = SlotAttentionWMask(D, 2, S, D, 2 * D).train()
+    net = small_unet(dropout=0.1).train()
+    init = torch.nn.Parameter(torch.randn(1, S, D))
+    img = torch.randn(B, 3, 32, 32).clamp(-1, 1)
+    with torch.no_grad():
+        x0 = vae(img)
+    assert x0.shape == (B, 3, 8, 8)
+    feats = enc(img)
+    assert feats.shape == (B, 64, D)
+    slots, mask = autograd.slot_attention_apply(sa, feats, init.expand(B, -1, -1), True)
+    eps = torch.randn_like(x0)
+    loss = torch.nn.functional.mse_loss(net._exec(0.7 * x0 + 0.3 * eps, torch.tensor([10, 900]), slots), eps)
+    loss.backward()
+    for name, mod in (('encoder', enc), ('slot attention', sa), ('unet', net)):
+        assert all(p.grad is not None for p in mod.parameters()), name
+    assert init.grad is not None and init.grad.shape == init.shape
