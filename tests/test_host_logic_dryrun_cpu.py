@@ -188,3 +188,29 @@ def test_full_model_training_chain_wires_up(dry):
     for name, mod in (('encoder', enc), ('slot attention', sa), ('unet', net)):
         assert all(p.grad is not None for p in mod.parameters()), name
     assert init.grad is not None and init.grad.shape == init.shape
+
+
+def test_video_recurrence_chain_wires_up(dry):
+    """SAViDiffusion.encode (savi_diffusion.py:183-196) in miniature: the same Slot-Attention module applied once per frame,
+    frame t+1 initialised by a TransformerPredictor of frame t's slots; backward runs through all T applications (a fresh
+    flat gradient buffer per application, accumulated by autograd)"""
+    from slotdiffusion_b200 import autograd
+    from slotdiffusion_b200.slot_attention import SlotAttentionWMask
+    B, T, N, S, D = 2, 3, 64, 5, 64
+    sa = SlotAttentionWMask(D, 2, S, D, 2 * D).train()
+    layer = torch.nn.TransformerEncoderLayer(d_model=D, nhead=4, dim_feedforward=4 * D, norm_first=True, batch_first=True)
+    predictor = torch.nn.TransformerEncoder(layer, num_layers=2).train()
+    init = torch.nn.Parameter(torch.randn(1, S, D))
+    feats = torch.randn(B, T, N, D, requires_grad=True)
+    prev, frames = None, []
+    for f in range(T):
+        lat = init.expand(B, -1, -1) if prev is None else predictor(prev)
+        prev, mask = autograd.slot_attention_apply(sa, feats[:, f].contiguous(), lat, True)
+        assert mask.shape == (B, S, N) and not mask.requires_grad
+        frames.append(prev)
+    slots = torch.stack(frames, 1)
+    assert slots.shape == (B, T, S, D)
+    slots.sum().backward()
+    assert feats.grad.shape == feats.shape and init.grad is not None
+    assert all(p.grad is not None for p in sa.parameters()) and all(p.grad is not None for p in predictor.parameters())
+    assert dry.calls['sdb_slot_attend_bwd'] == T * 2            # iterations x frames

@@ -25,6 +25,7 @@ TIM=$PWD/slotdiffusion_b200/libsdb200_gtiming.so
 SDB_LIB=$TIM timeout 300 python tools/gemm_wait_split.py 2>&1 | tail -10 | tee gpurun_out/gemm_wait_split.log
 echo "=== full-model training step (reference's eager encoder / VQ-VAE encoder around the B200 modules)"
 timeout 300 python tools/full_model_train_bench.py --batch 64 2>&1 | tail -2 | tee gpurun_out/full_model_train.log
+timeout 300 python tools/full_model_train_bench.py --frames 3 --slots 15 --iters 2 --batch 16 2>&1 | tail -2 | tee gpurun_out/full_model_train_video.log
 # second call (separate, ~6 GPU-min): source-level ncu reports to read offline with tools/ncu_wait_share.py / ncu_stalls.py
 #   gpurun --timeout 900 -- 'bash tools/gpu_profile.sh r2a "gemm_kernel" 6; SA_B=256 bash tools/gpu_sa_profile.sh sa_b256'
 #   sanitizer pass over the new kernel (memcheck + racecheck on the smallest cases; slow, keep it to a few tests):
