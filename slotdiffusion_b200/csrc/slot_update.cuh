@@ -33,19 +33,25 @@ struct Lay {   // float offsets into the CTA's scratch; every array starts 16-by
   int u, h, gi, gh, hn, ln, y1, so, stat, red, total;
 };
 
+// SU_LAYOUT_PAD (host emulation only): unused floats after every array, so that the emulation can check that no phase
+// writes outside the array it owns; the kernel is compiled with 0.
+#ifndef SU_LAYOUT_PAD
+#define SU_LAYOUT_PAD 0
+#endif
+
 SU_HD Lay layout(int RT, int Din, int D, int M, int nt) {
   Lay l;
   int o = 0;
-  l.u = o;    o += RT * Din;     // normalised weighted feature means U (GRU input before the folded projection)
-  l.h = o;    o += RT * D;       // previous slots
-  l.gi = o;   o += RT * 3 * D;   // GRU input projection  (r | z | n)
-  l.gh = o;   o += RT * 3 * D;   // GRU hidden projection (r | z | n)
-  l.hn = o;   o += RT * D;       // GRU output
-  l.ln = o;   o += RT * D;       // LayerNorm output (MLP input, later the q-projection input)
-  l.y1 = o;   o += RT * M;       // MLP hidden
-  l.so = o;   o += RT * D;       // new slots
-  l.stat = o; o += 2 * RT;       // (mean, rstd) per row
-  l.red = o;  o += (nt + 3) / 4 * 4;   // per-thread partials of the row reductions
+  l.u = o;    o += RT * Din + SU_LAYOUT_PAD;     // normalised weighted feature means U (GRU input before the folded projection)
+  l.h = o;    o += RT * D + SU_LAYOUT_PAD;       // previous slots
+  l.gi = o;   o += RT * 3 * D + SU_LAYOUT_PAD;   // GRU input projection  (r | z | n)
+  l.gh = o;   o += RT * 3 * D + SU_LAYOUT_PAD;   // GRU hidden projection (r | z | n)
+  l.hn = o;   o += RT * D + SU_LAYOUT_PAD;       // GRU output
+  l.ln = o;   o += RT * D + SU_LAYOUT_PAD;       // LayerNorm output (MLP input, later the q-projection input)
+  l.y1 = o;   o += RT * M + SU_LAYOUT_PAD;       // MLP hidden
+  l.so = o;   o += RT * D + SU_LAYOUT_PAD;       // new slots
+  l.stat = o; o += 2 * RT + SU_LAYOUT_PAD;       // (mean, rstd) per row
+  l.red = o;  o += (nt + 3) / 4 * 4 + SU_LAYOUT_PAD;   // per-thread partials of the row reductions
   l.total = o;
   return l;
 }

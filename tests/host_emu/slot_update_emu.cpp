@@ -7,6 +7,8 @@
 
 #include "../../slotdiffusion_b200/csrc/slot_update.cuh"
 
+static long g_canary_violations = 0;
+
 template <int RT>
 static void run(const SdbSlotUpdate& p, int nt, int order) {
   const sdb::su::Lay l = sdb::su::layout(RT, p.Din, p.D, p.M, nt);
@@ -19,9 +21,18 @@ static void run(const SdbSlotUpdate& p, int nt, int order) {
       // order 0: threads 0..nt-1; order 1: reversed (a result that depends on the order within a phase is a race)
       for (int i = 0; i < nt; ++i) sdb::su::phase<RT>(ph, order ? nt - 1 - i : i, nt, tile, p, sm.data());
     }
+#if SU_LAYOUT_PAD > 0
+    // the SU_LAYOUT_PAD floats after every array must still hold their NaN fill: nothing wrote past an array's end
+    const int starts[] = {l.u, l.h, l.gi, l.gh, l.hn, l.ln, l.y1, l.so, l.stat, l.red, l.total};
+    for (int a = 1; a <= 10; ++a)
+      for (int i = starts[a] - SU_LAYOUT_PAD; i < starts[a]; ++i)
+        if (!std::isnan(sm[(size_t)i])) ++g_canary_violations;
+#endif
   }
 }
 
+extern "C" long su_canary_violations() { return g_canary_violations; }
+extern "C" int su_layout_pad() { return SU_LAYOUT_PAD; }
 extern "C" int su_scratch_floats(int RT, int Din, int D, int M, int nt) { return sdb::su::layout(RT, Din, D, M, nt).total; }
 
 extern "C" int su_emulate(const SdbSlotUpdate* p, int RT, int nt, int order) {

@@ -20,17 +20,28 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ASCALE = 4096.0
 
 
-@pytest.fixture(scope='module')
-def emu(tmp_path_factory):
-    so = str(tmp_path_factory.mktemp('su_emu') / 'slot_update_emu.so')
+def _build_emu(tmp_path_factory, name, extra=()):
+    so = str(tmp_path_factory.mktemp(name) / 'slot_update_emu.so')
     src = os.path.join(ROOT, 'tests', 'host_emu', 'slot_update_emu.cpp')
-    flags = ['-O2', '-std=c++17', '-shared', '-fPIC']
+    flags = ['-O2', '-std=c++17', '-shared', '-fPIC'] + list(extra)
     if 'fma' in open('/proc/cpuinfo').read():
         flags.append('-mfma')          # fmaf -> one instruction, same rounding as the device FFMA
     subprocess.check_call(['g++'] + flags + ['-o', so, src])
     lib = ctypes.CDLL(so)
     lib.su_emulate.restype = ctypes.c_int
+    lib.su_canary_violations.restype = ctypes.c_long
     return lib
+
+
+@pytest.fixture(scope='module')
+def emu(tmp_path_factory):
+    return _build_emu(tmp_path_factory, 'su_emu')
+
+
+@pytest.fixture(scope='module')
+def emu_padded(tmp_path_factory):
+    """same phase code, scratch arrays separated by 64 NaN-filled floats each (SU_LAYOUT_PAD)"""
+    return _build_emu(tmp_path_factory, 'su_emu_pad', ['-DSU_LAYOUT_PAD=64'])
 
 
 def attend_cpu(chunks):
@@ -111,6 +122,17 @@ def test_chunk_count_and_row_tile_do_not_change_the_result(emu):
     ref = run_module(emu, name, 8, chunks=1)[0]
     for RT, chunks in ((4, 1), (8, 3), (4, 5)):
         assert rel_l2(run_module(emu, name, RT, chunks=chunks)[0], ref) < 1e-6
+
+
+def test_no_phase_writes_outside_its_scratch_array(emu_padded):
+    """every scratch array followed by 64 canary floats: they stay untouched, and the results stay finite and equal"""
+    assert emu_padded.su_layout_pad() == 64
+    for name in ('sa_img_clevrtex', 'sa_ragged_small', 'sa_coco_vitb16', 'sa_movie_24slots'):
+        for RT in (4, 8):
+            slots, mask, (p, x, s0, iters) = run_module(emu_padded, name, RT)
+            ref_s, _ = sa_ref.slot_attention_forward(p, x.double(), s0.double(), iters)
+            assert rel_l2(slots, ref_s) < 2e-6
+    assert emu_padded.su_canary_violations() == 0
 
 
 def test_pad_columns_of_qa_are_written(emu):
