@@ -16,12 +16,12 @@ SA_B=256 timeout 120 python tools/sa_timeline.py 2>&1 | tail -40 | tee gpurun_ou
 echo "=== fused attend: experimental build (cheaper mbarrier polls, tail selects only in the partial group) -- parity, then timing"
 # variants are prebuilt here (SDB_SF_EXPERIMENTAL=1 / SDB_GEMM_TIMING=1 python -m slotdiffusion_b200.build) and travel with the snapshot
 EXP=$PWD/slotdiffusion_b200/libsdb200_sfexp.so
-[ -f "$EXP" ] || SDB_SF_EXPERIMENTAL=1 python -m slotdiffusion_b200.build > /dev/null 2>&1
+SDB_SF_EXPERIMENTAL=1 python -m slotdiffusion_b200.build > /dev/null 2>&1      # no-op when the prebuilt variant is up to date
 SDB_LIB=$EXP timeout 300 python -m pytest tests/test_modules_gpu.py tests/test_ops_gpu.py -q -m gpu -k "slot_att" 2>&1 | tail -4 | tee gpurun_out/sf_experimental_tests.log
 SDB_LIB=$EXP timeout 300 python tools/sa_bench.py --batch 64 256 2>&1 | tail -2 | tee gpurun_out/sa_bench_experimental.log
 echo "=== GEMM issuer wait split (DESIGN 8.3): operands vs accumulator vs issuing"
 TIM=$PWD/slotdiffusion_b200/libsdb200_gtiming.so
-[ -f "$TIM" ] || SDB_GEMM_TIMING=1 python -m slotdiffusion_b200.build > /dev/null 2>&1
+SDB_GEMM_TIMING=1 python -m slotdiffusion_b200.build > /dev/null 2>&1
 SDB_LIB=$TIM timeout 300 python tools/gemm_wait_split.py 2>&1 | tail -10 | tee gpurun_out/gemm_wait_split.log
 echo "=== full-model training step (reference's eager encoder / VQ-VAE encoder around the B200 modules)"
 timeout 300 python tools/full_model_train_bench.py --batch 64 2>&1 | tail -2 | tee gpurun_out/full_model_train.log
