@@ -135,6 +135,7 @@ class DPMSolverSampler:
         self._graphs = {}
         self._t_all = {}
         self._sig = None
+        self._params = None
 
     @property
     def nfe(self):
@@ -144,8 +145,10 @@ class DPMSolverSampler:
         """Changes whenever a UNet parameter is updated in place (optimizer step, load_state_dict: `_version`) or
         re-allocated (`.to()`, `.data = ...`: `data_ptr`).  A captured graph holds the addresses of the PACKED weights
         of the parameter version it was captured with (ops.WeightCache re-packs into new buffers afterwards)."""
+        if self._params is None:          # the Parameter objects of a module are stable (.to() / load_state_dict keep them)
+            self._params = tuple(self.unet.parameters())
         v, a = 0, 0
-        for p in self.unet.parameters():
+        for p in self._params:
             v += p._version
             a ^= p.data_ptr()
         return v, a
