@@ -24,6 +24,11 @@ from oracle import unet_ref  # noqa: E402
 
 
 def timed(fn, reps):
+    if not torch.cuda.is_available():        # --cpu-selftest: exercise the code path only
+        import time
+        t0 = time.perf_counter()
+        fn()
+        return (time.perf_counter() - t0) * 1e3
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
@@ -40,8 +45,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--batch', type=int, default=64)
     ap.add_argument('--reps', type=int, default=5)
+    ap.add_argument('--cpu-selftest', action='store_true', help='run the eager arm once on the CPU (no libsdb200 arm): script check')
     args = ap.parse_args()
-    dev = torch.device('cuda')
+    dev = torch.device('cpu' if args.cpu_selftest else 'cuda')
     B, S, D, N = args.batch, 11, 192, 1024
     sd = {k: v.to(dev) for k, v in unet_ref.random_state_dict(seed=0).items()}
     p = {k: v.to(dev) for k, v in sa_ref.random_params(D, D, 2 * D, seed=0).items()}
@@ -63,6 +69,9 @@ def main():
         torch.backends.cudnn.allow_tf32 = False
         ref32 = unet_ref.unet_forward(sd, x, t, ctx)
         out['eager_tf32_vs_fp32_rel_l2'] = float((ref - ref32).norm() / ref32.norm())
+        if args.cpu_selftest:
+            print(json.dumps(out))
+            return
         from slotdiffusion_b200.slot_attention import SlotAttentionWMask
         from slotdiffusion_b200.unet import UNetModel
         net = UNetModel(dropout=0.1, **unet_ref.DEFAULT_CFG).to(dev).eval()
