@@ -86,3 +86,28 @@ def test_slot_update_op_matches_the_host_emulation_math():
     same, qa0 = ops.slot_update(w, None, slots, S, Din, D, M, True)
     assert same is slots
     assert rel_l2(qa0[:, :Din + 1], (sa_ref.layer_norm(slots.double(), wd['ln_q_g'], wd['ln_q_b']) @ wd['w_qaT'])[:, :Din + 1]) < 1e-5
+
+
+def test_fused_tail_forward_is_graph_capturable(fused_tail):
+    """enqueue-only, allocation-free inside the library: the 7-launch forward replays from a CUDA graph"""
+    from slotdiffusion_b200.slot_attention import SlotAttentionWMask
+    B, N, S, D = 8, 1024, 11, 192
+    mod = SlotAttentionWMask(D, 3, S, D, 2 * D).cuda()
+    mod.load_state_dict(sa_ref.random_params(D, D, 2 * D, seed=5))
+    x, s0 = seeded((B, N, D), 61).cuda(), seeded((B, S, D), 62).cuda()
+    with torch.no_grad():
+        ref_s, ref_m = mod(x, s0)                              # warm-up: weight fold, cudaFuncSetAttribute
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            mod(x, s0)
+        torch.cuda.current_stream().wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out_s, out_m = mod(x, s0)
+        x.copy_(seeded((B, N, D), 63).cuda())
+        g.replay()
+        torch.cuda.synchronize()
+        chk_s, chk_m = mod(x, s0)
+    assert torch.equal(out_s, chk_s) and torch.equal(out_m, chk_m)
+    assert not torch.equal(out_s, ref_s)
