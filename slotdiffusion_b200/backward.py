@@ -26,6 +26,26 @@ class Tape:
         self.fns = []
         self.g = {}
         self.keep = []
+        # per-call state of the module schedules (never kept on the shared trainer / module: re-entrancy)
+        self.G = None          # GradBuffer.instance of this call
+        self.dctx = None       # UNet: gradient of the context rows
+        self.xpk = None        # UNet: packed input operand (key of dx)
+        self.ykey = None       # UNet: key of the output gradient
+        self.reduced_lo = None  # data parallel: flat[reduced_lo:] has already been handed to the all-reduce
+
+    def bucket(self, start_off, force=False):
+        """Data-parallel gradient exchange overlapped with backward: the flat buffer is laid out in module
+        order, the tape runs in reverse module order, so when the backward of a top-level block has finished,
+        flat[start_off:] is final.  Ranges are handed to NCCL (its own stream, ordered after the kernels enqueued so far)
+        once they reach parallel.BUCKET_BYTES; the remaining backward kernels keep running on the compute stream."""
+        if not parallel.enabled():
+            return
+        hi = self.G.total if self.reduced_lo is None else self.reduced_lo
+        if start_off >= hi:
+            return
+        if force or (hi - start_off) * 4 >= parallel.BUCKET_BYTES:
+            parallel.allreduce_flat(self.G.flat[start_off:hi], async_op=True)
+            self.reduced_lo = start_off
 
     def acc(self, key, grad):
         if grad is None:
@@ -81,10 +101,15 @@ class GradBuffer:
         self.flat = None
         self.params = [p for p, _ in order]
 
-    def zero(self, device):
-        # a FRESH buffer per backward: autograd may adopt the returned views as .grad (gradient accumulation across
-        # micro-batches must not be clobbered by the next step's zeroing)
-        self.flat = torch.zeros(self.total, dtype=torch.float32, device=device)
+    def instance(self, device):
+        """Storage for ONE forward/backward pair: same layout, its own zeroed flat buffer.  The module may be called
+        several times before a single backward (the video models run Slot Attention once per frame,
+        savi_diffusion.py:183-196; two UNet evaluations can share one graph), so gradient storage belongs to the call,
+        never to the module; autograd may also adopt the returned views as .grad, so a buffer is never reused."""
+        g = GradBuffer.__new__(GradBuffer)
+        g.off, g.total, g.params = self.off, self.total, self.params
+        g.flat = torch.zeros(self.total, dtype=torch.float32, device=device)
+        return g
 
     def view(self, p):
         o = self.off[id(p)]
@@ -93,6 +118,10 @@ class GradBuffer:
     def span(self, plist, rows, cols):
         o = self.off[id(plist[0])]
         assert sum(p.numel() for p in plist) == rows * cols
+        e = o
+        for p in plist:                       # fused projections must really be back to back
+            assert self.off[id(p)] == e, 'GradBuffer.span: parameters are not contiguous in the flat buffer'
+            e += p.numel()
         return self.flat[o:o + rows * cols].view(rows, cols)
 
 
@@ -217,9 +246,12 @@ class UNetTrainer:
         self.net = ex.net
         self.wc = ex.wc
         net = self.net
+        # Flat gradient layout: the GLOBAL fused groups first (cross-attention K|V of every layer, the timestep
+        # projections of every ResBlock: their wgrad runs at the very end of backward), then every other parameter in
+        # module order -- so the backward of top-level block i completes flat[block_off[i]:] (see Tape.bucket).
+        # attn1.to_q / to_k / to_v of a block are consecutive in module order (attention.py:171-173), C*C % 4 == 0: the
+        # fused QKV wgrad still writes one contiguous [3C, C] range (GradBuffer.span asserts it).
         groups = []
-        for blk in ex.tblocks:
-            groups.append([blk.attn1.to_q.weight, blk.attn1.to_k.weight, blk.attn1.to_v.weight])
         kv = []
         for blk in ex.tblocks:
             kv += [blk.attn2.to_k.weight, blk.attn2.to_v.weight]
@@ -228,6 +260,14 @@ class UNetTrainer:
         groups.append([m.emb_layers[1].bias for m in ex.resblocks])
         self.G = GradBuffer(net, groups)
         self.kv_params = kv
+        front = {id(p) for g in groups for p in g}
+
+        def first_off(block):
+            offs = [self.G.off[id(p)] for p in block.parameters() if id(p) not in front]
+            return min(offs) if offs else None
+        self.block_off = {id(b): first_off(b) for b in
+                          list(net.input_blocks)[1:] + [net.middle_block] + list(net.output_blocks)}
+        self.block_off[id(net.out)] = first_off(net.out)
 
     # ------------------------------------------------------------------ pieces
     def _stats(self, x1, x2, gs1, gs2, gn, B, HW):
@@ -238,7 +278,7 @@ class UNetTrainer:
         return ops.groupnorm_stats(x1, x2, B, HW, gn.num_groups, gn.eps)
 
     def res_block(self, tp, m, x1, x2, emb_all, demb_all, B, drop_p, seed):
-        ex, wc, G, key = self.ex, self.wc, self.G, id(m)
+        ex, wc, G, key = self.ex, self.wc, tp.G, id(m)
         H, W = x1.H, x1.W
         HW = H * W
         Cin = x1.C + (x2.C if x2 is not None else 0)
@@ -284,7 +324,7 @@ class UNetTrainer:
         return Act(t, H, W, C, gs)
 
     def attention(self, tp, a, xn, B, L, t_res, key, kv=None, dkv=None, S=None):
-        wc, G = self.wc, self.G
+        wc, G = self.wc, tp.G
         C = a.to_q.weight.shape[0]
         heads, d = a.heads, C // a.heads
         if kv is None:
@@ -320,7 +360,7 @@ class UNetTrainer:
                            G.view(lo.weight), G.view(lo.bias), bias=lo.bias, residual=t_res)
 
     def spatial_transformer(self, tp, m, x, ctx_kv, d_ctx_kv, B, S):
-        ex, wc, G, key = self.ex, self.wc, self.G, id(m)
+        ex, wc, G, key = self.ex, self.wc, tp.G, id(m)
         H, W, C = x.H, x.W, x.C
         L = H * W
         st = self._stats(x.t, None, x.gs, None, m.norm, B, L)
@@ -372,7 +412,7 @@ class UNetTrainer:
         return self.ex_act(out, H, W, C, gs_o)
 
     def downsample(self, tp, m, x, B):
-        ex, wc, G = self.ex, self.wc, self.G
+        ex, wc, G = self.ex, self.wc, tp.G
         Ho, Wo = x.H // 2, x.W // 2
         xp = ops.pack_nhwc(x.t, None, B, x.H, x.W, SDB_PACK_PHASE2)
         gs = ex._gs(B, Ho * Wo, m.out_channels)
@@ -394,7 +434,7 @@ class UNetTrainer:
         return self.ex_act(y, Ho, Wo, m.out_channels, gs)
 
     def upsample(self, tp, m, x, B):
-        ex, wc, G = self.ex, self.wc, self.G
+        ex, wc, G = self.ex, self.wc, tp.G
         Ho, Wo = 2 * x.H, 2 * x.W
         xp = ops.pack_nhwc(x.t, None, B, x.H, x.W, SDB_PACK_UP2)
 
@@ -428,14 +468,14 @@ class UNetTrainer:
 
     # ------------------------------------------------------------------ whole forward (recording) and backward
     def forward(self, tp, x, timesteps, context, need_dx):
-        ex, net, wc, G = self.ex, self.net, self.wc, self.G
+        ex, net, wc = self.ex, self.net, self.wc
         B, Cin, H, W = x.shape
         S, Dc = context.shape[1], context.shape[2]
         dev = x.device
-        G.zero(dev)
+        G = tp.G = self.G.instance(dev)
         ex.begin(B, dev)
         drop_p = float(net.dropout) if net.training else 0.0
-        seed0 = (torch.initial_seed() * 1000003 + next(_step_counter) * 7907) & 0x7FFFFFFFFFFF
+        seed0 = ((torch.initial_seed() + 0x9E3779B1 * parallel.rank()) * 1000003 + next(_step_counter) * 7907) & 0x7FFFFFFFFFFF
         # ---- timestep embedding chain (unet.py:560-564 + every ResBlock's emb_layers in one GEMM)
         t = timesteps
         if t.numel() == 1 and B > 1:
@@ -461,11 +501,10 @@ class UNetTrainer:
         cp = ops.pack_rows(ctx2)
         ctx_kv = ops.gemm(cp, wc.linear('ctx_kv_all', *self.kv_params))
         d_ctx_kv = torch.zeros_like(ctx_kv)
-        self._dctx = None
 
         def bw_ctx():
             dyp, dyT = ops.grad_pack(d_ctx_kv)
-            self._dctx = ops.gemm(dyp, _cat_T(wc, 'ctx_kv_all', *self.kv_params))
+            tp.dctx = ops.gemm(dyp, _cat_T(wc, 'ctx_kv_all', *self.kv_params))
             ops.gemm(dyT, ops.transpose_packed(cp, to_bf16=True), out=G.span(self.kv_params, ex.kv_total, Dc))
         tp.push(bw_ctx)
         # ---- input conv (3 -> model_channels) as a GEMM on channels zero-padded to 64
@@ -475,17 +514,26 @@ class UNetTrainer:
         h0 = conv3_node(tp, xpk, w_in, lambda: wc._get('conv_in_pad_dg', (conv_in.weight,), lambda: ops.pack_weight_conv3_dgrad(
                             _pad_conv(conv_in.weight, conv_in.weight.shape[0], 64))),
                         G.view(conv_in.weight), G.view(conv_in.bias), (B, H, W, 64), bias=conv_in.bias, need_da=need_dx)
-        self._xpk = xpk
+        tp.xpk = xpk
         h = self.ex_act(h0, H, W, net.model_channels)
         hs = [h]
         blocks = list(net.input_blocks)[1:]
+        def mark(block):
+            # pushed BEFORE the block's nodes: runs AFTER all of them in the reversed replay
+            o = self.block_off[id(block)]
+            if o is not None:
+                tp.push(lambda: tp.bucket(o))
         for bi, block in enumerate(blocks):
+            mark(block)
             h = self.run_block(tp, block, h, None, emb_all, demb_all, ctx_kv, d_ctx_kv, B, S, drop_p, seed0 + 104729 * bi)
             hs.append(h)
+        mark(net.middle_block)
         h = self.run_block(tp, net.middle_block, h, None, emb_all, demb_all, ctx_kv, d_ctx_kv, B, S, drop_p, seed0 + 15485863)
         for bi, block in enumerate(net.output_blocks):
+            mark(block)
             h = self.run_block(tp, block, h, hs.pop(), emb_all, demb_all, ctx_kv, d_ctx_kv, B, S, drop_p,
                                seed0 + 32452843 + 104729 * bi)
+        mark(net.out)
         # ---- output head: GN + SiLU + conv3x3 (C -> out_channels), NHWC -> NCHW
         gn, conv = net.out[0], net.out[2]
         HW = h.H * h.W
@@ -496,7 +544,7 @@ class UNetTrainer:
         y = ops.nhwc_to_nchw(y_rows, B, Co, h.H, h.W)
         hC, hH, hW = h.C, h.H, h.W
 
-        ykey = self._ykey = object()     # NOT the output tensor: ctx -> output -> grad_fn -> ctx would be a reference
+        ykey = tp.ykey = object()     # NOT the output tensor: ctx -> output -> grad_fn -> ctx would be a reference
         #                                  cycle that keeps stale AccumulateGrad nodes alive (breaks CUDA-graph capture)
 
         def bw_head():
@@ -512,13 +560,13 @@ class UNetTrainer:
         tp.push(bw_head)
         return y
 
-    def backward(self, tp, ykey, dy, x_shape, need_dx):
-        tp.set(ykey, dy.contiguous().float())
+    def backward(self, tp, dy, x_shape, need_dx):
+        tp.set(tp.ykey, dy.contiguous().float())
         tp.run()
-        dctx = self._dctx
+        dctx = tp.dctx
         dx = None
         if need_dx:
-            da = tp.pop(self._xpk)                           # [M, 64]
+            da = tp.pop(tp.xpk)                           # [M, 64]
             B, Cin, H, W = x_shape
             dx = ops.nhwc_to_nchw(da, B, Cin, H, W)
         return dx, dctx
@@ -530,19 +578,23 @@ class UNetFn(torch.autograd.Function):
         tp = Tape()
         need_dx = x.requires_grad
         y = trainer.forward(tp, x.detach(), timesteps, context.detach(), need_dx)
-        ctx.trainer, ctx.tape, ctx.ykey, ctx.need_dx = trainer, tp, trainer._ykey, need_dx
+        ctx.trainer, ctx.tape, ctx.need_dx = trainer, tp, need_dx
         ctx.x_shape, ctx.ctx_shape = tuple(x.shape), tuple(context.shape)
         ctx.params = params
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        tr = ctx.trainer
-        dx, dctx = tr.backward(ctx.tape, ctx.ykey, dy, ctx.x_shape, ctx.need_dx)
+        tr, tp = ctx.trainer, ctx.tape
+        if tp is None:
+            raise RuntimeError('slotdiffusion_b200: UNet backward called twice on the same graph (retain_graph is not supported)')
+        dx, dctx = tr.backward(tp, dy, ctx.x_shape, ctx.need_dx)
+        G = tp.G
         ctx.tape = None
-        if parallel.enabled():              # one all-reduce of the whole flat gradient buffer (data parallel)
-            parallel.allreduce_flat(tr.G.flat, async_op=False)
-        grads = tuple(tr.G.view(p) if p.requires_grad else None for p in ctx.params)
+        if parallel.enabled():              # data parallel: what the buckets have not covered yet, then join
+            tp.bucket(0, force=True)
+            parallel.wait_all()
+        grads = tuple(G.view(p) if p.requires_grad else None for p in ctx.params)
         dcontext = dctx.view(ctx.ctx_shape) if dctx is not None and ctx.needs_input_grad[3] else None
         return (None, dx, None, dcontext) + grads
 
@@ -564,14 +616,15 @@ class SlotAttentionFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, mod, want_mask, inputs, slots, *params):
         tp = Tape()
-        G = getattr(mod, '_gradbuf', None)
-        if G is None:
-            G = GradBuffer(mod, [[mod.project_k.weight, mod.project_v.weight]])
-            mod._gradbuf = G
+        layout = getattr(mod, '_gradbuf', None)
+        if layout is None or layout.params_ids != tuple(id(p) for p in mod.parameters()):
+            layout = GradBuffer(mod, [[mod.project_k.weight, mod.project_v.weight]])
+            layout.params_ids = tuple(id(p) for p in mod.parameters())
+            mod._gradbuf = layout
         B, N, Din = inputs.shape
         S, D = slots.shape[1], slots.shape[2]
         dev = inputs.device
-        G.zero(dev)
+        G = tp.G = layout.instance(dev)      # per call: T frames -> T buffers, summed by autograd
         wc = mod._wcache
         x = inputs.detach().contiguous().float().reshape(B * N, Din)
         s0 = slots.detach().contiguous().float().reshape(B * S, D)
@@ -652,6 +705,8 @@ class SlotAttentionFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dslots, _dmask):
         tp, G = ctx.tape, ctx.G
+        if tp is None:
+            raise RuntimeError('slotdiffusion_b200: Slot Attention backward called twice on the same graph (retain_graph is not supported)')
         B, S, D = ctx.shapes[1]
         tp.set(ctx.out, dslots.contiguous().float().reshape(B * S, D))
         tp.run()
@@ -659,7 +714,8 @@ class SlotAttentionFn(torch.autograd.Function):
         ds0 = tp.pop(ctx.s0)
         ctx.tape = None
         if parallel.enabled():
-            parallel.allreduce_flat(G.flat, async_op=False)
+            parallel.allreduce_flat(G.flat, async_op=True)
+            parallel.wait_all()
         grads = tuple(G.view(p) if p.requires_grad else None for p in ctx.params)
         dx = dx.view(ctx.shapes[0]) if dx is not None and ctx.needs_input_grad[2] else None
         ds0 = ds0.view(ctx.shapes[1]) if ds0 is not None and ctx.needs_input_grad[3] else None

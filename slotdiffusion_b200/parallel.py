@@ -4,8 +4,11 @@ The reference trains with DistributedDataParallel inside the un-vendored `nerv` 
 `--ddp`, one process per GPU, NCCL).  Every hot-path op is per-sample (GroupNorm / LayerNorm only, no BatchNorm), so
 the only exchange is the sum of parameter gradients.  The backward of each hand-written module produces all of its
 parameter gradients in ONE flat fp32 buffer (backward.GradBuffer); when a process group is registered here that buffer
-is averaged across ranks with a single all-reduce enqueued the moment the module's backward has finished (537 MB for
-the UNet: ~1 ms on NVLink 5 / NVSwitch against a >100 ms step, so it is issued in stream order rather than bucketed).
+is averaged across ranks.  The UNet's 537 MB buffer is laid out in module order and exchanged in reverse-order BUCKETS
+while backward is still running (backward.Tape.bucket: a range is handed to NCCL as soon as the top-level block that
+owns it has finished its wgrads; NCCL runs on its own stream, the compute stream only joins before the gradients are
+returned to autograd), so only the last bucket (time embedding, input conv, the fused global projections) is exposed.
+Round 1 issued one blocking all-reduce after backward: 2.3 ms of a 42 ms step at 8 GPUs, fully exposed.
 Works with any torch.distributed backend (gloo in the CPU tests, nccl on the B200 box).
 """
 import torch
@@ -14,6 +17,11 @@ import torch.distributed as dist
 _group = None
 _enabled = False
 _pending = []
+BUCKET_BYTES = 64 << 20      # ~8 buckets for the 537 MB UNet gradient; NVSwitch all-reduce is latency-bound below ~16 MB
+
+
+def rank():
+    return dist.get_rank(_group) if dist.is_available() and dist.is_initialized() else 0
 
 
 def enable_grad_allreduce(group=None):
@@ -43,7 +51,7 @@ def allreduce_flat(flat, async_op=True):
     if flat.is_cuda:
         work = dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=_group, async_op=async_op)
     else:                                  # gloo has no AVG
-        work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=_group, async_op=False)
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=_group, async_op=False)
         flat.div_(world)
         work = None
     if work is not None and async_op:

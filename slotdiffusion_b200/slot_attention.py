@@ -47,11 +47,17 @@ class SlotAttention(nn.Module):
     def __getstate__(self):          # deepcopy / pickle: the packed-weight cache is derived state
         d = self.__dict__.copy()
         d.pop('_wcache', None)
+        d.pop('_gradbuf', None)      # gradient layout is keyed by id(parameter) of THIS instance
         return d
 
     def __setstate__(self, d):
         super().__setstate__(d)
         self._wcache = ops.WeightCache()
+
+    def invalidate_caches(self):
+        """Drop the packed / folded weights (needed after parameter updates made through `p.data`, which change neither
+        data_ptr nor _version -- the two things the cache watches)."""
+        self._wcache._c.clear()
 
     def _run(self, inputs, slots, want_mask):
         if not inputs.is_cuda:

@@ -230,6 +230,16 @@ class UNetModel(nn.Module):
         from .unet_exec import UNetExecutor
         self._exec = UNetExecutor(self)
 
+    def invalidate_caches(self):
+        """Drop packed weights and captured sampler graphs.  Parameter changes are detected through
+        (data_ptr, _version); updates made through `p.data` (EMA swaps, some optimizers, manual weight surgery) bump
+        neither -- call this after such an update."""
+        self._exec.wc._c.clear()
+        tr = getattr(self._exec, '_trainer', None)
+        if tr is not None:
+            tr.wc._c.clear()
+        self.__dict__.pop('_sdb_samplers', None)
+
     def forward(self, x, timesteps=None, context=None, **kwargs):
         """x [N,C,h,w], timesteps [N] (int or fractional float), context [N,S,Dc] -> [N,C,h,w]."""
         if not x.is_cuda:

@@ -48,6 +48,7 @@ class UNetExecutor:
             off += 2 * m.attn2.to_k.weight.shape[0]
         self.kv_total = off
         self._gs_arena = None
+        self._gs_retired = []      # outgrown arenas: captured CUDA graphs keep zeroing / accumulating into them
         self._gs_off = 0
 
     # ------------------------------------------------------------------ GroupNorm partial-sum arena
@@ -55,6 +56,12 @@ class UNetExecutor:
         """Start of a forward: one memset clears every partial-sum buffer the epilogues will accumulate into."""
         need = B * 2 * 16384          # floats: sum over producing sites of C/4 * 2 (~11k) per sample
         if self._gs_arena is None or self._gs_arena.numel() < need or self._gs_arena.device != device:
+            # A sampler graph captured at a smaller batch has this arena's ADDRESS baked into its memset and epilogue
+            # atomics and stays cached by shape: the old block must never return to the caching allocator (a replay
+            # would zero / accumulate into whatever tensor owns it by then), so it is retired, not freed (33 MB at
+            # B = 256; growth events are rare).
+            if self._gs_arena is not None:
+                self._gs_retired.append(self._gs_arena)
             self._gs_arena = torch.zeros(need, dtype=torch.float32, device=device)
         else:
             self._gs_arena.zero_()

@@ -53,3 +53,21 @@ def sa_case(name):
     s0 = seeded((B, S, D), 22)
     gw = seeded((B, S, D), 23)
     return p, x, s0, gw, I
+
+
+def vq_mismatch(idx, z, codebook, dz):
+    """Nearest-code parity with near-tie accounting (same idea as argmax_mismatch).  idx: indices under test [P];
+    z: the reference pre-quantisation latents [P, C]; codebook [K, C]; dz: per-pixel (or scalar) bound on how far z may
+    legitimately move (the fp32 round-off of whatever produced z).  In fp64: a pixel whose distance to the bisector
+    plane between its best and second-best code, (d2^2 - d1^2) / (2 |e2 - e1|), is below dz is a near-tie -- round-off
+    decides it.  Returns (real, near, ref_idx): disagreements outside / inside near-ties."""
+    z = torch.as_tensor(z).double().cpu()
+    e = torch.as_tensor(codebook).double().cpu()
+    d = torch.cdist(z, e) ** 2
+    two = d.topk(2, dim=1, largest=False)
+    ref = two.indices[:, 0]
+    sep = (e[two.indices[:, 0]] - e[two.indices[:, 1]]).norm(dim=1).clamp_min(1e-300)
+    bis = (two.values[:, 1] - two.values[:, 0]) / (2 * sep)
+    bad = torch.as_tensor(idx).long().cpu().flatten() != ref
+    near = bis < torch.as_tensor(dz).double()
+    return int((bad & ~near).sum()), int((bad & near).sum()), ref

@@ -371,10 +371,18 @@ def test_dpm_glue(ops):
     x0, idx = ops.dpm_x0(x, eps, 0.8, 0.6, cb, want_idx=True)
     z = (x.cpu() - 0.6 * eps.cpu()) / 0.8
     zq, ridx = dpm_ref.vq_quantize(z, cb.cpu())
-    agree = (idx.cpu().view(B, 32, 32) == ridx).float().mean().item()
-    assert agree > 0.999                      # ties in fp32 distance may break differently
+    # index parity is exact outside fp64 near-ties (bisector distance below the fp32 round-off of z itself, 4 ulp)
+    from helpers import vq_mismatch
+    zf = z.permute(0, 2, 3, 1).reshape(-1, 3)
+    real, near, ref64 = vq_mismatch(idx, zf, cb, 4 * 1.2e-7 * zf.abs().amax(1).clamp_min(1.0))
+    assert real == 0, (real, near)
+    assert near <= 2
     same = (idx.cpu().view(B, 32, 32) == ridx)[:, None].expand_as(zq)
+    assert same.float().mean().item() > 0.999
     assert torch.equal(x0.cpu()[same], zq[same])
+    # the same bar applied to the reference's own fp32 argmin: it also only deviates from fp64 on near-ties
+    real_r, _, _ = vq_mismatch(ridx.flatten(), zf, cb, 4 * 1.2e-7 * zf.abs().amax(1).clamp_min(1.0))
+    assert real_r == 0
     x0n = ops.dpm_x0(x, eps, 0.8, 0.6, None)
     assert rel_l2(x0n, z) < 1e-6
     m0, m1 = rnd(B, 3, 32, 32, seed=44), rnd(B, 3, 32, 32, seed=45)

@@ -96,9 +96,87 @@ def test_unet_full_gradients_match_reference_golden():
     assert n > 0
 
 
+def test_video_recurrence_gradients_match_oracle():
+    """SAViDiffusion.encode (savi_diffusion.py:183-196) calls the SAME module once per frame before a single backward:
+    every call owns its gradient buffer (a module-level buffer returned the last frame's gradient T times)."""
+    from slotdiffusion_b200.slot_attention import SlotAttentionWMask
+    B, T, N, S, D, I = 2, 3, 96, 5, 192, 2
+    p = sa_ref.random_params(D, D, 2 * D, seed=11)
+    mod = SlotAttentionWMask(D, I, S, D, 2 * D).cuda().train()
+    mod.load_state_dict(p)
+    frames, s0, gw = seeded((B, T, N, D), 61), seeded((B, S, D), 62), seeded((B, T, S, D), 63)
+    wp = seeded((D, D), 64) * D ** -0.5                      # stand-in for the predictor: a linear map of the slots
+    fg, sg = frames.cuda().requires_grad_(True), s0.cuda().requires_grad_(True)
+    prev, outs = None, []
+    for t in range(T):
+        init = sg if prev is None else prev @ wp.cuda()
+        prev, mask = mod(fg[:, t], init)
+        outs.append(prev)
+    (torch.stack(outs, 1) * gw.cuda()).sum().backward()
+    p64 = {k: v.double().clone().requires_grad_(True) for k, v in p.items()}
+    f64, s64 = frames.double().requires_grad_(True), s0.double().requires_grad_(True)
+    ref, _ = sa_ref.slot_attention_video(p64, f64, s64, I, predictor=lambda s: s @ wp.double())
+    (ref * gw.double()).sum().backward()
+    assert rel_l2(torch.stack(outs, 1), ref) < 5e-5
+    assert rel_l2(fg.grad, f64.grad) < GTOL and rel_l2(sg.grad, s64.grad) < GTOL
+    for k, v in mod.named_parameters():
+        if p64[k].grad.norm().item() > 1e-9 * max(1.0, p64[k].norm().item()):
+            assert rel_l2(v.grad, p64[k].grad) < GTOL, k
+
+
+def test_unet_two_forwards_before_one_backward():
+    """two evaluations in one autograd graph (two loss terms / two timesteps): per-call gradient storage"""
+    cfg_over = dict(model_channels=64, channel_mult=(1, 2), attention_resolutions=(2,), num_res_blocks=1, context_dim=64)
+    net, sd, cfg = _unet(cfg_over)
+    xa, xb, ctx = seeded((2, 3, 16, 16), 41), seeded((2, 3, 16, 16), 44), seeded((2, 5, 64), 42)
+    ta, tb = torch.tensor([7, 503]), torch.tensor([950, 20])
+    gwa, gwb = seeded((2, 3, 16, 16), 43), seeded((2, 3, 16, 16), 45)
+    xag, xbg, cg = xa.cuda().requires_grad_(True), xb.cuda().requires_grad_(True), ctx.cuda().requires_grad_(True)
+    ya = net(xag, ta.cuda(), context=cg)
+    yb = net(xbg, tb.cuda(), context=cg)
+    ((ya * gwa.cuda()).sum() + (yb * gwb.cuda()).sum()).backward()
+    sdg = {k: v.double().clone().requires_grad_(True) for k, v in sd.items()}
+    xa64, xb64, c64 = xa.double().requires_grad_(True), xb.double().requires_grad_(True), ctx.double().requires_grad_(True)
+    ra, rb = unet_ref.unet_forward(sdg, xa64, ta, c64, cfg), unet_ref.unet_forward(sdg, xb64, tb, c64, cfg)
+    ((ra * gwa.double()).sum() + (rb * gwb.double()).sum()).backward()
+    assert rel_l2(xag.grad, xa64.grad) < GTOL and rel_l2(xbg.grad, xb64.grad) < GTOL and rel_l2(cg.grad, c64.grad) < GTOL
+    for k, v in net.named_parameters():
+        assert rel_l2(v.grad, sdg[k].grad) < GTOL, k
+
+
+def test_unet_dropout_backward_uses_the_forward_mask(monkeypatch):
+    """Model-level mask consistency: with the dropout seed stream pinned (same masks in every forward), the analytic
+    directional derivative of the train-mode loss equals its central finite difference.  A backward that regenerated a
+    DIFFERENT mask would be off by O(1).  (Keep rate and the 1/(1-p) scaling are checked at op level:
+    test_backward_ops_gpu.py::test_groupnorm_bwd with p = 0.1.)"""
+    import itertools
+    import slotdiffusion_b200.backward as bwd
+    cfg_over = dict(model_channels=64, channel_mult=(1, 2), attention_resolutions=(2,), num_res_blocks=1, context_dim=64)
+    net, sd, cfg = _unet(cfg_over, dropout=0.3, train=True)
+    x, ctx = seeded((4, 3, 16, 16), 41).cuda(), seeded((4, 5, 64), 42).cuda()
+    t = torch.tensor([7, 503, 999, 1]).cuda()
+    d = seeded((4, 5, 64), 47).cuda()
+    d = d / d.norm()
+
+    def loss_at(c):
+        monkeypatch.setattr(bwd, '_step_counter', itertools.count(1234))       # same seed -> same masks
+        return (net(x, t, context=c) * 0.37).square().mean()
+    cg = ctx.clone().requires_grad_(True)
+    loss_at(cg).backward()
+    analytic = (cg.grad * d).sum().item()
+    h = 2e-2
+    with torch.enable_grad():
+        lp = loss_at((ctx + h * d).requires_grad_(True)).item()
+        lm = loss_at((ctx - h * d).requires_grad_(True)).item()
+    fd = (lp - lm) / (2 * h)
+    assert abs(analytic) > 1e-6
+    assert abs(fd - analytic) / abs(analytic) < 3e-2, (fd, analytic)
+
+
 def test_unet_dropout_train_mode():
-    """nn.Dropout(p) in every ResBlock (unet.py:245-246) is active in train mode: output differs from eval, the mask
-    regenerated in backward matches the forward one (finite-difference check on a linear probe)."""
+    """nn.Dropout(p) in every ResBlock (unet.py:245-246) is active in train mode: finite output and gradients, and the
+    output differs from eval mode by a plausible amount (mask statistics: test_backward_ops_gpu.py, mask consistency
+    between forward and backward: test_unet_dropout_backward_uses_the_forward_mask)."""
     cfg_over = dict(model_channels=64, channel_mult=(1, 2), attention_resolutions=(2,), num_res_blocks=1, context_dim=64)
     net, sd, cfg = _unet(cfg_over, dropout=0.1, train=True)
     x, ctx = seeded((4, 3, 16, 16), 41).cuda(), seeded((4, 5, 64), 42).cuda().requires_grad_(True)
