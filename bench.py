@@ -9,8 +9,10 @@ DPM-Solver++ sampling loop of the slot-conditioned UNet (vq_denoised) on that ba
 metric = denoise sample-steps/s = (batch x 20 UNet evaluations) / time, whole job over all ranks.
 One process per GPU (torchrun), batch sharded across ranks, no data-path collective (weak scaling).
 
---impl reference: the CPU restatement of the reference (oracle/, torch fp32 on the host cores, all threads)
-on a bounded sample of the same workload; rank 0 only.
+--impl reference: the reference's own CPU path -- the UNMODIFIED reference from baseline/_ref (kind "reference"; falls
+back to the oracle port, kind "port", only if that copy is absent) on the host cores, all threads, on a bounded sample
+of the same workload; rank 0 only.
+gpu_baseline (N=1): the same unmodified reference, eager PyTorch ON THE SAME B200, same step and batch.
 """
 import argparse
 import json
@@ -187,6 +189,18 @@ def run_ours(args):
     roof = gemm_roofline(unet, sampler, B, dev)
     sa_stat = time_sa(sa, feats_d, slots0, load_peaks()[0])
 
+    gpu_base = None
+    if world == 1 and not args.no_gpu_baseline:
+        try:
+            gpu_base = gpu_baseline(dev, B)
+            gpu_base['speedup_vs_tf32_stock'] = (B * NFE * args.steps / (ms / 1e3)) / gpu_base['tf32_stock']['value'] \
+                if 'tf32_stock' in gpu_base else None
+            gpu_base['speedup_vs_tf32_all'] = (B * NFE * args.steps / (ms / 1e3)) / gpu_base['tf32_all']['value'] \
+                if 'tf32_all' in gpu_base else None
+        except Exception as e:                                         # noqa: BLE001
+            gpu_base = {'unavailable': repr(e)[:300]}
+            torch.cuda.empty_cache()
+
     train = None
     if not args.no_train:
         del feats_d, noise_d
@@ -228,6 +242,7 @@ def run_ours(args):
                          'how': 'all %d GEMM launches of one UNet evaluation replayed from a CUDA graph, CUDA events' % roof['launches']},
             'roofline_slot_attention': sa_stat['attend_kernel'],
             'cpu_baseline': cpu_baseline(sample_nfe=NFE, batch=4) if world == 1 else None,   # rank 0, N=1 only
+            'gpu_baseline': gpu_base,
             'train': train,
         }
         print(json.dumps(line))
@@ -564,16 +579,89 @@ def cpu_step(batch, nfe, seed=0, state={}):
 def cpu_baseline(sample_nfe, batch):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cpu_step(batch, 2)   # warm-up (weight generation, thread pool)
+    model = load_reference_model(torch.device('cpu')) if sample_nfe == NFE else None
+    if model is not None:              # the reference's own code on the host cores
+        g = torch.Generator().manual_seed(0)
+        feats = torch.randn(batch, N_TOK, D, generator=g)
+        slots0 = torch.randn(1, S, D, generator=g).expand(batch, -1, -1).contiguous()
+        with torch.no_grad():
+            model.slot_attention(feats, slots0)          # warm-up (thread pool)
+        fn, kind, what = (lambda: reference_step(model, feats, slots0, batch)), 'reference', \
+            'unmodified reference (baseline/_ref), torch CPU fp32'
+    else:
+        cpu_step(batch, 2)             # warm-up (weight generation, thread pool)
+        fn, kind, what = (lambda: cpu_step(batch, sample_nfe)), 'port', \
+            'oracle (torch CPU fp32 restatement of the reference)'
     runs, dt = 0, 0.0
     t0 = time.perf_counter()
     while dt < 10.0 and runs < 8:      # bounded sample: ~10-30 s of host work
-        cpu_step(batch, sample_nfe)
+        fn()
         runs += 1
         dt = time.perf_counter() - t0
-    return {'value': runs * batch * sample_nfe / dt, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-            'sample': f'oracle (torch CPU fp32 restatement of the reference): SlotAttention + {sample_nfe}-NFE '
-                      f'DPM-Solver++ at batch {batch}, {runs} run(s), {dt:.1f} s'}
+    return {'value': runs * batch * sample_nfe / dt, 'unit': UNIT, 'cores': cores, 'kind': kind,
+            'sample': f'{what}: SlotAttention + {sample_nfe}-NFE DPM-Solver++ at batch {batch}, {runs} run(s), {dt:.1f} s'}
+
+
+def load_reference_model(device):
+    """The UNMODIFIED reference SADiffusion (CLEVRTex config) from baseline/_ref (baseline/install_ref.sh; travels to the
+    GPU box) with tools/ref_stubs for its un-vendored imports, or None when that copy is absent."""
+    sys.path.insert(0, os.path.join(ROOT, 'tools'))
+    import ref_import
+    if not ref_import.box_copy_available():
+        return None
+    import contextlib
+    import io
+    import warnings
+    ref_import.use_box_copy()
+    torch.manual_seed(0)
+    with warnings.catch_warnings(), contextlib.redirect_stdout(io.StringIO()):
+        warnings.simplefilter('ignore')
+        model = ref_import.img_models().build_model(
+            ref_import.fresh_params('img_based', 'sa_ldm/sa_ldm_clevrtex_params-res128.py'))
+    with torch.no_grad():
+        for p in model.parameters():
+            if p.abs().max() == 0:
+                p.normal_(0, 0.02)
+    return model.to(device).eval()
+
+
+def reference_step(model, feats, slots0, batch):
+    """The same step through the reference's own code: SlotAttentionWMask.forward (sa_diffusion.py:15-70) and
+    dm_decoder.generate_imgs(use_dpm=True) (cond_ddpm.py:155-189: DPM-Solver++ singlestep order 3, 20 NFE, vq_denoised)."""
+    with torch.no_grad():
+        slots, _ = model.slot_attention(feats, slots0)
+        return model.dm_decoder.generate_imgs(cond=slots, batch_size=batch, use_dpm=True, verbose=False)
+
+
+def gpu_baseline(dev, batch):
+    """The honest bar: the reference's eager PyTorch path on THIS GPU, same step, same batch; PyTorch's stock
+    TF32 policy (cuDNN convolutions TF32, matmul fp32) and TF32 everywhere (the fastest setting a user can pick)."""
+    model = load_reference_model(dev)
+    if model is None:
+        return {'unavailable': 'baseline/_ref missing (run baseline/install_ref.sh in the build container)'}
+    g = torch.Generator().manual_seed(99)
+    feats = torch.randn(batch, N_TOK, D, generator=g).to(dev)
+    slots0 = torch.randn(1, S, D, generator=g).to(dev).expand(batch, -1, -1).contiguous()
+    out = {'what': 'unmodified reference (baseline/_ref), eager PyTorch %s on the same GPU: SlotAttentionWMask.forward + '
+                   'generate_imgs(use_dpm=True), batch %d, inputs resident, 1 warm-up + 2 timed steps' % (torch.__version__, batch),
+           'unit': UNIT}
+    saved = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    for name, mm, cd in (('tf32_stock', False, True), ('tf32_all', True, True)):
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = mm, cd
+        reference_step(model, feats, slots0, batch)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(2):
+            reference_step(model, feats, slots0, batch)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 2
+        out[name] = {'value': batch * NFE / (ms / 1e3), 'ms_per_step': ms}
+    torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = saved
+    del model
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_reference(args):
@@ -582,23 +670,44 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    batch = 4   # BASELINE configs[0]: the reference's CPU-runnable batch
+    batch = 4   # bounded sample of the workload (BASELINE configs[0]: the reference's CPU-runnable batch)
     steps = max(1, min(args.steps, 3))
     warm = 1 if args.warmup > 0 else 0
-    for _ in range(warm):
-        cpu_step(batch, 2)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        cpu_step(batch, NFE)
-    dt = time.perf_counter() - t0
+    model = load_reference_model(torch.device('cpu'))
+    kind = 'reference' if model is not None else 'port'
+    if model is not None:
+        g = torch.Generator().manual_seed(0)
+        feats = torch.randn(batch, N_TOK, D, generator=g)
+        slots0 = torch.randn(1, S, D, generator=g).expand(batch, -1, -1).contiguous()
+        dec = model.dm_decoder
+        if warm:      # one 2-evaluation pass: thread pool, allocator
+            with torch.no_grad():
+                model.slot_attention(feats, slots0)
+                dec.model.diffusion_model(torch.randn(batch, 3, 32, 32), torch.full((batch,), 500.), context=slots0)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            reference_step(model, feats, slots0, batch)
+        dt = time.perf_counter() - t0
+    else:
+        for _ in range(warm):
+            cpu_step(batch, 2)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            cpu_step(batch, NFE)
+        dt = time.perf_counter() - t0
     value = batch * NFE * steps / dt
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': steps,
         'warmup': warm, 'ms_per_step': dt / steps * 1e3, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'same workload through the CPU port of the reference (oracle/), batch %d, 20 NFE; '
-                               'steps bounded to %d so the run ends within minutes' % (batch, steps)},
-        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+        'config': {'workload': 'SlotDiffusion img LDM CLEVRTex 128x128: SlotAttention(3 it, 11 slots, 1024x192 features) + '
+                               'DPM-Solver++ 20 NFE UNet(134M) vq_denoised through %s on the host cores, bounded sample: '
+                               'batch %d per step, %d step(s) (the B200 arm runs the same step at per-GPU batch 256)'
+                               % ('the UNMODIFIED reference (baseline/_ref: SlotAttentionWMask.forward + '
+                                  'generate_imgs(use_dpm=True))' if kind == 'reference'
+                                  else 'the CPU port of the reference (oracle/)', batch, steps),
+                   'per_gpu_batch': batch, 'nfe': NFE, 'num_slots': S, 'same_workload_smaller_batch': True},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': kind,
                          'sample': f'{steps} step(s) of batch {batch} x {NFE} NFE'},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
@@ -615,6 +724,7 @@ def main():
     ap.add_argument('--train-steps', type=int, default=5)
     ap.add_argument('--no-train', action='store_true', help='skip the training-step measurement')
     ap.add_argument('--no-train-graph', action='store_true', help='time the eager training step (no CUDA graph)')
+    ap.add_argument('--no-gpu-baseline', action='store_true', help='skip timing the unmodified reference on the same GPU')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--profile-train-once', action='store_true', help='ncu helper: one eager training step')
     ap.add_argument('--profile-once', action='store_true',

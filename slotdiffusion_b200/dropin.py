@@ -59,8 +59,10 @@ class _ModelFn:
         self.unconditional_condition = unconditional_condition
         self.model_kwargs = model_kwargs
 
-    def __call__(self, x, t):
-        return self.fn(x, t)
+    def __call__(self, *args, **kwargs):
+        # the reference closure is model_fn(x, t_continuous=None, quantize=False) (dpm_solver.py:386-392): the reference
+        # loop calls it as model(x0, None, quantize=True) when vq_denoised (dpm_solver.py:532-533)
+        return self.fn(*args, **kwargs)
 
 
 def _make_adapters(ref_dpm):

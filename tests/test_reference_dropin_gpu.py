@@ -1,0 +1,174 @@
+"""The UNMODIFIED reference model on the B200, stock and with the B200 hot path dropped in.
+
+baseline/_ref holds the reference's python tree (baseline/install_ref.sh); tools/ref_stubs supplies its un-vendored
+imports.  The reference's own build_model() constructs SADiffusion (CLEVRTex config) twice -- once as shipped, once after
+slotdiffusion_b200.dropin.install() -- with the same weights and the same CUDA RNG seed, and runs the reference's own
+forward -> calc_train_loss -> backward and dm_decoder.generate_imgs(use_dpm=True).  Everything outside the two hot
+modules (ResNet encoder, VQ-VAE, q_sample, loss, sampler call site) is the reference's eager PyTorch in BOTH runs, so the
+difference isolates the drop-in.  Tolerances: 1e-3 relative (north_star); TF32 is switched off for the stock run so the
+bar is the reference's fp32 arithmetic."""
+import os
+import sys
+import warnings
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, 'tools'))
+import ref_import  # noqa: E402
+
+from helpers import rel_l2  # noqa: E402
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900),
+              pytest.mark.skipif(not ref_import.box_copy_available(),
+                                 reason='baseline/_ref missing: run baseline/install_ref.sh in the build container')]
+CFG = ('img_based', 'sa_ldm/sa_ldm_clevrtex_params-res128.py')
+VCFG = ('video_based', 'savi_ldm/savi_ldm_movid_params-res128.py')
+
+
+def _build(task, rel, dropout=0.0):
+    ref_import.use_box_copy()
+    mods = ref_import.img_models() if task == 'img_based' else ref_import.video_models()
+    params = ref_import.fresh_params(task, rel)
+    params.unet_dict['dropout'] = dropout            # mask streams differ (torch Philox vs counter-based): parity with p = 0
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        return mods.build_model(params)
+
+
+def _nonzero_init(model, seed=5):
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for p in model.parameters():
+            if p.abs().max() == 0:                   # zero_module convs: make every path contribute
+                p.copy_(torch.randn(p.shape, generator=g) * 0.02)
+
+
+@pytest.fixture
+def dropin():
+    from slotdiffusion_b200 import dropin as d
+    d.uninstall()
+    yield d
+    d.uninstall()
+
+
+def _train_pass(model, img, seed):
+    model.train()
+    model.zero_grad(set_to_none=True)
+    torch.manual_seed(seed)                          # t ~ randint and eps ~ randn_like come from the CUDA generator
+    data = {'img': img}
+    out = model(data)
+    loss = model.calc_train_loss(data, out)['denoise_loss']
+    loss.backward()
+    return out, loss.detach(), {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+
+
+def test_reference_sadiffusion_stock_vs_dropin_train_and_sample(dropin):
+    from slotdiffusion_b200.slot_attention import SlotAttentionWMask
+    from slotdiffusion_b200.unet import UNetModel
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    dev = torch.device('cuda')
+    B = 4
+    ref_model = _build(*CFG)
+    _nonzero_init(ref_model)
+    ref_model = ref_model.to(dev)
+    img = torch.randn(B, 3, 128, 128, generator=torch.Generator().manual_seed(7)).clamp(-1, 1).to(dev)
+    out_r, loss_r, g_r = _train_pass(ref_model, img, 123)
+
+    dropin.install()
+    new_model = _build(*CFG)
+    assert type(new_model.slot_attention) is SlotAttentionWMask
+    assert type(new_model.dm_decoder.model.diffusion_model) is UNetModel
+    new_model.load_state_dict(ref_model.state_dict(), strict=True)
+    new_model = new_model.to(dev)
+    out_n, loss_n, g_n = _train_pass(new_model, img, 123)
+
+    # ---- forward: slots, masks, loss
+    assert rel_l2(out_n['slots'], out_r['slots']) < 1e-3
+    assert rel_l2(out_n['masks'], out_r['masks']) < 1e-3
+    assert out_n['masks'].shape == out_r['masks'].shape and not out_n['masks'].requires_grad
+    assert abs(loss_n.item() - loss_r.item()) / abs(loss_r.item()) < 1e-3, (loss_n.item(), loss_r.item())
+    # ---- backward: every parameter of the whole model (encoder, init_latents, Slot Attention, UNet), 1e-3 relative
+    assert set(g_n) == set(g_r)
+    worst = ('', 0.0)
+    tot_d = tot_r = 0.0
+    for k, r in g_r.items():
+        d = (g_n[k].double() - r.double()).norm().item()
+        tot_d += d * d
+        tot_r += r.double().norm().item() ** 2
+        if r.norm().item() > 1e-7 * max(1.0, float(r.numel()) ** 0.5):
+            e = d / r.double().norm().item()
+            worst = max(worst, (k, e), key=lambda t: t[1])
+    print('loss', loss_r.item(), loss_n.item(), 'global grad rel', (tot_d / tot_r) ** 0.5, 'worst parameter', worst)
+    assert (tot_d / tot_r) ** 0.5 < 1e-3
+    assert worst[1] < 5e-3, worst
+
+    # ---- sampling through the reference's call site (cond_ddpm.py:155-189), eval mode
+    ref_model.eval()
+    new_model.eval()
+    with torch.no_grad():
+        slots = ref_model({'img': img})['slots']
+        masks_r = ref_model({'img': img})['masks']
+        masks_n = new_model({'img': img})['masks']               # eval: masks upsampled to the image resolution (:172-180)
+        assert masks_r.shape == (B, 11, 128, 128) and rel_l2(masks_n, masks_r) < 1e-3
+        for vq in (False, True):
+            ref_model.dm_decoder.vq_denoised = new_model.dm_decoder.vq_denoised = vq
+            # generate_imgs looks the sampler classes up in its module globals at CALL time: the stock run must see the
+            # reference's own DPM_Solver, the drop-in run the patched one
+            dropin.uninstall()
+            torch.manual_seed(77)
+            y_r = ref_model.dm_decoder.generate_imgs(cond=slots, batch_size=B, use_dpm=True, verbose=False)
+            dropin.install()
+            torch.manual_seed(77)
+            y_n = new_model.dm_decoder.generate_imgs(cond=slots, batch_size=B, use_dpm=True, verbose=False)
+            assert y_n.shape == y_r.shape == (B, 3, 32, 32)
+            if not vq:
+                assert rel_l2(y_n, y_r) < 1e-3, rel_l2(y_n, y_r)
+            else:       # free-running with a discrete step: statistical (teacher-forced exactness: test_modules_gpu.py)
+                diff = (y_n - y_r).abs().amax(1)
+                assert (diff > 1e-3).float().mean().item() < 0.05
+        # the B200 sampler (one captured graph) was used, not the reference loop
+        assert getattr(new_model.dm_decoder.model.diffusion_model, '_sdb_samplers', None)
+        # a request outside the B200 plan runs the REFERENCE loop around the B200 UNet -- including its vq_denoised call
+        # model(x0, None, quantize=True) (dpm_solver.py:532-533), which the adapter must pass through
+        from slotdiffusion.img_based.models.ddpm import cond_ddpm
+        dec = new_model.dm_decoder
+        dec.model.vae = dec.vae
+        ns = cond_ddpm.NoiseScheduleVP(betas=dec.betas)
+        fn = cond_ddpm.model_wrapper(model=dec.model, noise_schedule=ns, model_type='noise',
+                                     guidance_type='classifier-free', condition=slots)
+        solver = cond_ddpm.DPM_Solver(fn, ns, algorithm_type='dpmsolver++', correcting_x0_fn=False, vq_denoised=True)
+        with pytest.warns(UserWarning, match='outside the B200 plan'):
+            y_f = solver.sample(torch.randn(B, 3, 32, 32, device=dev), steps=4, order=2, method='multistep')
+        dec.model.vae = None
+        assert y_f.shape == (B, 3, 32, 32) and torch.isfinite(y_f).all()
+
+
+def test_reference_savidiffusion_video_train_step_stock_vs_dropin(dropin):
+    """configs[2] shape: SAViDiffusion (MOVi-D config), T frames per clip, the module called once per frame before ONE
+    backward (per-call gradient buffers) -- the reference's own encode / predictor / loss code around the drop-in."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    dev = torch.device('cuda')
+    B, T = 2, 3
+    ref_model = _build(*VCFG)
+    _nonzero_init(ref_model)
+    ref_model = ref_model.to(dev)
+    img = torch.randn(B, T, 3, 128, 128, generator=torch.Generator().manual_seed(9)).clamp(-1, 1).to(dev)
+    out_r, loss_r, g_r = _train_pass(ref_model, img, 321)
+    dropin.install()
+    new_model = _build(*VCFG)
+    new_model.load_state_dict(ref_model.state_dict(), strict=True)
+    new_model = new_model.to(dev)
+    out_n, loss_n, g_n = _train_pass(new_model, img, 321)
+    assert rel_l2(out_n['slots'], out_r['slots']) < 1e-3
+    assert abs(loss_n.item() - loss_r.item()) / abs(loss_r.item()) < 1e-3
+    tot_d = sum((g_n[k].double() - r.double()).norm().item() ** 2 for k, r in g_r.items())
+    tot_r = sum(r.double().norm().item() ** 2 for r in g_r.values())
+    sa_d = sum((g_n[k].double() - r.double()).norm().item() ** 2 for k, r in g_r.items() if k.startswith('slot_attention.'))
+    sa_r = sum(r.double().norm().item() ** 2 for k, r in g_r.items() if k.startswith('slot_attention.'))
+    print('video: global grad rel', (tot_d / tot_r) ** 0.5, 'slot_attention grad rel', (sa_d / sa_r) ** 0.5)
+    assert (tot_d / tot_r) ** 0.5 < 1e-3
+    assert (sa_d / sa_r) ** 0.5 < 1e-3

@@ -7,7 +7,7 @@ import torch
 from helpers import SA_CASES, argmax_mismatch, golden, rel_l2, sa_case, seeded
 from oracle import slot_attention_ref as sa_ref
 
-pytestmark = [pytest.mark.gpu_next, pytest.mark.timeout(300)]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
 TIGHT = 5e-5
 
 

@@ -1,8 +1,8 @@
-"""Import the reference (Wuziyi616/SlotDiffusion) in the build container.
+"""Import the UNMODIFIED reference (Wuziyi616/SlotDiffusion) with stubs for its un-vendored dependencies.
 
-Only tools/make_golden.py and ad-hoc probes use this.  /root/reference does not
-exist on the GPU box, so nothing under tests/, bench.py or the product imports
-this file.  Recipe follows SURVEY.md Appendix B.
+Users: tools/make_golden.py (build container, /root/reference), and -- through the copy under baseline/_ref that
+travels to the GPU box -- tests/test_reference_dropin_gpu.py, tools/ref_gpu_bar.py and bench.py's reference /
+gpu_baseline legs.  The product never imports this file.  Recipe follows SURVEY.md Appendix B.
 """
 import importlib
 import os
@@ -10,8 +10,30 @@ import sys
 import types
 import warnings
 
-REF_ROOT = os.environ.get('SDB_REFERENCE_ROOT', '/root/reference')
 STUBS = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'ref_stubs')
+_BOX_COPY = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'baseline', '_ref')
+
+
+def _find_root():
+    """/root/reference in the build container; on the GPU box only baseline/_ref exists (the unmodified python tree put
+    there by baseline/install_ref.sh: git-ignored, travels with the gpurun snapshot)."""
+    for c in (os.environ.get('SDB_REFERENCE_ROOT'), '/root/reference', _BOX_COPY):
+        if c and os.path.isdir(os.path.join(c, 'slotdiffusion')):
+            return c
+    return '/root/reference'
+
+
+REF_ROOT = _find_root()
+
+
+def box_copy_available():
+    return os.path.isdir(os.path.join(_BOX_COPY, 'slotdiffusion'))
+
+
+def use_box_copy():
+    """Point this module at baseline/_ref (what the -m gpu tests and bench.py use: nothing there may read /root/reference)."""
+    global REF_ROOT
+    REF_ROOT = _BOX_COPY
 
 
 def setup():
@@ -43,6 +65,14 @@ def load_params(task, cfg_relpath):
     mod = importlib.import_module(f[:-3])
     sys.path.pop(0)
     return mod.SlotAttentionParams()
+
+
+def fresh_params(task, cfg_relpath):
+    """A params object from a FRESH class: build_model() pops entries from the class-level dicts, so every build needs
+    its own copy of the config module."""
+    import runpy
+    setup()
+    return runpy.run_path(os.path.join(REF_ROOT, 'slotdiffusion', task, 'configs', cfg_relpath))['SlotAttentionParams']()
 
 
 def img_models():
