@@ -1,4 +1,5 @@
-"""bench.py contract checks that run without a GPU: the reference arm (the reference's CPU path = the oracle port) prints
+"""bench.py contract checks that run without a GPU: the reference arm (the reference's CPU path: the unmodified reference
+from baseline/_ref when that copy is present -- kind "reference" -- else the oracle port) prints
 ONE JSON line with the agreed keys, and the product arm refuses to run without CUDA instead of falling back."""
 import json
 import os
@@ -23,7 +24,9 @@ def test_reference_arm_json_line():
               'vs_baseline', 'dtype', 'data', 'config', 'cpu_baseline', 'e2e'):
         assert k in d, k
     assert d['metric'] == 'dpm_solver_denoise_steps_per_sec' and d['unit'] == 'sample-steps/s'
-    assert d['value'] > 0 and d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
+    have_ref = os.path.isdir(os.path.join(ROOT, 'baseline', '_ref', 'slotdiffusion'))
+    assert d['value'] > 0 and d['cpu_baseline']['kind'] == ('reference' if have_ref else 'port')
+    assert d['cpu_baseline']['cores'] >= 1 and d['config']['per_gpu_batch'] == 4
     assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['d2h_bytes_per_step'] == 0
     assert d['vs_baseline'] is None
 
