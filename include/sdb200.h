@@ -15,6 +15,11 @@
  *   - "packed" = GEMM operand format: 16-bit [2][rows][K], plane 0 = hi = fp16(x), plane 1 = lo =
  *     fp16(x - hi) (gradient operands of the backward pass use the same layout with bf16, see SdbGemm.a_bf16).  hi*hi + hi*lo + lo*hi on the fp16 tensor pipe with fp32 accumulation
  *     reproduces an fp32 product to ~2^-22 (DESIGN.md "precision").
+ *     SDB_FMT_F8C ("fp8-corrected", inference): the bytes of plane 1 hold two e4m3 half-planes instead,
+ *     [rows][K] h8 = e4m3(hi * 2^eh) then [rows][K] l8 = e4m3(lo * 2^el); a product is then one fp16 pass hi*hi
+ *     plus the two correction products l8*h8' + h8*l8' on the fp8 pipe (twice the fp16 rate) in a second
+ *     accumulator: C = D1 + 2^-s D2 -- two pass-equivalents instead of three.  Activations use static exponents
+ *     (eh = 2, el = 12), weights a per-tensor exponent given to the sdb_pack_weight*_fmt calls.
  */
 #ifndef SDB200_H_
 #define SDB200_H_
@@ -24,6 +29,9 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+
+#define SDB_FMT_F16X2 0 /* plane 1 = fp16 lo plane */
+#define SDB_FMT_F8C 2   /* plane 1 = e4m3(hi) | e4m3(lo) half-planes */
 
 #define SDB_OK 0
 #define SDB_ERR_INVALID 1 /* bad shape / alignment / argument */
@@ -71,7 +79,8 @@ typedef struct SdbGemm {
   int32_t mode;
   int32_t B, H, W, C;     /* conv geometry (modes 1,2) */
   int32_t rows_per_group; /* H*W for rowvec */
-  int32_t passes;         /* 3 = hi*hi + lo*hi + hi*lo (fp32-faithful), 1 = hi*hi only */
+  int32_t passes;         /* 3 = hi*hi + lo*hi + hi*lo (fp32-faithful), 1 = hi*hi only, 2 = both operands are SDB_FMT_F8C:
+                             hi*hi (kind::f16) + corr_scale * (l8*h8' + h8*l8') (kind::f8f6f4, second accumulator) */
   int32_t relu;           /* apply max(.,0) to the result (slot-attention MLP, slot_attention.py:51) */
   void* out_packed;       /* optional: also emit act(result) as a packed operand [2][M][N] for the next GEMM (c may then be NULL) */
   float* gsum;            /* optional: atomically accumulate GroupNorm partial sums [M / rows_per_group][N / 4][2] = (sum, sum of
@@ -83,6 +92,8 @@ typedef struct SdbGemm {
   int32_t a_bf16, w_bf16; /* the planes of A / W hold a BF16 hi/lo split (gradient operands from sdb_grad_pack /
                              sdb_pack_zero_up2: fp32 exponent range, ~16 mantissa bits) instead of the FP16 split.
                              tcgen05 kind::f16 takes ONE input format: a_bf16 must equal w_bf16 */
+  float corr_scale;       /* passes == 2: 2^-s with s = el(A) + eh(W) = eh(A) + el(W) (= 12 + wexp of the packed weight) */
+  int32_t reserved0;
 } SdbGemm;
 
 int sdb_gemm(const SdbGemm* p, void* stream);
@@ -92,6 +103,15 @@ int sdb_gemm(const SdbGemm* p, void* stream);
 int sdb_pack_weight(const float* w, void* out, int64_t N, int64_t K, void* stream);
 /* W [Cout,Cin,3,3] -> packed [2][Cout][9*Cin], k = (ky*3+kx)*Cin + c */
 int sdb_pack_weight_conv3(const float* w, void* out, int64_t Cout, int64_t Cin, void* stream);
+
+/* the same with an explicit operand format: fmt SDB_FMT_F16X2 (wexp ignored) or SDB_FMT_F8C with h8 = e4m3(hi * 2^wexp),
+ * l8 = e4m3(lo * 2^(wexp+10)); the caller picks wexp = floor(log2(448 / max|w|)) per tensor */
+int sdb_pack_weight_fmt(const float* w, void* out, int64_t N, int64_t K, int fmt, int wexp, void* stream);
+int sdb_pack_weight_conv3_fmt(const float* w, void* out, int64_t Cout, int64_t Cin, int fmt, int wexp, void* stream);
+/* Format written by every ACTIVATION operand producer (sdb_pack_rows, sdb_layernorm_pack, sdb_groupnorm_apply_pack*,
+ * sdb_pack_nhwc, sdb_geglu_pack, the packed epilogues of sdb_gemm, ...) from this point of `stream` on: a one-thread kernel
+ * flips a device flag, so the switch is stream-ordered and CUDA-graph capturable.  Default SDB_FMT_F16X2. */
+int sdb_set_pack_mode(int fmt, void* stream);
 
 /* rows x [M,K] (ldx) -> packed [2][M][K]; act: 0 none, 1 SiLU (unet.py:237-238), 2 ReLU */
 int sdb_pack_rows(const float* x, int64_t ldx, void* out, int64_t M, int64_t K, int act, void* stream);

@@ -22,7 +22,7 @@ class SdbGemm(Structure):
         ('M', c_int32), ('N', c_int32), ('K', c_int32), ('mode', c_int32), ('B', c_int32), ('H', c_int32),
         ('W', c_int32), ('C', c_int32), ('rows_per_group', c_int32), ('passes', c_int32), ('relu', c_int32),
         ('out_packed', c_void_p), ('gsum', c_void_p), ('out_plane_stride', c_int64), ('out_act', c_int32),
-        ('geglu', c_int32), ('a_bf16', c_int32), ('w_bf16', c_int32),
+        ('geglu', c_int32), ('a_bf16', c_int32), ('w_bf16', c_int32), ('corr_scale', c_float), ('reserved0', c_int32),
     ]
 
 
@@ -42,6 +42,9 @@ SIGNATURES = {
     'sdb_gemm': (c_int, [POINTER(SdbGemm), c_void_p]),
     'sdb_gemm_timing': (c_int, [c_void_p, c_int]),
     'sdb_pack_weight': (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
+    'sdb_pack_weight_fmt': (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p]),
+    'sdb_pack_weight_conv3_fmt': (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p]),
+    'sdb_set_pack_mode': (c_int, [c_int, c_void_p]),
     'sdb_pack_weight_conv3': (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     'sdb_pack_rows': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_void_p]),
     'sdb_layernorm_pack': (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int64, c_int64,

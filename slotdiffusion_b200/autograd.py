@@ -135,5 +135,6 @@ def slot_attention_apply(mod, inputs, slots, want_mask):
         from .backward import SlotAttentionFn
         out = SlotAttentionFn.apply(mod, want_mask, inputs, slots, *params)
         return out[0], (out[1] if want_mask else None)
-    with torch.no_grad():
+    # always the fp32-faithful three-pass operand format (bit-exact argmax masks), whatever scope the caller is in
+    with torch.no_grad(), ops.pack_format(ops.SDB_FMT_F16X2):
         return slot_attention_forward(mod, inputs, slots, want_mask)

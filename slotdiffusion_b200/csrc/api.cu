@@ -42,3 +42,13 @@ int num_sms() {
 extern "C" int sdb_version(void) { return 1; }
 extern "C" const char* sdb_last_error(void) { return sdb::g_err; }
 extern "C" int64_t sdb_launch_count(void) { return sdb::g_launches.load(); }
+
+extern "C" int sdb_set_pack_mode(int fmt, void* stream) {
+  SDB_REQUIRE(fmt == SDB_FMT_F16X2 || fmt == SDB_FMT_F8C, "sdb_set_pack_mode: bad format %d", fmt);
+  // one flag per translation unit that writes packed operands (no relocatable device code)
+  int rc = sdb::set_pack_mode_elementwise(fmt, sdb::as_stream(stream));
+  if (!rc) rc = sdb::set_pack_mode_gemm(fmt, sdb::as_stream(stream));
+  if (!rc) rc = sdb::set_pack_mode_attention(fmt, sdb::as_stream(stream));
+  if (!rc) rc = sdb::set_pack_mode_attention_tc(fmt, sdb::as_stream(stream));
+  return rc;
+}

@@ -7,6 +7,8 @@
 
 namespace sdb {
 
+SDB_DEFINE_PACK_MODE_SETTER(set_pack_mode_attention)
+
 constexpr int ATT_THREADS = 64;
 constexpr int ATT_KV_TILE = 64;
 
@@ -96,13 +98,8 @@ attention_pack_kernel(const float* __restrict__ q, int64_t ldq, const float* __r
     const float inv = 1.f / lrun;
     const int64_t o = (b * Lq + row) * C + h * D;
 #pragma unroll
-    for (int i = 0; i < D; i += 2) {
-      __half h0, l0, h1, l1;
-      split_f16(acc[i] * inv, h0, l0);
-      split_f16(acc[i + 1] * inv, h1, l1);
-      *reinterpret_cast<__half2*>(out + o + i) = __halves2half2(h0, h1);
-      *reinterpret_cast<__half2*>(out + plane + o + i) = __halves2half2(l0, l1);
-    }
+    for (int i = 0; i < D; i += 4)     // operand format of the consumer GEMM follows the stream-ordered pack mode (common.cuh)
+      store_split4(out, out + plane, o + i, make_float4(acc[i] * inv, acc[i + 1] * inv, acc[i + 2] * inv, acc[i + 3] * inv));
   }
 }
 

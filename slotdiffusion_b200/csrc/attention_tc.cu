@@ -21,6 +21,8 @@
 
 namespace sdb {
 
+SDB_DEFINE_PACK_MODE_SETTER(set_pack_mode_attention_tc)
+
 constexpr int AT_THREADS = 128;
 constexpr int AT_M = 128;        // queries per CTA
 constexpr int AT_KC = 64;        // keys per chunk
@@ -290,13 +292,19 @@ attention_tc_kernel(const float* __restrict__ q, int64_t ldq, const float* __res
       const int h = G == 1 ? (int)blockIdx.y : pi - (int)b * heads;
       const float inv = 1.f / lrun;
       const int64_t ob = (b * Lq + lr) * C + h * AT_D;
+      if (g_pack_mode == SDB_FMT_F8C) {     // operand format of the consumer GEMM (to_out projection), common.cuh
 #pragma unroll
-      for (int i = 0; i < AT_D; i += 8) {
-        uint4 hi, lo;
-        split8(make_float4(o[i] * inv, o[i + 1] * inv, o[i + 2] * inv, o[i + 3] * inv),
-               make_float4(o[i + 4] * inv, o[i + 5] * inv, o[i + 6] * inv, o[i + 7] * inv), hi, lo);
-        *reinterpret_cast<uint4*>(out + ob + i) = hi;
-        *reinterpret_cast<uint4*>(out + plane + ob + i) = lo;
+        for (int i = 0; i < AT_D; i += 4)
+          store_split4(out, out + plane, ob + i, make_float4(o[i] * inv, o[i + 1] * inv, o[i + 2] * inv, o[i + 3] * inv));
+      } else {
+#pragma unroll
+        for (int i = 0; i < AT_D; i += 8) {
+          uint4 hi, lo;
+          split8(make_float4(o[i] * inv, o[i + 1] * inv, o[i + 2] * inv, o[i + 3] * inv),
+                 make_float4(o[i + 4] * inv, o[i + 5] * inv, o[i + 6] * inv, o[i + 7] * inv), hi, lo);
+          *reinterpret_cast<uint4*>(out + ob + i) = hi;
+          *reinterpret_cast<uint4*>(out + plane + ob + i) = lo;
+        }
       }
     }
   }

@@ -3,6 +3,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -52,13 +53,78 @@ __device__ __forceinline__ void split_f16x2(float a, float b, uint32_t& hi, uint
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
+// ---- operand format of the second plane (sdb200.h "packed") ----
+//   SDB_FMT_F16X2 (0): fp16 lo plane -- three kind::f16 passes per product (hi*hi + lo*hi + hi*lo)
+//   SDB_FMT_F8C   (2): the SAME bytes hold two e4m3 half-planes, h8 = e4m3(hi * 2^eh) then l8 = e4m3(lo * 2^el): one
+//                      kind::f16 pass (hi*hi) plus two kind::f8f6f4 correction products (l8*h8' + h8*l8') in a second
+//                      accumulator = 2 pass-equivalents.  Activations use the static exponents below; weights a
+//                      per-tensor exponent chosen at pack time.
+// The format the operand PRODUCERS write is a stream-ordered device flag (one copy per translation unit: the library is
+// built without relocatable device code), flipped by sdb_set_pack_mode() -- a 1-thread kernel, so it is CUDA-graph
+// capturable and ordered with the producers on the same stream.
+static __device__ int g_pack_mode = 0;
+constexpr int F8_ACT_HI_EXP = 2;     // |x| < 112 before the e4m3 copy of hi saturates (448 / 4)
+constexpr int F8_ACT_LO_EXP = 12;    // lo = x - fp16(x) <= 2^-12 |x|
+
+__device__ __forceinline__ uint32_t e4m3x4(float a, float b, float c, float d) {
+  const uint32_t p0 = __nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E4M3);   // low byte = a
+  const uint32_t p1 = __nv_cvt_float2_to_fp8x2(make_float2(c, d), __NV_SATFINITE, __NV_E4M3);
+  return p0 | (p1 << 16);
+}
+
+// fp16 hi plane + two e4m3 half-planes in place of the lo plane; `lo - hi` is the plane size in elements (= bytes of one
+// e4m3 half-plane), sh / sl = 2^eh / 2^el
+__device__ __forceinline__ void store_split4_f8(__half* hi, __half* lo, long long idx, float4 v, float sh, float sl) {
+  v.x = fminf(fmaxf(v.x, -65504.f), 65504.f); v.y = fminf(fmaxf(v.y, -65504.f), 65504.f);
+  v.z = fminf(fmaxf(v.z, -65504.f), 65504.f); v.w = fminf(fmaxf(v.w, -65504.f), 65504.f);
+  const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+  const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+  uint2 ph;
+  ph.x = *reinterpret_cast<const uint32_t*>(&h0);
+  ph.y = *reinterpret_cast<const uint32_t*>(&h1);
+  *reinterpret_cast<uint2*>(hi + idx) = ph;
+  uint8_t* p8 = reinterpret_cast<uint8_t*>(lo);
+  const long long plane = lo - hi;
+  *reinterpret_cast<uint32_t*>(p8 + idx) = e4m3x4(f0.x * sh, f0.y * sh, f1.x * sh, f1.y * sh);
+  *reinterpret_cast<uint32_t*>(p8 + plane + idx) =
+      e4m3x4((v.x - f0.x) * sl, (v.y - f0.y) * sl, (v.z - f1.x) * sl, (v.w - f1.y) * sl);
+}
+
 __device__ __forceinline__ void store_split4(__half* hi, __half* lo, long long idx, float4 v) {
+  if (g_pack_mode == SDB_FMT_F8C) {
+    store_split4_f8(hi, lo, idx, v, float(1 << F8_ACT_HI_EXP), float(1 << F8_ACT_LO_EXP));
+    return;
+  }
   uint2 ph, pl;
   split_f16x2(v.x, v.y, ph.x, pl.x);
   split_f16x2(v.z, v.w, ph.y, pl.y);
   *reinterpret_cast<uint2*>(hi + idx) = ph;
   *reinterpret_cast<uint2*>(lo + idx) = pl;
 }
+
+// weights: fmt / exponent are explicit arguments of the pack calls (wexp: e4m3(hi * 2^wexp), e4m3(lo * 2^(wexp+10)))
+__device__ __forceinline__ void store_split4_w(__half* hi, __half* lo, long long idx, float4 v, int fmt, int wexp) {
+  if (fmt == SDB_FMT_F8C) {
+    store_split4_f8(hi, lo, idx, v, exp2f((float)wexp), exp2f((float)(wexp + 10)));
+    return;
+  }
+  uint2 ph, pl;
+  split_f16x2(v.x, v.y, ph.x, pl.x);
+  split_f16x2(v.z, v.w, ph.y, pl.y);
+  *reinterpret_cast<uint2*>(hi + idx) = ph;
+  *reinterpret_cast<uint2*>(lo + idx) = pl;
+}
+
+#define SDB_DEFINE_PACK_MODE_SETTER(name)                                         \
+  __global__ void name##_kernel(int m) { g_pack_mode = m; }                        \
+  int name(int m, cudaStream_t st) {                                              \
+    name##_kernel<<<1, 1, 0, st>>>(m);                                            \
+    return check_cuda(cudaGetLastError(), #name);                                 \
+  }
+int set_pack_mode_elementwise(int m, cudaStream_t st);
+int set_pack_mode_gemm(int m, cudaStream_t st);
+int set_pack_mode_attention(int m, cudaStream_t st);
+int set_pack_mode_attention_tc(int m, cudaStream_t st);
 
 // Gradient operands: bf16 hi/lo split (x ~= hi + lo, ~16 mantissa bits, fp32 exponent range).  Loss gradients are
 // routinely 1e-6 and smaller, far inside fp16's subnormal range where the fp16 split would keep only a few bits.

@@ -13,10 +13,26 @@ static inline int grid_for(int64_t work_items, int threads, int max_waves = 8) {
 }
 
 // ------------------------------------------------------------------ weights
-__global__ void pack_weight_kernel(const float* __restrict__ w, __half* __restrict__ out, int64_t n4, int64_t plane) {
+SDB_DEFINE_PACK_MODE_SETTER(set_pack_mode_elementwise)
+
+__global__ void pack_weight_kernel(const float* __restrict__ w, __half* __restrict__ out, int64_t n4, int64_t plane,
+                                   int fmt, int wexp) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 v = reinterpret_cast<const float4*>(w)[i];
-    store_split4(out, out + plane, i * 4, v);
+    store_split4_w(out, out + plane, i * 4, v, fmt, wexp);
+  }
+}
+
+// [Cout][Cin][3][3] -> [Cout][tap][Cin], four input channels per thread (SDB_FMT_F8C needs 4-byte e4m3 stores)
+__global__ void pack_weight_conv3_v4_kernel(const float* __restrict__ w, __half* __restrict__ out, int64_t Cout,
+                                            int64_t Cin, int fmt, int wexp) {
+  const int64_t c4n = Cin / 4, total4 = Cout * 9 * c4n, plane = Cout * 9 * Cin;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t c = (i % c4n) * 4;
+    const int64_t tap = (i / c4n) % 9;
+    const int64_t o = i / (9 * c4n);
+    const float* src = w + (o * Cin + c) * 9 + tap;
+    store_split4_w(out, out + plane, (o * 9 + tap) * Cin + c, make_float4(src[0], src[9], src[18], src[27]), fmt, wexp);
   }
 }
 
@@ -413,18 +429,22 @@ __global__ void timestep_embedding_pack_kernel(const float* __restrict__ t, __ha
                                                int dim) {
   const int half = dim / 2;
   const int64_t total = B * dim;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+  // four consecutive columns per thread (dim % 8 == 0: a group never straddles the cos | sin halves), written in the
+  // operand format of the current pack mode (common.cuh)
+  for (int64_t i4 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i4 < total / 4; i4 += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = i4 * 4;
     const int64_t b = i / dim;
     const int j = int(i % dim);
-    const int f = j < half ? j : j - half;
-    // freqs = exp(-ln(1e4) * f / half) in fp32 (unet/utils.py:81-84)
-    const float freq = expf(-9.210340371976184f * (float)f / (float)half);
-    const float arg = t[b] * freq;
-    const float v = j < half ? cosf(arg) : sinf(arg);
-    __half h, l;
-    split_f16(v, h, l);
-    out[i] = h;
-    out[total + i] = l;
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int f = j < half ? j + e : j + e - half;
+      // freqs = exp(-ln(1e4) * f / half) in fp32 (unet/utils.py:81-84)
+      const float freq = expf(-9.210340371976184f * (float)f / (float)half);
+      const float arg = t[b] * freq;
+      v[e] = j < half ? cosf(arg) : sinf(arg);
+    }
+    store_split4(out, out + total, i, make_float4(v[0], v[1], v[2], v[3]));
   }
 }
 
@@ -730,7 +750,29 @@ extern "C" int sdb_pack_weight(const float* w, void* out, int64_t N, int64_t K, 
   SDB_REQUIRE(w && out && N > 0 && K > 0 && K % 4 == 0, "sdb_pack_weight: bad args N=%lld K=%lld", (long long)N,
               (long long)K);
   const int64_t n4 = N * K / 4;
-  pack_weight_kernel<<<grid_for(n4, 256), 256, 0, as_stream(stream)>>>(w, (__half*)out, n4, N * K);
+  pack_weight_kernel<<<grid_for(n4, 256), 256, 0, as_stream(stream)>>>(w, (__half*)out, n4, N * K, SDB_FMT_F16X2, 0);
+  SDB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sdb_pack_weight_fmt(const float* w, void* out, int64_t N, int64_t K, int fmt, int wexp, void* stream) {
+  SDB_REQUIRE(w && out && N > 0 && K > 0 && K % 4 == 0, "sdb_pack_weight_fmt: bad args N=%lld K=%lld", (long long)N,
+              (long long)K);
+  SDB_REQUIRE(fmt == SDB_FMT_F16X2 || fmt == SDB_FMT_F8C, "sdb_pack_weight_fmt: bad fmt %d", fmt);
+  SDB_REQUIRE(wexp >= -24 && wexp <= 40, "sdb_pack_weight_fmt: weight exponent %d out of range", wexp);
+  const int64_t n4 = N * K / 4;
+  pack_weight_kernel<<<grid_for(n4, 256), 256, 0, as_stream(stream)>>>(w, (__half*)out, n4, N * K, fmt, wexp);
+  SDB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sdb_pack_weight_conv3_fmt(const float* w, void* out, int64_t Cout, int64_t Cin, int fmt, int wexp,
+                                         void* stream) {
+  SDB_REQUIRE(w && out && Cout > 0 && Cin > 0 && Cin % 4 == 0, "sdb_pack_weight_conv3_fmt: bad args (Cin %% 4 == 0)");
+  SDB_REQUIRE(fmt == SDB_FMT_F16X2 || fmt == SDB_FMT_F8C, "sdb_pack_weight_conv3_fmt: bad fmt %d", fmt);
+  SDB_REQUIRE(wexp >= -24 && wexp <= 40, "sdb_pack_weight_conv3_fmt: weight exponent %d out of range", wexp);
+  pack_weight_conv3_v4_kernel<<<grid_for(Cout * 9 * Cin / 4, 256), 256, 0, as_stream(stream)>>>(w, (__half*)out, Cout, Cin,
+                                                                                                fmt, wexp);
   SDB_LAUNCH_CHECK();
   return 0;
 }
@@ -805,7 +847,8 @@ extern "C" int sdb_geglu_pack(const float* u, void* out, int64_t M, int64_t F, v
 
 extern "C" int sdb_timestep_embedding_pack(const float* t, void* out, int64_t B, int dim, void* stream) {
   SDB_REQUIRE(t && out && B > 0 && dim > 0 && dim % 2 == 0, "sdb_timestep_embedding_pack: bad args");
-  timestep_embedding_pack_kernel<<<grid_for(B * dim, 128), 128, 0, as_stream(stream)>>>(t, (__half*)out, B, dim);
+  SDB_REQUIRE(dim % 8 == 0, "sdb_timestep_embedding_pack: dim %% 8 == 0 required (got %d)", dim);
+  timestep_embedding_pack_kernel<<<grid_for(B * dim / 4, 128), 128, 0, as_stream(stream)>>>(t, (__half*)out, B, dim);
   SDB_LAUNCH_CHECK();
   return 0;
 }

@@ -11,6 +11,12 @@
 //                              residual / ReLU fused; all global loads of a 32x32 block are issued before use
 // Operands are fp16 hi/lo planes (see sdb200.h "packed"); passes=3 issues hi*hi + lo*hi + hi*lo per k-step,
 // which reproduces the fp32 product to ~2^-22 while running on the fp16 tensor pipe.
+// passes=2 (SDB_FMT_F8C operands, inference): hi*hi as kind::f16 into accumulator D1, the two correction products
+// l8*h8' + h8*l8' as kind::f8f6f4 (e4m3, K = 32 per instruction, twice the fp16 rate) into a second accumulator D2 in
+// the same TMEM stage, C = D1 + corr_scale * D2 in the epilogue: 8 instead of 12 instructions per k-block and
+// 1 + 1/2 + 1/2 = 2 pass-equivalents of tensor time (measured 0.669 of the 3-pass issue time, profiles/README 13).
+// The stage holds the same bytes (fp16 tile + two half-size e4m3 tiles, 64-byte rows, SWIZZLE_64B); bn <= 128 so that
+// D1 | D2 fit the 256 columns of an accumulator stage.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -28,6 +34,8 @@ namespace sdb {
 #if SDB_GEMM_TIMING
 __device__ unsigned long long g_gemm_timing[4];   // wait full | wait acc_empty | issuer lifetime | tiles issued
 #endif
+
+SDB_DEFINE_PACK_MODE_SETTER(set_pack_mode_gemm)
 
 constexpr int BM = 128;          // rows of A per CTA (UMMA M = 128 * CG)
 constexpr int BK = 64;           // fp16 elements per stage row = 128 B = one swizzle-128B row
@@ -81,6 +89,11 @@ struct GemmArgs {
   int H, W;             // output H, W (conv modes)
   int ctiles;           // WGRAD modes: channel blocks per tap
   int a_bf16, w_bf16;   // operand planes hold bf16 (gradient operands) instead of fp16
+  float corr_scale;     // passes == 2: C = D1 + corr_scale * D2
+  int acc_two;          // two accumulator stages (epilogue of tile i overlaps the main loop of tile i+1); 0: passes == 2
+                        // with bn > 128, where D1 | D2 fill all 512 TMEM columns (long-K tiles: the exposed epilogue costs
+                        // less than the shared-memory traffic of narrower tiles)
+  int d2_off;           // passes == 2: TMEM column offset of the correction accumulator inside a stage
   int debug;            // SDB_GEMM_DEBUG (launch-floor experiments): 1 = exit at entry, 2 = prologue + teardown only
 };
 
@@ -92,6 +105,7 @@ template <int CG, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
             const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+            const __grid_constant__ CUtensorMap map_a_l8, const __grid_constant__ CUtensorMap map_b_l8,
             const GemmArgs g) {
   extern __shared__ uint8_t smem_raw[];
   if (g.debug == 1) return;
@@ -103,7 +117,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
   const int group = blockIdx.x / CG, ngroups = gridDim.x / CG;
   const int num_items = g.n_tiles_m * g.n_tiles_n * g.splits;
   const int ksteps = g.kblocks * g.ntaps;   // k-blocks (stages) of a whole tile
-  const bool three = g.passes == 3;
+  const bool three = g.passes >= 2;    // a second operand plane is staged (fp16 lo, or the two e4m3 half-planes)
+  const bool f8c = g.passes == 2;      // map_*_lo then address the h8 half-plane, map_*_l8 the l8 half-plane
   const uint32_t b_tile_bytes = uint32_t(g.bnl) * BK * 2;
 
   if (warp == 0 && lane == 0) {
@@ -112,6 +127,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
     if (three) {
       tma_prefetch_desc(&map_a_lo);
       tma_prefetch_desc(&map_b_lo);
+    }
+    if (f8c) {
+      tma_prefetch_desc(&map_a_l8);
+      tma_prefetch_desc(&map_b_l8);
     }
     for (int s = 0; s < g.stages; ++s) {
       mbar_init(&ctl.full[s], 1);
@@ -226,12 +245,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
               tma_load_5d_pair(a_lo, &map_a_lo, &ctl.full[stage], c0, cx, cy, c3, c4);
               tma_load_2d_pair(b_lo, &map_b_lo, &ctl.full[stage], ks * BK, nrow);
             }
+            if (f8c) {   // second e4m3 half-plane: half a 16-bit tile further on
+              tma_load_5d_pair(a_lo + TILE_A_BYTES / 2, &map_a_l8, &ctl.full[stage], c0, cx, cy, c3, c4);
+              tma_load_2d_pair(b_lo + b_tile_bytes / 2, &map_b_l8, &ctl.full[stage], ks * BK, nrow);
+            }
           } else {
             tma_load_5d(a_hi, &map_a_hi, &ctl.full[stage], c0, cx, cy, c3, c4);
             tma_load_2d(b_hi, &map_b_hi, &ctl.full[stage], ks * BK, nrow);
             if (three) {
               tma_load_5d(a_lo, &map_a_lo, &ctl.full[stage], c0, cx, cy, c3, c4);
               tma_load_2d(b_lo, &map_b_lo, &ctl.full[stage], ks * BK, nrow);
+            }
+            if (f8c) {
+              tma_load_5d(a_lo + TILE_A_BYTES / 2, &map_a_l8, &ctl.full[stage], c0, cx, cy, c3, c4);
+              tma_load_2d(b_lo + b_tile_bytes / 2, &map_b_l8, &ctl.full[stage], ks * BK, nrow);
             }
           }
           if (++stage == g.stages) { stage = 0; phase ^= 1; }
@@ -256,8 +283,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
         const int tile = item / g.splits, split = item - tile * g.splits;
         const int ks_begin = (int)((long long)ksteps * split / g.splits);
         const int ks_end = (int)((long long)ksteps * (split + 1) / g.splits);
-        const int as = it & 1;
-        const uint32_t aphase = (it >> 1) & 1;
+        const int as = g.acc_two ? (it & 1) : 0;
+        const uint32_t aphase = g.acc_two ? ((it >> 1) & 1) : (it & 1);
 #if SDB_GEMM_TIMING
         const long long ta = clock64();
 #endif
@@ -284,6 +311,30 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
           const uint64_t da_lo = mn_major ? umma_desc_mnmajor_sw128(a_lo) : umma_desc_kmajor_sw128(a_lo);
           const uint64_t db_hi = mn_major ? umma_desc_mnmajor_sw128(b_hi) : umma_desc_kmajor_sw128(b_hi);
           const uint64_t db_lo = mn_major ? umma_desc_mnmajor_sw128(b_lo) : umma_desc_kmajor_sw128(b_lo);
+          if (f8c) {
+            // D1 += A_h W_h (4 x kind::f16, K = 16);  D2 += A_l8 W_h8 + A_h8 W_l8 (2 x 2 x kind::f8f6f4, K = 32)
+            const uint32_t d2 = d_tmem + g.d2_off;
+            const uint32_t first = (ks != ks_begin) ? 1u : 0u;
+#pragma unroll
+            for (int k = 0; k < BK / UK; ++k) {
+              const uint64_t adv = uint64_t((k * UK * 2) >> 4);
+              if (CG == 2) umma_f16_pair(d_tmem, da_hi + adv, db_hi + adv, idesc, k ? 1u : first);
+              else umma_f16(d_tmem, da_hi + adv, db_hi + adv, idesc, k ? 1u : first);
+            }
+            const uint64_t da_h8 = umma_desc_kmajor_sw64(a_lo), da_l8 = umma_desc_kmajor_sw64(a_lo + TILE_A_BYTES / 2);
+            const uint64_t db_h8 = umma_desc_kmajor_sw64(b_lo), db_l8 = umma_desc_kmajor_sw64(b_lo + b_tile_bytes / 2);
+#pragma unroll
+            for (int k = 0; k < BK / 32; ++k) {
+              const uint64_t adv = uint64_t((k * 32) >> 4);     // 32 e4m3 = 32 B inside the 64-B swizzle row
+              if (CG == 2) {
+                umma_f8_pair(d2, da_l8 + adv, db_h8 + adv, idesc, k ? 1u : first);
+                umma_f8_pair(d2, da_h8 + adv, db_l8 + adv, idesc, 1u);
+              } else {
+                umma_f8(d2, da_l8 + adv, db_h8 + adv, idesc, k ? 1u : first);
+                umma_f8(d2, da_h8 + adv, db_l8 + adv, idesc, 1u);
+              }
+            }
+          } else
 #pragma unroll
           for (int k = 0; k < BK / UK; ++k) {
             // K-major: 32 B per k-step inside the 128-B swizzle row; MN-major: 16 K rows = two 1024-B atoms per k-step
@@ -291,13 +342,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
             const uint32_t acc = (ks != ks_begin || k != 0) ? 1u : 0u;
             if (CG == 2) {
               umma_f16_pair(d_tmem, da_hi + adv, db_hi + adv, idesc, acc);
-              if (three) {
+              if (g.passes == 3) {
                 umma_f16_pair(d_tmem, da_lo + adv, db_hi + adv, idesc, 1);
                 umma_f16_pair(d_tmem, da_hi + adv, db_lo + adv, idesc, 1);
               }
             } else {
               umma_f16(d_tmem, da_hi + adv, db_hi + adv, idesc, acc);
-              if (three) {
+              if (g.passes == 3) {
                 umma_f16(d_tmem, da_lo + adv, db_hi + adv, idesc, 1);
                 umma_f16(d_tmem, da_hi + adv, db_lo + adv, idesc, 1);
               }
@@ -329,8 +380,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
       const int tile = item / g.splits, split = item - tile * g.splits;
       const int tm = (tile / g.n_tiles_n) * CG + (int)rank, tn = tile % g.n_tiles_n;
       const bool first = split == 0;       // the split that also adds bias / rowvec / residual
-      const int as = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
+      const int as = g.acc_two ? (it & 1) : 0;
+      const uint32_t aphase = g.acc_two ? ((it >> 1) & 1) : (it & 1);
       const long long row0l = (long long)tm * g.tile_rows + q * 32;   // first output row of this warp
       const int rows_valid = (int)min((long long)min(g.tile_rows - q * 32, 32), (long long)g.M - row0l);
       const int row0 = (int)min(row0l, (long long)g.M);
@@ -377,6 +428,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
 #pragma unroll
         for (int i = 0; i < 8; ++i) cur[i] = pre[i];
         if (j + 2 < nch) prefetch(j + 2, pre);
+        if (f8c) {      // correction accumulator: same lanes, ACC_COLS / 2 columns further on
+          uint32_t r2[32];
+          if (g.bn - cb >= 32) {
+            tmem_ld_32x32(taddr + g.d2_off, r2);
+          } else {
+            uint32_t r16[16];
+            tmem_ld_32x16(taddr + g.d2_off, r16);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) { r2[k] = r16[k]; r2[k + 16] = 0; }
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(fmaf(g.corr_scale, __uint_as_float(r2[k]), __uint_as_float(r[k])));
+        }
         tmem_ld_wait();
         if (rows_valid <= 0) continue;       // warp-uniform
         // thread `lane` holds row (q*32+lane), columns cb..cb+31 -> stage (swizzled) so that 8 lanes cover one
@@ -519,7 +584,7 @@ static EncodeTiledFn get_encode() {
 
 // fp16 tensor map, up to rank 5, SWIZZLE_128B, zero OOB fill. dims/box innermost first; strides in bytes for dims 1..
 static int make_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                    const uint32_t* box) {
+                    const uint32_t* box, bool e4m3 = false) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled not available (no CUDA driver?)");
@@ -534,8 +599,10 @@ static int make_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* d
     es[i] = 1;
     if (i > 0) gs[i - 1] = strides_bytes[i - 1];
   }
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(ptr), gd, gs, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  // e4m3 planes: one byte per element, 64-element (64-byte) box rows, SWIZZLE_64B
+  CUresult r = enc(m, e4m3 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank,
+                   const_cast<void*>(ptr), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   e4m3 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu %llu %llu] box [%u %u %u %u %u]", (int)r,
@@ -568,7 +635,8 @@ static int env_int(const char* name, int dflt) {
 
 template <int CG, int EPI>
 static int launch_gemm(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const CUtensorMap& mb_hi,
-                       const CUtensorMap& mb_lo, const GemmArgs& g, int groups, size_t smem, cudaStream_t st) {
+                       const CUtensorMap& mb_lo, const CUtensorMap& ma_l8, const CUtensorMap& mb_l8, const GemmArgs& g,
+                       int groups, size_t smem, cudaStream_t st) {
   static size_t attr = 0;
   if (smem > attr) {
     SDB_CHECK(cudaFuncSetAttribute(gemm_kernel<CG, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -586,7 +654,7 @@ static int launch_gemm(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  SDB_CHECK(cudaLaunchKernelEx(&cfg, gemm_kernel<CG, EPI>, ma_hi, ma_lo, mb_hi, mb_lo, g));
+  SDB_CHECK(cudaLaunchKernelEx(&cfg, gemm_kernel<CG, EPI>, ma_hi, ma_lo, mb_hi, mb_lo, ma_l8, mb_l8, g));
   SDB_LAUNCH_CHECK();
   return 0;
 }
@@ -598,7 +666,15 @@ using namespace sdb;
 extern "C" int sdb_gemm(const SdbGemm* p, void* stream) {
   SDB_REQUIRE(p && p->a && p->w && (p->c || p->out_packed), "sdb_gemm: null operand");
   SDB_REQUIRE(p->M > 0 && p->N > 0 && p->K > 0, "sdb_gemm: empty problem M=%d N=%d K=%d", p->M, p->N, p->K);
-  SDB_REQUIRE(p->passes == 1 || p->passes == 3, "sdb_gemm: passes must be 1 or 3");
+  SDB_REQUIRE(p->passes == 1 || p->passes == 2 || p->passes == 3, "sdb_gemm: passes must be 1, 2 or 3");
+  const bool f8c = p->passes == 2;
+  if (f8c) {
+    SDB_REQUIRE(p->mode == SDB_A_PLAIN || p->mode == SDB_A_CONV3 || p->mode == SDB_A_CONV3S2,
+                "sdb_gemm: passes = 2 (SDB_FMT_F8C operands) is a forward-only path (mode %d)", p->mode);
+    SDB_REQUIRE(!p->a_bf16 && !p->w_bf16, "sdb_gemm: passes = 2 takes fp16 + e4m3 operands, not bf16");
+    SDB_REQUIRE(p->K % 16 == 0, "sdb_gemm: passes = 2 needs K %% 16 == 0 (16-byte rows of the e4m3 planes), K=%d", p->K);
+    SDB_REQUIRE(p->corr_scale > 0.f, "sdb_gemm: passes = 2 needs corr_scale = 2^-(12 + wexp)");
+  }
   SDB_REQUIRE((p->a_bf16 != 0) == (p->w_bf16 != 0), "sdb_gemm: A and W must use the same 16-bit format (fp16 or bf16)");
   SDB_REQUIRE(p->K % 8 == 0 || p->mode == SDB_A_WGRAD || p->mode == SDB_A_WGRAD_S2,
               "sdb_gemm: K=%d must be a multiple of 8 (16-byte TMA rows)", p->K);
@@ -610,6 +686,7 @@ extern "C" int sdb_gemm(const SdbGemm* p, void* stream) {
   g.out_packed = reinterpret_cast<__half*>(p->out_packed); g.gsum = p->gsum;
   g.out_plane = p->out_plane_stride; g.out_act = p->out_act;
   g.a_bf16 = p->a_bf16 != 0; g.w_bf16 = p->w_bf16 != 0;
+  g.corr_scale = p->corr_scale;
   g.debug = env_int("SDB_GEMM_DEBUG", 0);
   g.ldc = p->ldc; g.ldv = p->ldv; g.ldr = p->ldr;
   g.M = p->M; g.N = p->N; g.K = p->K; g.mode = p->mode; g.passes = p->passes; g.relu = p->relu;
@@ -688,7 +765,13 @@ extern "C" int sdb_gemm(const SdbGemm* p, void* stream) {
   if (force_cg == 1 || force_cg == 2) cg = force_cg;
   const bool wgrad_mode = (p->mode == SDB_A_WGRAD || p->mode == SDB_A_WGRAD_S2);
   if (wgrad_mode) g.bn = pick_bn(p->N, 128 * cg, 64 * cg);   // each CTA stages whole 64-column (128-byte) blocks of dY
-  else g.bn = (cg == 2) ? pick_bn(p->N, 256, 32) : pick_bn(p->N, 128, geglu ? 32 : 16);
+  else {
+    // f8c: D1 | D2 share an accumulator stage -> bn <= 128 with two stages; long-K pair tiles take bn up to 256 with ONE
+    // stage instead (each staged byte is read once, so shared-memory traffic per flop falls with the tile width:
+    // 256 * (256 + 1.5 bn) bytes per k-block and CTA against 64 * bn / 128 * 8 tensor cycles -- profiles/README 13)
+    const bool wide = f8c && cg == 2 && p->N >= 256 && (long long)cdiv(p->K, BK) >= 16 && env_int("SDB_GEMM_F8_WIDE", 1);
+    g.bn = (cg == 2) ? pick_bn(p->N, (f8c && !wide) ? 128 : 256, 32) : pick_bn(p->N, 128, geglu ? 32 : 16);
+  }
   g.n_tiles_m = (int)cdiv(n_tiles_m1, cg);
   const int ksteps = g.kblocks * g.ntaps;
   const int units = sms / cg;
@@ -709,6 +792,8 @@ extern "C" int sdb_gemm(const SdbGemm* p, void* stream) {
     g.bn = best_bn;
   }
   g.bnl = g.bn / cg;
+  g.acc_two = !(f8c && g.bn > 128);
+  g.d2_off = g.bn > 128 ? ACC_COLS : ACC_COLS / 2;
   g.n_tiles_n = (int)cdiv(p->N, g.bn);
   const long long tiles = (long long)g.n_tiles_m * g.n_tiles_n;
   g.splits = 1;
@@ -727,7 +812,7 @@ extern "C" int sdb_gemm(const SdbGemm* p, void* stream) {
   SDB_REQUIRE(g.stages >= 2, "sdb_gemm: tile does not fit shared memory");
 
   // ---- tensor maps
-  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo, ma_l8, mb_l8;   // *_lo: fp16 lo plane, or (passes 2) the e4m3 h8 half-plane
   const __half* a = reinterpret_cast<const __half*>(p->a);
   const __half* w = reinterpret_cast<const __half*>(p->w);
   int rc;
@@ -737,7 +822,15 @@ extern "C" int sdb_gemm(const SdbGemm* p, void* stream) {
                       (uint64_t)p->K * 2 * p->M};
     uint32_t box[5] = {BK, BM, 1, 1, 1};
     if ((rc = make_map(&ma_hi, a, 5, dims, st, box))) return rc;
-    if ((rc = make_map(&ma_lo, a + p->a_plane_stride, 5, dims, st, box))) return rc;
+    if (f8c) {   // e4m3 half-planes: 1 byte per element, a_plane_stride BYTES each
+      uint64_t st8[4] = {(uint64_t)p->K, (uint64_t)p->K * p->M, (uint64_t)p->K * p->M, (uint64_t)p->K * p->M};
+      const uint8_t* a8 = reinterpret_cast<const uint8_t*>(a + p->a_plane_stride);
+      if ((rc = make_map(&ma_lo, a8, 5, dims, st8, box, true))) return rc;
+      if ((rc = make_map(&ma_l8, a8 + p->a_plane_stride, 5, dims, st8, box, true))) return rc;
+    } else {
+      if ((rc = make_map(&ma_lo, a + p->a_plane_stride, 5, dims, st, box))) return rc;
+      ma_l8 = ma_lo;
+    }
   } else if (wgrad_mode) {
     // the NHWC activation (or its stride-2 phase split): box = 64 channels x 64 pixels
     const int H = p->H, W = p->W, B = p->B, C = p->C;
@@ -747,6 +840,7 @@ extern "C" int sdb_gemm(const SdbGemm* p, void* stream) {
     uint32_t box[5] = {64, (uint32_t)W, (uint32_t)box_h, 1, (uint32_t)box_b};
     if ((rc = make_map(&ma_hi, a, 5, dims, st, box))) return rc;
     if ((rc = make_map(&ma_lo, a + p->a_plane_stride, 5, dims, st, box))) return rc;
+    ma_l8 = ma_lo;
   } else {
     const int H = p->H, W = p->W, B = p->B, C = p->C;
     const uint64_t phases = (p->mode == SDB_A_CONV3S2) ? 4 : 1;   // phase-split input [B][4][H][W][C]
@@ -754,7 +848,15 @@ extern "C" int sdb_gemm(const SdbGemm* p, void* stream) {
     uint64_t st[4] = {(uint64_t)C * 2, (uint64_t)C * 2 * W, (uint64_t)C * 2 * W * H, (uint64_t)C * 2 * W * H * phases};
     uint32_t box[5] = {BK, (uint32_t)W, (uint32_t)box_h, 1, (uint32_t)box_b};
     if ((rc = make_map(&ma_hi, a, 5, dims, st, box))) return rc;
-    if ((rc = make_map(&ma_lo, a + p->a_plane_stride, 5, dims, st, box))) return rc;
+    if (f8c) {
+      uint64_t st8[4] = {(uint64_t)C, (uint64_t)C * W, (uint64_t)C * W * H, (uint64_t)C * W * H * phases};
+      const uint8_t* a8 = reinterpret_cast<const uint8_t*>(a + p->a_plane_stride);
+      if ((rc = make_map(&ma_lo, a8, 5, dims, st8, box, true))) return rc;
+      if ((rc = make_map(&ma_l8, a8 + p->a_plane_stride, 5, dims, st8, box, true))) return rc;
+    } else {
+      if ((rc = make_map(&ma_lo, a + p->a_plane_stride, 5, dims, st, box))) return rc;
+      ma_l8 = ma_lo;
+    }
   }
   if (wgrad_mode) {   // dY rows [K = pixels][N], N contiguous: 64 x 64 boxes
     uint64_t dims[2] = {(uint64_t)p->N, (uint64_t)p->K};
@@ -762,12 +864,21 @@ extern "C" int sdb_gemm(const SdbGemm* p, void* stream) {
     uint32_t box[2] = {64, BK};
     if ((rc = make_map(&mb_hi, w, 2, dims, st, box))) return rc;
     if ((rc = make_map(&mb_lo, w + (long long)p->N * p->K, 2, dims, st, box))) return rc;
+    mb_l8 = mb_lo;
   } else {
     uint64_t dims[2] = {(uint64_t)p->K, (uint64_t)p->N};
     uint64_t st[1] = {(uint64_t)p->K * 2};
     uint32_t box[2] = {BK, (uint32_t)g.bnl};
     if ((rc = make_map(&mb_hi, w, 2, dims, st, box))) return rc;
-    if ((rc = make_map(&mb_lo, w + (long long)p->N * p->K, 2, dims, st, box))) return rc;
+    if (f8c) {
+      uint64_t st8[1] = {(uint64_t)p->K};
+      const uint8_t* w8 = reinterpret_cast<const uint8_t*>(w + (long long)p->N * p->K);
+      if ((rc = make_map(&mb_lo, w8, 2, dims, st8, box, true))) return rc;
+      if ((rc = make_map(&mb_l8, w8 + (long long)p->N * p->K, 2, dims, st8, box, true))) return rc;
+    } else {
+      if ((rc = make_map(&mb_lo, w + (long long)p->N * p->K, 2, dims, st, box))) return rc;
+      mb_l8 = mb_lo;
+    }
   }
   cudaStream_t st = as_stream(stream);
   if (g.splits > 1) {   // partial sums are accumulated with red.global.add: C starts at zero
@@ -778,10 +889,10 @@ extern "C" int sdb_gemm(const SdbGemm* p, void* stream) {
   const long long items = tiles * g.splits;
   const int groups = (int)(items < units ? items : units);
   if (geglu)
-    return cg == 2 ? launch_gemm<2, EPI_GEGLU>(ma_hi, ma_lo, mb_hi, mb_lo, g, groups, smem, st)
-                   : launch_gemm<1, EPI_GEGLU>(ma_hi, ma_lo, mb_hi, mb_lo, g, groups, smem, st);
-  return cg == 2 ? launch_gemm<2, EPI_F32>(ma_hi, ma_lo, mb_hi, mb_lo, g, groups, smem, st)
-                 : launch_gemm<1, EPI_F32>(ma_hi, ma_lo, mb_hi, mb_lo, g, groups, smem, st);
+    return cg == 2 ? launch_gemm<2, EPI_GEGLU>(ma_hi, ma_lo, mb_hi, mb_lo, ma_l8, mb_l8, g, groups, smem, st)
+                   : launch_gemm<1, EPI_GEGLU>(ma_hi, ma_lo, mb_hi, mb_lo, ma_l8, mb_l8, g, groups, smem, st);
+  return cg == 2 ? launch_gemm<2, EPI_F32>(ma_hi, ma_lo, mb_hi, mb_lo, ma_l8, mb_l8, g, groups, smem, st)
+                 : launch_gemm<1, EPI_F32>(ma_hi, ma_lo, mb_hi, mb_lo, ma_l8, mb_l8, g, groups, smem, st);
 }
 
 /* issuer wait accounting of the SDB_GEMM_TIMING build: out4 = {cycles waiting for operands, cycles waiting for a free

@@ -155,6 +155,10 @@ class DPMSolverSampler:
 
     def _run(self, x, context):
         """Enqueue the whole sampling loop on the current stream; returns the final latents."""
+        with ops.pack_format(ops.unet_inference_format()):      # UNet inference operand format (stream-ordered switch)
+            return self._run_plan(x, context)
+
+    def _run_plan(self, x, context):
         ex = self.ex
         B = x.shape[0]
         dev = x.device
@@ -208,7 +212,7 @@ class DPMSolverSampler:
         if sig != self._sig:            # train-then-sample (method.py logs samples every epoch): stale graphs go
             self._graphs.clear()
             self._sig = sig
-        key = (tuple(x_T.shape), tuple(context.shape), x_T.device.index, ops.get_passes())
+        key = (tuple(x_T.shape), tuple(context.shape), x_T.device.index, ops.precision_key())
         g = self._graphs.get(key)
         if g is None:
             sx, sc = x_T.clone(), context.clone()

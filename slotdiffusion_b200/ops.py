@@ -12,20 +12,62 @@ from . import _lib
 from ._lib import (SDB_A_CONV3, SDB_A_CONV3S2, SDB_A_PLAIN, SDB_PACK_PHASE2, SDB_PACK_PLAIN, SDB_PACK_UP2,
                    SdbGemm, SdbSlotUpdate, check, lib)
 
+import contextlib
+import math
+import os
+
+SDB_FMT_F16X2, SDB_FMT_F8C = 0, 2
+
 _PASSES = 3   # 3: hi*hi + lo*hi + hi*lo (fp32-faithful, default); 1: single fp16 pass
+_FMT = SDB_FMT_F16X2          # format the activation producers write NOW on the current stream / weights get packed in
+# Format of the UNet INFERENCE path (no-grad forward, DPM-Solver sampling): 'fp8c' = SDB_FMT_F8C operands, two
+# pass-equivalents per product (fp16 main term + two e4m3 correction terms, sdb200.h), UNet output 2.8e-5 rel-L2 from the
+# reference golden (three passes: 3.9e-6; contract 1e-3).  Measured on the B200 (profiles/README 13): the GEMMs are
+# shared-memory-bandwidth bound, not tensor bound, so the format buys 6-8 % of GEMM time and 1-3 % of a sampling step --
+# it stays OPT-IN (set_precision('fp8c') / SDB_UNET_PRECISION=fp8c); the default is the fp32-faithful three-pass format.
+# Training and Slot Attention (bit-exact argmax masks) always use three passes.
+_UNET_INFERENCE = os.environ.get('SDB_UNET_PRECISION', 'fp32')
 
 
 def set_precision(mode):
-    """'fp32' (default): 3-pass split-fp16 tensor-core products, ~2^-22 relative product error.
+    """'fp32' (default): 3-pass split-fp16 tensor-core products everywhere, ~2^-22 relative product error.
+    'fp8c': the same, except that UNet inference runs SDB_FMT_F8C operands (2 pass-equivalents, ~2^-15).
     'fp16': single pass (hi planes only), ~2^-11 -- the accuracy class of the reference under TF32/AMP."""
-    global _PASSES
-    if mode not in ('fp32', 'fp16'):
+    global _PASSES, _UNET_INFERENCE
+    if mode not in ('fp32', 'fp16', 'fp8c'):
         raise ValueError(mode)
-    _PASSES = 3 if mode == 'fp32' else 1
+    _PASSES = 1 if mode == 'fp16' else 3
+    _UNET_INFERENCE = 'fp8c' if mode == 'fp8c' else 'fp32'
 
 
 def get_passes():
     return _PASSES
+
+
+def precision_key():
+    """What a captured graph depends on (sampler graph cache key)."""
+    return (_PASSES, _UNET_INFERENCE, _FMT)
+
+
+@contextlib.contextmanager
+def pack_format(fmt):
+    """Stream-ordered scope in which every activation producer writes `fmt` and weights are packed in `fmt`
+    (sdb_set_pack_mode is a one-thread kernel: CUDA-graph capturable)."""
+    global _FMT
+    prev = _FMT
+    if fmt != prev:
+        check(lib().sdb_set_pack_mode(fmt, _stream()), 'sdb_set_pack_mode')
+        _FMT = fmt
+    try:
+        yield
+    finally:
+        if fmt != prev:
+            check(lib().sdb_set_pack_mode(prev, _stream()), 'sdb_set_pack_mode')
+            _FMT = prev
+
+
+def unet_inference_format():
+    return SDB_FMT_F8C if (_UNET_INFERENCE == 'fp8c' and _PASSES == 3) else SDB_FMT_F16X2
 
 
 def _stream():
@@ -43,18 +85,30 @@ def _f32(t, name='tensor'):
 
 
 class Packed:
-    """GEMM operand: 16-bit [2][rows][K] (hi plane, lo plane); fp16 split, or bf16 split for gradient operands."""
-    __slots__ = ('t', 'rows', 'K', 'bf16')
+    """GEMM operand: 16-bit [2][rows][K] (hi plane, lo plane); fp16 split, or bf16 split for gradient operands; fmt
+    SDB_FMT_F8C: plane 1 holds two e4m3 half-planes (sdb200.h), exponents (eh, el) = (2, 12) for activations,
+    (wexp, wexp + 10) for weights."""
+    __slots__ = ('t', 'rows', 'K', 'bf16', 'fmt', 'wexp')
 
-    def __init__(self, t, rows, K, bf16=False):
-        self.t, self.rows, self.K, self.bf16 = t, rows, K, bf16
+    def __init__(self, t, rows, K, bf16=False, fmt=SDB_FMT_F16X2, wexp=None):
+        self.t, self.rows, self.K, self.bf16, self.fmt, self.wexp = t, rows, K, bf16, fmt, wexp
 
     @staticmethod
-    def empty(rows, K, device, bf16=False):
-        return Packed(torch.empty(2 * rows * K, dtype=torch.float16, device=device), rows, K, bf16)
+    def empty(rows, K, device, bf16=False, fmt=None):
+        """fmt None: whatever the activation producers write on the current stream (pack_format scope)."""
+        if fmt is None:
+            fmt = SDB_FMT_F16X2 if bf16 else _FMT
+        return Packed(torch.empty(2 * rows * K, dtype=torch.float16, device=device), rows, K, bf16, fmt)
 
     def unpack(self):
         """fp32 value of the operand (tests only)."""
+        if self.fmt == SDB_FMT_F8C:
+            n = self.rows * self.K
+            hi = self.t[:n].view(self.rows, self.K).float()
+            f8 = self.t[n:].view(torch.float8_e4m3fn).view(2, self.rows, self.K).float()
+            eh, el = (2, 12) if self.wexp is None else (self.wexp, self.wexp + 10)
+            assert torch.allclose(f8[0] * 2.0 ** -eh, hi, rtol=2.0 ** -3, atol=2.0 ** (-9 - eh))    # e4m3 copy of hi
+            return hi + f8[1] * 2.0 ** -el
         t = self.t.view(torch.bfloat16) if self.bf16 else self.t
         t = t.view(2, self.rows, self.K).float()
         return t[0] + t[1]
@@ -85,6 +139,7 @@ class WeightCache:
         self._c = {}
 
     def _get(self, key, tensors, fn):
+        key = (key, _FMT)           # packed weights exist per operand format
         sig = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in tensors)
         hit = self._c.get(key)
         if hit is not None and hit[0] == sig:
@@ -152,10 +207,23 @@ class WeightCache:
         self._c.clear()
 
 
+def weight_exponent(w):
+    """Per-tensor exponent of an SDB_FMT_F8C weight: the largest b with max|w| * 2^b <= 448 (e4m3 max).  Parameter
+    preprocessing, once per parameter version (host read of one scalar)."""
+    m = float(w.detach().abs().max())
+    if not math.isfinite(m) or m <= 0.0:
+        return 0
+    return max(-24, min(40, int(math.floor(math.log2(448.0 / m)))))
+
+
 def pack_weight(w):
     _f32(w, 'weight')
     N, K = w.shape
     out = Packed.empty(N, K, w.device)
+    if out.fmt == SDB_FMT_F8C:
+        out.wexp = weight_exponent(w)
+        check(lib().sdb_pack_weight_fmt(_p(w), _p(out.t), N, K, SDB_FMT_F8C, out.wexp, _stream()), 'sdb_pack_weight_fmt')
+        return out
     check(lib().sdb_pack_weight(_p(w), _p(out.t), N, K, _stream()), 'sdb_pack_weight')
     return out
 
@@ -165,6 +233,11 @@ def pack_weight_conv3(w):
     Cout, Cin, kh, kw = w.shape
     assert kh == 3 and kw == 3
     out = Packed.empty(Cout, 9 * Cin, w.device)
+    if out.fmt == SDB_FMT_F8C:
+        out.wexp = weight_exponent(w)
+        check(lib().sdb_pack_weight_conv3_fmt(_p(w), _p(out.t), Cout, Cin, SDB_FMT_F8C, out.wexp, _stream()),
+              'sdb_pack_weight_conv3_fmt')
+        return out
     check(lib().sdb_pack_weight_conv3(_p(w), _p(out.t), Cout, Cin, _stream()), 'sdb_pack_weight_conv3')
     return out
 
@@ -283,6 +356,11 @@ def gemm(a, w, bias=None, rowvec=None, rows_per_group=0, residual=None, relu=Fal
     g.B, g.H, g.W, g.C = geo
     g.rows_per_group = rows_per_group
     g.passes = passes or _PASSES
+    if a.fmt == SDB_FMT_F8C or w.fmt == SDB_FMT_F8C:
+        if not (a.fmt == SDB_FMT_F8C and w.fmt == SDB_FMT_F8C and w.wexp is not None):
+            raise RuntimeError('sdb_gemm: mixed operand formats (activation fmt %d, weight fmt %d)' % (a.fmt, w.fmt))
+        g.passes = 2
+        g.corr_scale = 2.0 ** -(12 + w.wexp)
     g.relu = int(relu)
     if packed is not None:
         g.out_packed = packed.t.data_ptr()
@@ -307,6 +385,13 @@ def pack_weight_geglu(w, bias):
     bout = torch.empty_like(bias) if bias is not None else None
     check(lib().sdb_pack_weight_geglu(_p(w), _p(bias), _p(out.t), _p(bout), F2 // 2, K, _stream()),
           'sdb_pack_weight_geglu')
+    if out.fmt == SDB_FMT_F8C:
+        # the interleave [16 a | 16 g] is a row permutation: applied here (parameter preprocessing), then the generic
+        # per-tensor-exponent packer
+        F = F2 // 2
+        wp = torch.stack([w[:F].view(F // 16, 16, K), w[F:].view(F // 16, 16, K)], 1).reshape(F2, K).contiguous()
+        out.wexp = weight_exponent(w)
+        check(lib().sdb_pack_weight_fmt(_p(wp), _p(out.t), F2, K, SDB_FMT_F8C, out.wexp, _stream()), 'sdb_pack_weight_fmt')
     return out, bout
 
 

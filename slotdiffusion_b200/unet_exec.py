@@ -261,5 +261,5 @@ class UNetExecutor:
             return unet_forward_train(self, x, timesteps, context)
         if net.training and net.dropout > 0 and torch.is_grad_enabled():
             raise RuntimeError('training-mode forward without gradients is not supported; use torch.no_grad()/eval()')
-        with torch.no_grad():
+        with torch.no_grad(), ops.pack_format(ops.unet_inference_format()):
             return self.forward_inference(x, timesteps, context, ctx_kv)

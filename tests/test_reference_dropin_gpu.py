@@ -20,7 +20,7 @@ import ref_import  # noqa: E402
 
 from helpers import rel_l2  # noqa: E402
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900),
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900), pytest.mark.product_precision,
               pytest.mark.skipif(not ref_import.box_copy_available(),
                                  reason='baseline/_ref missing: run baseline/install_ref.sh in the build container')]
 CFG = ('img_based', 'sa_ldm/sa_ldm_clevrtex_params-res128.py')

@@ -155,21 +155,21 @@ def test_unet_dropout_backward_uses_the_forward_mask(monkeypatch):
     net, sd, cfg = _unet(cfg_over, dropout=0.3, train=True)
     x, ctx = seeded((4, 3, 16, 16), 41).cuda(), seeded((4, 5, 64), 42).cuda()
     t = torch.tensor([7, 503, 999, 1]).cuda()
-    d = seeded((4, 5, 64), 47).cuda()
-    d = d / d.norm()
+    gw = seeded((4, 3, 16, 16), 48).cuda()
 
     def loss_at(c):
         monkeypatch.setattr(bwd, '_step_counter', itertools.count(1234))       # same seed -> same masks
-        return (net(x, t, context=c) * 0.37).square().mean()
+        return (net(x, t, context=c).double() * gw).sum()
     cg = ctx.clone().requires_grad_(True)
     loss_at(cg).backward()
+    d = cg.grad / cg.grad.norm()                  # steepest direction: the derivative along it is |grad|
     analytic = (cg.grad * d).sum().item()
-    h = 2e-2
+    h = 1e-2
     with torch.enable_grad():
         lp = loss_at((ctx + h * d).requires_grad_(True)).item()
         lm = loss_at((ctx - h * d).requires_grad_(True)).item()
     fd = (lp - lm) / (2 * h)
-    assert abs(analytic) > 1e-6
+    assert abs(analytic) > 1e-3
     assert abs(fd - analytic) / abs(analytic) < 3e-2, (fd, analytic)
 
 

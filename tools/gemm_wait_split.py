@@ -30,6 +30,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--batch', type=int, default=256)
     ap.add_argument('--reps', type=int, default=5)
+    ap.add_argument('--fmt', default='f16x3', choices=['f16x3', 'f8c'], help='operand format: three fp16 passes or fp8-corrected (2 pass-equivalents)')
     args = ap.parse_args()
     B = args.batch
     dev = torch.device('cuda')
@@ -50,8 +51,9 @@ def main():
         else:
             M, K = geo
             arows, aK, conv = M, K, None
-        a = ops.Packed(torch.randn(2 * arows * aK, device=dev).half(), arows, aK)
-        w = ops.Packed((torch.randn(2 * N * K, device=dev) * K ** -0.5).half(), N, K)
+        fmt = ops.SDB_FMT_F8C if args.fmt == 'f8c' else ops.SDB_FMT_F16X2      # timing only: plane contents are random bits
+        a = ops.Packed(torch.randn(2 * arows * aK, device=dev).half(), arows, aK, fmt=fmt)
+        w = ops.Packed((torch.randn(2 * N * K, device=dev) * K ** -0.5).half(), N, K, fmt=fmt, wexp=0)
         bias = torch.randn(N, device=dev)
         res = torch.randn(M, N, device=dev) if with_res else None
         out = torch.empty(M, N, device=dev)
