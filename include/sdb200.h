@@ -345,6 +345,21 @@ int sdb_slot_attend_bwd(const float* kv, const float* q, const float* upd, const
                         float* dkv, float* dq, int64_t B, int64_t N, int64_t S, int64_t D, float scale, float eps,
                         int accumulate, void* stream);
 
+/* ------------------------------------------------------------------ boundary fusions (csrc/boundary.cu)
+ * q_sample: x_t[b] = sqrt_abar[t[b]] * x0[b] + sqrt_1m_abar[t[b]] * eps[b], rows of n = C*H*W floats (n % 4 == 0); the two
+ * products and the sum are rounded separately, so x_t is bit-identical to eager PyTorch (ddpm.py:161-165). */
+int sdb_q_sample(const float* x0, const float* eps, const int64_t* t, const float* sqrt_abar, const float* sqrt_1m_abar,
+                 float* out, int64_t B, int64_t n, void* stream);
+/* F.mse_loss(pred, target) (ldm.py:76-77): loss[0] = mean((pred - target)^2); diff (optional) keeps pred - target for
+ * sdb_mse_loss_bwd: dpred = diff * 2/n * grad_out[0]. */
+int sdb_mse_loss_fwd(const float* pred, const float* target, float* diff, float* loss, int64_t n, void* stream);
+int sdb_mse_loss_bwd(const float* diff, const float* grad_out, float* dpred, int64_t n, void* stream);
+/* eval-time slot masks (sa_diffusion.py:172-180, savi_diffusion.py:205-213 + test_seg.py:27): bilinear resize
+ * (align_corners = False, ATen's weights and evaluation order) of masks [B,S,h,w] to up [B,S,H,W] (optional) and the
+ * per-pixel argmax over slots idx [B,H,W] int64 (optional), first maximum wins. */
+int sdb_mask_upsample_argmax(const float* masks, float* up, int64_t* idx, int64_t B, int S, int h, int w, int H, int W,
+                             void* stream);
+
 #ifdef __cplusplus
 }
 #endif

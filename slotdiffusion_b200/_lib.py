@@ -45,6 +45,11 @@ SIGNATURES = {
     'sdb_pack_weight_fmt': (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p]),
     'sdb_pack_weight_conv3_fmt': (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p]),
     'sdb_set_pack_mode': (c_int, [c_int, c_void_p]),
+    'sdb_q_sample': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
+    'sdb_mse_loss_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    'sdb_mse_loss_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    'sdb_mask_upsample_argmax': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int,
+                                         c_void_p]),
     'sdb_pack_weight_conv3': (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     'sdb_pack_rows': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_void_p]),
     'sdb_layernorm_pack': (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int64, c_int64,

@@ -34,6 +34,8 @@ import runpy
 import sys
 import warnings
 
+import torch
+
 _TASKS = ('img_based', 'video_based')
 _saved = []          # (module, name, original) for uninstall()
 _installed = False
@@ -166,14 +168,18 @@ def _make_adapters(ref_dpm):
     return NoiseScheduleVP, model_wrapper, DPM_Solver
 
 
-def install(tasks=_TASKS, sampler=True):
+def install(tasks=_TASKS, sampler=True, boundary=True):
     """Rebind the reference's hot-path names to the B200 implementations (idempotent).  The reference package
-    `slotdiffusion` must be importable (on sys.path / installed)."""
+    `slotdiffusion` must be importable (on sys.path / installed).
+    boundary: also route q_sample (DDPM._sample_xt_from_x0, ddpm.py:161-165), F.mse_loss of LDM / CondDDPM.loss_function
+    (ldm.py:76-77, cond_ddpm.py:205-206) and the eval-time bilinear mask resize of SADiffusion / SAViDiffusion.encode
+    (sa_diffusion.py:172-180, savi_diffusion.py:205-213) to csrc/boundary.cu."""
     global _installed
     if _installed:
         return
     from .slot_attention import SlotAttention, SlotAttentionWMask
     from .unet import UNetModel
+    from . import boundary as _bd
     ref_dpm = importlib.import_module('slotdiffusion.video_based.models.ddpm.dpm_solver')
     adapters = _make_adapters(ref_dpm) if sampler else None
     for task in tasks:
@@ -190,6 +196,23 @@ def install(tasks=_TASKS, sampler=True):
             m = importlib.import_module(base + 'ddpm.cond_ddpm')
             for name, obj in zip(('NoiseScheduleVP', 'model_wrapper', 'DPM_Solver'), adapters):
                 _rebind(m, name, obj)
+        if boundary:
+            proxy = _bd.FunctionalProxy()
+            for mod_name in ('ddpm.ldm', 'ddpm.cond_ddpm', wmask_mod):
+                m = importlib.import_module(base + mod_name)
+                if hasattr(m, 'F'):
+                    _rebind(m, 'F', proxy)
+            ddpm_cls = importlib.import_module(base + 'ddpm.ddpm').DDPM
+            orig_q = ddpm_cls._sample_xt_from_x0
+
+            def _sample_xt_from_x0(self, x0, t, noise=None, _orig=orig_q):
+                if noise is None:
+                    noise = torch.randn_like(x0)          # same RNG call as the reference's default(...)
+                if x0.is_cuda and x0.dtype == torch.float32 and not x0.requires_grad and not noise.requires_grad \
+                        and x0[0].numel() % 4 == 0:
+                    return _bd.q_sample(x0, t, noise, self.sqrt_alphas_bar, self.sqrt_one_minus_alphas_bar)
+                return _orig(self, x0, t, noise)
+            _rebind(ddpm_cls, '_sample_xt_from_x0', _sample_xt_from_x0)
     _installed = True
 
 
