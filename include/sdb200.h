@@ -65,6 +65,9 @@ int64_t sdb_launch_count(void);
  * and zero padding are again TMA box shifts.  H, W = OUTPUT size.  C[9*C, N] with row = tap*C + ci;  M = 9*C, K = B*H*W. */
 #define SDB_A_WGRAD 3
 #define SDB_A_WGRAD_S2 4
+/* 3x3, stride 2 with the ASYMMETRIC padding of the VQ-VAE encoder's Downsample (modules.py:44-48: F.pad (0,1,0,1) then
+ * conv(stride 2, padding 0)): output (y,x) reads input (2y+ky, 2x+kx); same phase-split operand as SDB_A_CONV3S2. */
+#define SDB_A_CONV3S2A 5
 
 typedef struct SdbGemm {
   const void* a;         /* packed A, planes are a_plane_stride halves apart */
@@ -94,6 +97,8 @@ typedef struct SdbGemm {
                              tcgen05 kind::f16 takes ONE input format: a_bf16 must equal w_bf16 */
   float corr_scale;       /* passes == 2: 2^-s with s = el(A) + eh(W) = eh(A) + el(W) (= 12 + wexp of the packed weight) */
   int32_t reserved0;
+  int64_t w_plane_stride; /* halves between the hi and lo plane of W; 0 = N*K (a whole packed tensor).  Non-zero when W is
+                             a row range of a larger packed tensor (per-sample K / V^T operands of the VQ-VAE AttnBlock) */
 } SdbGemm;
 
 int sdb_gemm(const SdbGemm* p, void* stream);
@@ -344,6 +349,17 @@ int sdb_gru_gates_bwd(const float* gi, const float* gh, const float* h, const fl
 int sdb_slot_attend_bwd(const float* kv, const float* q, const float* upd, const float* colsum, const float* d_upd,
                         float* dkv, float* dq, int64_t B, int64_t N, int64_t S, int64_t D, float scale, float eps,
                         int accumulate, void* stream);
+
+/* ResNet18-GN encoder block end (resnet.py:72-90, stem :288-291): out = relu(GN(h; stats_h, gamma_h, beta_h) + identity),
+ * identity = idn (stats_i NULL), GN(idn; stats_i, gamma_i, beta_i) (the 1x1 `downsample` branch) or 0 (idn NULL).
+ * h, idn: NHWC rows [B*HW, C]; stats: [B,G,2] (mean, rstd).  Writes fp32 rows `out` and / or the packed operand. */
+int sdb_groupnorm_add_relu(const float* h, const float* stats_h, const float* gamma_h, const float* beta_h,
+                           const float* idn, const float* stats_i, const float* gamma_i, const float* beta_i, float* out,
+                           void* out_packed, int64_t B, int64_t HW, int64_t C, int G, void* stream);
+
+/* softmax over the last dim of x [M, N] (ldx) * scale, then pack: the P operand of the single-head attention of the
+ * VQ-VAE AttnBlock (modules.py:136-139: w_ = softmax(q k^T * C^-0.5)); N <= 4096, N % 4 == 0 */
+int sdb_softmax_pack(const float* x, int64_t ldx, float scale, void* out, int64_t M, int64_t N, void* stream);
 
 /* ------------------------------------------------------------------ boundary fusions (csrc/boundary.cu)
  * q_sample: x_t[b] = sqrt_abar[t[b]] * x0[b] + sqrt_1m_abar[t[b]] * eps[b], rows of n = C*H*W floats (n % 4 == 0); the two

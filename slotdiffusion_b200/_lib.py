@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # unset = the product build
 LIB_PATH = os.environ.get('SDB_LIB') or os.path.join(HERE, 'libsdb200.so')
 
-SDB_A_PLAIN, SDB_A_CONV3, SDB_A_CONV3S2, SDB_A_WGRAD, SDB_A_WGRAD_S2 = 0, 1, 2, 3, 4
+SDB_A_PLAIN, SDB_A_CONV3, SDB_A_CONV3S2, SDB_A_WGRAD, SDB_A_WGRAD_S2, SDB_A_CONV3S2A = 0, 1, 2, 3, 4, 5
 SDB_PACK_PLAIN, SDB_PACK_UP2, SDB_PACK_PHASE2 = 0, 1, 2
 
 
@@ -22,7 +22,7 @@ class SdbGemm(Structure):
         ('M', c_int32), ('N', c_int32), ('K', c_int32), ('mode', c_int32), ('B', c_int32), ('H', c_int32),
         ('W', c_int32), ('C', c_int32), ('rows_per_group', c_int32), ('passes', c_int32), ('relu', c_int32),
         ('out_packed', c_void_p), ('gsum', c_void_p), ('out_plane_stride', c_int64), ('out_act', c_int32),
-        ('geglu', c_int32), ('a_bf16', c_int32), ('w_bf16', c_int32), ('corr_scale', c_float), ('reserved0', c_int32),
+        ('geglu', c_int32), ('a_bf16', c_int32), ('w_bf16', c_int32), ('corr_scale', c_float), ('reserved0', c_int32), ('w_plane_stride', c_int64),
     ]
 
 
@@ -45,6 +45,8 @@ SIGNATURES = {
     'sdb_pack_weight_fmt': (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p]),
     'sdb_pack_weight_conv3_fmt': (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p]),
     'sdb_set_pack_mode': (c_int, [c_int, c_void_p]),
+    'sdb_groupnorm_add_relu': (c_int, [c_void_p] * 10 + [c_int64, c_int64, c_int64, c_int, c_void_p]),
+    'sdb_softmax_pack': (c_int, [c_void_p, c_int64, c_float, c_void_p, c_int64, c_int64, c_void_p]),
     'sdb_q_sample': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     'sdb_mse_loss_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     'sdb_mse_loss_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),

@@ -307,7 +307,8 @@ __global__ void __launch_bounds__(256) groupnorm_bwd_kernel(const GnBwdArgs a) {
       const float xh = (x[j] - mu[j]) * rs[j];
       float dz = d[j];
       if (a.drop_p > 0.f) dz *= dropout_scale(seed, (unsigned long long)(row * C + c + j), a.drop_p, inv_keep);
-      if (a.silu) dz *= silu_grad_f(xh * gm[j] + bt[j]);
+      if (a.silu == 1) dz *= silu_grad_f(xh * gm[j] + bt[j]);
+      else if (a.silu == 2) dz = (xh * gm[j] + bt[j] > 0.f) ? dz : 0.f;      // ReLU (ResNet18-GN encoder, resnet.py:76-78)
       if (APPLY) {
         o[j] = rs[j] * (dz * gm[j] - m1[j] - xh * m2[j]);
       } else {

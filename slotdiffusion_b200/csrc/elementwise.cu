@@ -194,9 +194,58 @@ __global__ void groupnorm_apply_pack_kernel(const float* __restrict__ x1, int C1
       const int g = (c + j) / cpg;   // cpg may not be a multiple of 4 (e.g. 28)
       const float mean = stats[(b * G + g) * 2], rstd = stats[(b * G + g) * 2 + 1];
       float o = (r[j] - mean) * rstd * gmv[j] + btv[j];
-      r[j] = silu ? silu_f(o) : o;
+      r[j] = silu == 1 ? silu_f(o) : (silu == 2 ? fmaxf(o, 0.f) : o);
     }
     store_split4(out, out + plane, row * C + c, make_float4(r[0], r[1], r[2], r[3]));
+  }
+}
+
+// Block end of the ResNet18-GN encoder (resnet.py:72-90): out = relu(GN_h(h) + identity), identity = the block input
+// (idn, stats_i == NULL), its normalised 1x1 projection (GN_i(idn), the `downsample` branch), or nothing (idn == NULL: the
+// stem conv1 -> bn1 -> relu, resnet.py:288-291).  Emits the fp32 rows (next block's identity) and / or the packed operand
+// of the next convolution in one pass.
+__global__ void groupnorm_add_relu_kernel(const float* __restrict__ h, const float* __restrict__ stats_h,
+                                          const float* __restrict__ gamma_h, const float* __restrict__ beta_h,
+                                          const float* __restrict__ idn, const float* __restrict__ stats_i,
+                                          const float* __restrict__ gamma_i, const float* __restrict__ beta_i,
+                                          float* __restrict__ out, __half* __restrict__ out_packed, int64_t B, int64_t HW,
+                                          int C, int G) {
+  const int c4n = C / 4, cpg = C / G;
+  const int64_t total = B * HW * c4n;
+  const int64_t plane = B * HW * (int64_t)C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = int(i % c4n) * 4;
+    const int64_t row = i / c4n;
+    const int64_t b = row / HW;
+    const float4 hv = *reinterpret_cast<const float4*>(h + row * C + c);
+    const float4 gm = *reinterpret_cast<const float4*>(gamma_h + c);
+    const float4 bt = *reinterpret_cast<const float4*>(beta_h + c);
+    float r[4] = {hv.x, hv.y, hv.z, hv.w};
+    const float gmv[4] = {gm.x, gm.y, gm.z, gm.w}, btv[4] = {bt.x, bt.y, bt.z, bt.w};
+    float id[4] = {0.f, 0.f, 0.f, 0.f};
+    if (idn) {
+      const float4 iv = *reinterpret_cast<const float4*>(idn + row * C + c);
+      id[0] = iv.x; id[1] = iv.y; id[2] = iv.z; id[3] = iv.w;
+      if (stats_i) {
+        const float4 gi = *reinterpret_cast<const float4*>(gamma_i + c);
+        const float4 bi = *reinterpret_cast<const float4*>(beta_i + c);
+        const float giv[4] = {gi.x, gi.y, gi.z, gi.w}, biv[4] = {bi.x, bi.y, bi.z, bi.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int g = (c + j) / cpg;
+          id[j] = (id[j] - stats_i[(b * G + g) * 2]) * stats_i[(b * G + g) * 2 + 1] * giv[j] + biv[j];
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int g = (c + j) / cpg;
+      const float z = (r[j] - stats_h[(b * G + g) * 2]) * stats_h[(b * G + g) * 2 + 1] * gmv[j] + btv[j];
+      r[j] = fmaxf(z + id[j], 0.f);
+    }
+    const float4 o = make_float4(r[0], r[1], r[2], r[3]);
+    if (out) *reinterpret_cast<float4*>(out + row * C + c) = o;
+    if (out_packed) store_split4(out_packed, out_packed + plane, row * C + c, o);
   }
 }
 
@@ -260,9 +309,12 @@ groupnorm_apply_pack_fused_kernel(const float* __restrict__ x1, int C1, const fl
     const int64_t row = b * HW + r;
     const float4 v = *reinterpret_cast<const float4*>(src + row * ld);
     float o[4] = {v.x * sc[0] + sh[0], v.y * sc[1] + sh[1], v.z * sc[2] + sh[2], v.w * sc[3] + sh[3]};
-    if (silu) {
+    if (silu == 1) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) o[j] = silu_f(o[j]);
+    } else if (silu == 2) {        // ReLU (ResNet18-GN encoder: conv -> GN -> ReLU, resnet.py:76-78)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = fmaxf(o[j], 0.f);
     }
     if (drop_p > 0.f) {
       const float inv_keep = 1.f / (1.f - drop_p);
@@ -445,6 +497,46 @@ __global__ void timestep_embedding_pack_kernel(const float* __restrict__ t, __ha
       v[e] = j < half ? cosf(arg) : sinf(arg);
     }
     store_split4(out, out + total, i, make_float4(v[0], v[1], v[2], v[3]));
+  }
+}
+
+// ------------------------------------------------------------------ row softmax (+ scale) -> packed operand
+// one warp per row, N <= 4096: the row lives in registers (up to 32 float4 per lane)
+__global__ void softmax_pack_kernel(const float* __restrict__ x, int64_t ldx, float scale, __half* __restrict__ out,
+                                    int64_t M, int N) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int n4 = N >> 2;
+  float4 v[32];
+  float mx = -3.0e38f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int j = i * 32 + lane;
+    if (j < n4) {
+      v[i] = *reinterpret_cast<const float4*>(x + row * ldx + j * 4);
+      v[i].x *= scale; v[i].y *= scale; v[i].z *= scale; v[i].w *= scale;
+      mx = fmaxf(mx, fmaxf(fmaxf(v[i].x, v[i].y), fmaxf(v[i].z, v[i].w)));
+    }
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int j = i * 32 + lane;
+    if (j < n4) {
+      v[i].x = expf(v[i].x - mx); v[i].y = expf(v[i].y - mx); v[i].z = expf(v[i].z - mx); v[i].w = expf(v[i].w - mx);
+      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.f / sum;
+  const int64_t plane = M * (int64_t)N;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int j = i * 32 + lane;
+    if (j < n4)
+      store_split4(out, out + plane, row * N + j * 4, make_float4(v[i].x * inv, v[i].y * inv, v[i].z * inv, v[i].w * inv));
   }
 }
 
@@ -849,6 +941,28 @@ extern "C" int sdb_timestep_embedding_pack(const float* t, void* out, int64_t B,
   SDB_REQUIRE(t && out && B > 0 && dim > 0 && dim % 2 == 0, "sdb_timestep_embedding_pack: bad args");
   SDB_REQUIRE(dim % 8 == 0, "sdb_timestep_embedding_pack: dim %% 8 == 0 required (got %d)", dim);
   timestep_embedding_pack_kernel<<<grid_for(B * dim / 4, 128), 128, 0, as_stream(stream)>>>(t, (__half*)out, B, dim);
+  SDB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sdb_groupnorm_add_relu(const float* h, const float* stats_h, const float* gamma_h, const float* beta_h,
+                                      const float* idn, const float* stats_i, const float* gamma_i, const float* beta_i,
+                                      float* out, void* out_packed, int64_t B, int64_t HW, int64_t C, int G, void* stream) {
+  SDB_REQUIRE(h && stats_h && gamma_h && beta_h && (out || out_packed), "sdb_groupnorm_add_relu: null argument");
+  SDB_REQUIRE(B > 0 && HW > 0 && C > 0 && C % 4 == 0 && G > 0 && C % G == 0, "sdb_groupnorm_add_relu: bad shape C=%lld G=%d",
+              (long long)C, G);
+  SDB_REQUIRE(!stats_i || (idn && gamma_i && beta_i), "sdb_groupnorm_add_relu: stats_i needs idn, gamma_i, beta_i");
+  groupnorm_add_relu_kernel<<<grid_for(B * HW * C / 4, 256), 256, 0, as_stream(stream)>>>(
+      h, stats_h, gamma_h, beta_h, idn, stats_i, gamma_i, beta_i, out, (__half*)out_packed, B, HW, (int)C, G);
+  SDB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sdb_softmax_pack(const float* x, int64_t ldx, float scale, void* out, int64_t M, int64_t N, void* stream) {
+  SDB_REQUIRE(x && out && M > 0 && N > 0 && N % 4 == 0 && N <= 4096 && ldx % 4 == 0,
+              "sdb_softmax_pack: bad args M=%lld N=%lld (N %% 4 == 0, N <= 4096)", (long long)M, (long long)N);
+  const int wpb = 4;
+  softmax_pack_kernel<<<(unsigned)cdiv(M, wpb), wpb * 32, 0, as_stream(stream)>>>(x, ldx, scale, (__half*)out, M, (int)N);
   SDB_LAUNCH_CHECK();
   return 0;
 }

@@ -195,15 +195,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
             const int hw = g.H * g.W;
             const int bimg = m0 / hw;
             const int yrow = (m0 - bimg * hw) / g.W;
+            const int xoff = (m0 - bimg * hw) - yrow * g.W;   // non-zero only for W > 64 (a k-block is a 64-pixel row segment)
             tap = wtap;
             c0 = wc0;
             if (g.mode == SDB_A_WGRAD) {
-              cx = tap % 3 - 1;
+              cx = tap % 3 - 1 + xoff;
               cy = yrow + tap / 3 - 1;
               c3 = 0;
             } else {
               const int ky = tap / 3, kx = tap % 3;
-              cx = (kx == 0) ? -1 : 0;
+              cx = ((kx == 0) ? -1 : 0) + xoff;
               cy = yrow + ((ky == 0) ? -1 : 0);
               c3 = ((ky != 1) ? 2 : 0) + ((kx != 1) ? 1 : 0);
             }
@@ -217,6 +218,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
             cp = ((ky != 1) ? 2 : 0) + ((kx != 1) ? 1 : 0);
             cx = (kx == 0) ? -1 : 0;
             cy = y0 + ((ky == 0) ? -1 : 0);
+          } else if (g.mode == SDB_A_CONV3S2A) {
+            // input pixel (2y+ky, 2x+kx), zero row / column past the bottom / right edge: ky=0 -> even phase, row y;
+            // ky=1 -> odd phase, row y; ky=2 -> even phase, row y+1 (out of bounds at y = H-1: TMA zero fill = the pad)
+            const int ky = tap / 3, kx = tap % 3;
+            cp = ((ky == 1) ? 2 : 0) + ((kx == 1) ? 1 : 0);
+            cx = (kx == 2) ? 1 : 0;
+            cy = y0 + ((ky == 2) ? 1 : 0);
           }
           if (!wgrad) { c3 = cp; c4 = b0; }
           uint8_t* a_hi = base, * a_lo = base + TILE_A_BYTES;
@@ -669,8 +677,9 @@ extern "C" int sdb_gemm(const SdbGemm* p, void* stream) {
   SDB_REQUIRE(p->passes == 1 || p->passes == 2 || p->passes == 3, "sdb_gemm: passes must be 1, 2 or 3");
   const bool f8c = p->passes == 2;
   if (f8c) {
-    SDB_REQUIRE(p->mode == SDB_A_PLAIN || p->mode == SDB_A_CONV3 || p->mode == SDB_A_CONV3S2,
+    SDB_REQUIRE(p->mode == SDB_A_PLAIN || p->mode == SDB_A_CONV3 || p->mode == SDB_A_CONV3S2 || p->mode == SDB_A_CONV3S2A,
                 "sdb_gemm: passes = 2 (SDB_FMT_F8C operands) is a forward-only path (mode %d)", p->mode);
+    SDB_REQUIRE(p->w_plane_stride == 0, "sdb_gemm: passes = 2 takes whole packed W tensors");
     SDB_REQUIRE(!p->a_bf16 && !p->w_bf16, "sdb_gemm: passes = 2 takes fp16 + e4m3 operands, not bf16");
     SDB_REQUIRE(p->K % 16 == 0, "sdb_gemm: passes = 2 needs K %% 16 == 0 (16-byte rows of the e4m3 planes), K=%d", p->K);
     SDB_REQUIRE(p->corr_scale > 0.f, "sdb_gemm: passes = 2 needs corr_scale = 2^-(12 + wexp)");
@@ -714,7 +723,7 @@ extern "C" int sdb_gemm(const SdbGemm* p, void* stream) {
 
   // ---- A-side tiling (per CTA: up to 128 rows)
   int n_tiles_m1;   // M tiles of ONE CTA
-  int box_h = 1, box_b = 1;
+  int box_h = 1, box_b = 1, box_w = 0;
   if (p->mode == SDB_A_PLAIN) {
     g.tile_rows = BM; g.ntaps = 1; g.kblocks = (int)cdiv(p->K, BK);
     n_tiles_m1 = (int)cdiv(p->M, BM);
@@ -724,18 +733,24 @@ extern "C" int sdb_gemm(const SdbGemm* p, void* stream) {
     SDB_REQUIRE(p->C % 64 == 0, "sdb_gemm: wgrad C=%d must be a multiple of 64", p->C);
     SDB_REQUIRE(p->M == 9 * p->C, "sdb_gemm: wgrad M=%d != 9*C", p->M);
     SDB_REQUIRE((long long)p->K == (long long)p->B * p->H * p->W, "sdb_gemm: wgrad K != B*H*W");
-    SDB_REQUIRE(p->W <= 64 && 64 % p->W == 0 && ((p->H * p->W) % 64 == 0 || 64 % (p->H * p->W) == 0),
-                "sdb_gemm: wgrad needs W | 64 and H*W a multiple or divisor of 64 (got %dx%d)", p->H, p->W);
+    SDB_REQUIRE(((p->W <= 64 && 64 % p->W == 0) || p->W % 64 == 0) && ((p->H * p->W) % 64 == 0 || 64 % (p->H * p->W) == 0),
+                "sdb_gemm: wgrad needs W | 64 (or 64 | W) and H*W a multiple or divisor of 64 (got %dx%d)", p->H, p->W);
     SDB_REQUIRE(p->N % 8 == 0, "sdb_gemm: wgrad N=%d must be a multiple of 8", p->N);
     g.H = p->H; g.W = p->W;
-    box_h = 64 / p->W < p->H ? 64 / p->W : p->H;
-    box_b = 64 / (p->W * box_h);
+    if (p->W > 64) {        // 128-wide feature maps (ResNet stem / layer1): a k-block is a 64-pixel segment of one row
+      box_w = 64; box_h = 1; box_b = 1;
+    } else {
+      box_w = p->W;
+      box_h = 64 / p->W < p->H ? 64 / p->W : p->H;
+      box_b = 64 / (p->W * box_h);
+    }
     g.tile_rows = (p->C % 128 == 0) ? 128 : 64;   // 64: the upper half of the UMMA tile is computed on stale rows and dropped
     g.ctiles = p->C / g.tile_rows;
     g.ntaps = 1; g.kblocks = (int)cdiv(p->K, BK);
     n_tiles_m1 = 9 * g.ctiles;
   } else {
-    SDB_REQUIRE(p->mode == SDB_A_CONV3 || p->mode == SDB_A_CONV3S2, "sdb_gemm: bad mode %d", p->mode);
+    SDB_REQUIRE(p->mode == SDB_A_CONV3 || p->mode == SDB_A_CONV3S2 || p->mode == SDB_A_CONV3S2A, "sdb_gemm: bad mode %d",
+                p->mode);
     SDB_REQUIRE(p->C % BK == 0, "sdb_gemm: conv C=%d must be a multiple of 64", p->C);
     SDB_REQUIRE(p->K == 9 * p->C, "sdb_gemm: conv K=%d != 9*C", p->K);
     SDB_REQUIRE((long long)p->M == (long long)p->B * p->H * p->W, "sdb_gemm: conv M != B*H*W");
@@ -815,6 +830,7 @@ extern "C" int sdb_gemm(const SdbGemm* p, void* stream) {
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo, ma_l8, mb_l8;   // *_lo: fp16 lo plane, or (passes 2) the e4m3 h8 half-plane
   const __half* a = reinterpret_cast<const __half*>(p->a);
   const __half* w = reinterpret_cast<const __half*>(p->w);
+  const long long w_plane = p->w_plane_stride > 0 ? (long long)p->w_plane_stride : (long long)p->N * p->K;
   int rc;
   if (p->mode == SDB_A_PLAIN) {
     uint64_t dims[5] = {(uint64_t)p->K, (uint64_t)p->M, 1, 1, 1};
@@ -837,13 +853,13 @@ extern "C" int sdb_gemm(const SdbGemm* p, void* stream) {
     const uint64_t phases = (p->mode == SDB_A_WGRAD_S2) ? 4 : 1;
     uint64_t dims[5] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, phases, (uint64_t)B};
     uint64_t st[4] = {(uint64_t)C * 2, (uint64_t)C * 2 * W, (uint64_t)C * 2 * W * H, (uint64_t)C * 2 * W * H * phases};
-    uint32_t box[5] = {64, (uint32_t)W, (uint32_t)box_h, 1, (uint32_t)box_b};
+    uint32_t box[5] = {64, (uint32_t)box_w, (uint32_t)box_h, 1, (uint32_t)box_b};
     if ((rc = make_map(&ma_hi, a, 5, dims, st, box))) return rc;
     if ((rc = make_map(&ma_lo, a + p->a_plane_stride, 5, dims, st, box))) return rc;
     ma_l8 = ma_lo;
   } else {
     const int H = p->H, W = p->W, B = p->B, C = p->C;
-    const uint64_t phases = (p->mode == SDB_A_CONV3S2) ? 4 : 1;   // phase-split input [B][4][H][W][C]
+    const uint64_t phases = (p->mode == SDB_A_CONV3S2 || p->mode == SDB_A_CONV3S2A) ? 4 : 1;   // phase-split input [B][4][H][W][C]
     uint64_t dims[5] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, phases, (uint64_t)B};
     uint64_t st[4] = {(uint64_t)C * 2, (uint64_t)C * 2 * W, (uint64_t)C * 2 * W * H, (uint64_t)C * 2 * W * H * phases};
     uint32_t box[5] = {BK, (uint32_t)W, (uint32_t)box_h, 1, (uint32_t)box_b};
@@ -863,7 +879,7 @@ extern "C" int sdb_gemm(const SdbGemm* p, void* stream) {
     uint64_t st[1] = {(uint64_t)p->N * 2};
     uint32_t box[2] = {64, BK};
     if ((rc = make_map(&mb_hi, w, 2, dims, st, box))) return rc;
-    if ((rc = make_map(&mb_lo, w + (long long)p->N * p->K, 2, dims, st, box))) return rc;
+    if ((rc = make_map(&mb_lo, w + w_plane, 2, dims, st, box))) return rc;
     mb_l8 = mb_lo;
   } else {
     uint64_t dims[2] = {(uint64_t)p->K, (uint64_t)p->N};
@@ -876,7 +892,7 @@ extern "C" int sdb_gemm(const SdbGemm* p, void* stream) {
       if ((rc = make_map(&mb_lo, w8, 2, dims, st8, box, true))) return rc;
       if ((rc = make_map(&mb_l8, w8 + (long long)p->N * p->K, 2, dims, st8, box, true))) return rc;
     } else {
-      if ((rc = make_map(&mb_lo, w + (long long)p->N * p->K, 2, dims, st, box))) return rc;
+      if ((rc = make_map(&mb_lo, w + w_plane, 2, dims, st, box))) return rc;
       mb_l8 = mb_lo;
     }
   }

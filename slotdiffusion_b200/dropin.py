@@ -19,6 +19,8 @@ training loop) keeps running as shipped:
   video_based/models/savi.py:17           SlotAttention            ...SlotAttention
   video_based/models/savi_diffusion.py:5,10 SlotAttention(WMask)   ...SlotAttention / SlotAttentionWMask
   {img,video}_based/models/ddpm/ddpm.py:24  UNetModel              slotdiffusion_b200.unet.UNetModel
+  video_based/models/vqvae/VQVAE.py:9      Encoder, Decoder         slotdiffusion_b200.vqvae.Encoder / Decoder (frozen, no-grad)
+  img_based/models/slot_attention.py:8, video_based/models/savi.py:8  resnet18, resnet34   slotdiffusion_b200.resnet (fwd + bwd)
   {img,video}_based/models/ddpm/cond_ddpm.py:15  NoiseScheduleVP,  thin adapters (below) that route the one sampler
                                           model_wrapper, DPM_Solver  configuration the repo uses (cond_ddpm.py:155-189)
                                                                     to slotdiffusion_b200.dpm_solver.DPMSolverSampler
@@ -168,7 +170,7 @@ def _make_adapters(ref_dpm):
     return NoiseScheduleVP, model_wrapper, DPM_Solver
 
 
-def install(tasks=_TASKS, sampler=True, boundary=True):
+def install(tasks=_TASKS, sampler=True, boundary=True, vqvae=True, encoder=True):
     """Rebind the reference's hot-path names to the B200 implementations (idempotent).  The reference package
     `slotdiffusion` must be importable (on sys.path / installed).
     boundary: also route q_sample (DDPM._sample_xt_from_x0, ddpm.py:161-165), F.mse_loss of LDM / CondDDPM.loss_function
@@ -180,6 +182,14 @@ def install(tasks=_TASKS, sampler=True, boundary=True):
     from .slot_attention import SlotAttention, SlotAttentionWMask
     from .unet import UNetModel
     from . import boundary as _bd
+    if vqvae:
+        # the frozen first stage of the LDM (VQVAEWrapper, VQVAE.py:155-194): Encoder / Decoder are looked up as module
+        # globals of vqvae/VQVAE.py when VQVAE.__init__ runs (VQVAE.py:9,66-67); img_based re-exports the same module.
+        # Inference only -- do not install with vqvae=True to TRAIN a VQ-VAE.
+        from . import vqvae as _vq
+        m = importlib.import_module('slotdiffusion.video_based.models.vqvae.VQVAE')
+        _rebind(m, 'Encoder', _vq.Encoder)
+        _rebind(m, 'Decoder', _vq.Decoder)
     ref_dpm = importlib.import_module('slotdiffusion.video_based.models.ddpm.dpm_solver')
     adapters = _make_adapters(ref_dpm) if sampler else None
     for task in tasks:
@@ -192,6 +202,13 @@ def install(tasks=_TASKS, sampler=True, boundary=True):
         _rebind(m, 'SlotAttentionWMask', SlotAttentionWMask)
         m = importlib.import_module(base + 'ddpm.ddpm')
         _rebind(m, 'UNetModel', UNetModel)
+        if encoder:
+            # the image encoder is built by eval(enc_dict['resnet'])(...) in the namespace of slot_attention.py / savi.py
+            # (slot_attention.py:8,185-188; savi.py:8,200-206)
+            from . import resnet as _rn
+            m = importlib.import_module(base + sa_mod)
+            _rebind(m, 'resnet18', _rn.resnet18)
+            _rebind(m, 'resnet34', _rn.resnet34)
         if adapters is not None:
             m = importlib.import_module(base + 'ddpm.cond_ddpm')
             for name, obj in zip(('NoiseScheduleVP', 'model_wrapper', 'DPM_Solver'), adapters):

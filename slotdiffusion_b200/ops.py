@@ -9,7 +9,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import (SDB_A_CONV3, SDB_A_CONV3S2, SDB_A_PLAIN, SDB_PACK_PHASE2, SDB_PACK_PLAIN, SDB_PACK_UP2,
+from ._lib import (SDB_A_CONV3, SDB_A_CONV3S2, SDB_A_CONV3S2A, SDB_A_PLAIN, SDB_PACK_PHASE2, SDB_PACK_PLAIN, SDB_PACK_UP2,
                    SdbGemm, SdbSlotUpdate, check, lib)
 
 import contextlib
@@ -88,10 +88,20 @@ class Packed:
     """GEMM operand: 16-bit [2][rows][K] (hi plane, lo plane); fp16 split, or bf16 split for gradient operands; fmt
     SDB_FMT_F8C: plane 1 holds two e4m3 half-planes (sdb200.h), exponents (eh, el) = (2, 12) for activations,
     (wexp, wexp + 10) for weights."""
-    __slots__ = ('t', 'rows', 'K', 'bf16', 'fmt', 'wexp')
+    __slots__ = ('t', 'rows', 'K', 'bf16', 'fmt', 'wexp', 'plane', 'off')
 
-    def __init__(self, t, rows, K, bf16=False, fmt=SDB_FMT_F16X2, wexp=None):
+    def __init__(self, t, rows, K, bf16=False, fmt=SDB_FMT_F16X2, wexp=None, plane=None, off=0):
         self.t, self.rows, self.K, self.bf16, self.fmt, self.wexp = t, rows, K, bf16, fmt, wexp
+        self.plane = rows * K if plane is None else plane      # halves between the hi and lo plane
+        self.off = off                                          # first half of the hi plane inside t (row-range views)
+
+    def ptr(self):
+        return self.t.data_ptr() + 2 * self.off
+
+    def row_range(self, r0, r1):
+        """Rows [r0, r1) as an operand of its own (no copy): same planes, shifted start -- e.g. the tokens of one sample."""
+        assert self.fmt == SDB_FMT_F16X2 and 0 <= r0 < r1 <= self.rows
+        return Packed(self.t, r1 - r0, self.K, self.bf16, self.fmt, self.wexp, plane=self.plane, off=self.off + r0 * self.K)
 
     @staticmethod
     def empty(rows, K, device, bf16=False, fmt=None):
@@ -253,6 +263,29 @@ def pack_rows(x, act=0):
     return out
 
 
+def groupnorm_add_relu(h, stats_h, gn_h, B, HW, idn=None, stats_i=None, gn_i=None, want_f32=True, want_packed=True):
+    """relu(GN(h) + identity) -> (fp32 rows | None, Packed | None); identity = idn, GN_i(idn) or nothing."""
+    C = h.shape[-1]
+    out = torch.empty_like(h) if want_f32 else None
+    pk = Packed.empty(B * HW, C, h.device) if want_packed else None
+    check(lib().sdb_groupnorm_add_relu(_p(h), _p(stats_h), _p(gn_h.weight), _p(gn_h.bias), _p(idn), _p(stats_i),
+                                       _p(gn_i.weight) if gn_i is not None else None,
+                                       _p(gn_i.bias) if gn_i is not None else None, _p(out),
+                                       _p(pk.t) if pk is not None else None, B, HW, C, gn_h.num_groups, _stream()),
+          'sdb_groupnorm_add_relu')
+    return out, pk
+
+
+def softmax_pack(x, scale=1.0):
+    """softmax(x * scale) over the last dim of x [M, N] (strided rows ok) -> Packed [M, N]."""
+    _f32(x)
+    assert x.dim() == 2 and x.stride(1) == 1
+    M, N = x.shape
+    out = Packed.empty(M, N, x.device)
+    check(lib().sdb_softmax_pack(_p(x), x.stride(0), float(scale), _p(out.t), M, N, _stream()), 'sdb_softmax_pack')
+    return out
+
+
 def layernorm_pack(x, gamma, beta, eps=1e-5, want_fp32=False):
     _f32(x)
     C = x.shape[-1]
@@ -343,12 +376,13 @@ def gemm(a, w, bias=None, rowvec=None, rows_per_group=0, residual=None, relu=Fal
     if keep_c and out is None:
         out = torch.empty(M, N, dtype=torch.float32, device=dev)
     g = SdbGemm()
-    g.a, g.w = a.t.data_ptr(), w.t.data_ptr()
+    g.a, g.w = a.ptr(), w.ptr()
+    g.w_plane_stride = 0 if w.plane == w.rows * w.K else w.plane
     g.c = out.data_ptr() if keep_c else None
     g.bias = bias.data_ptr() if bias is not None else None
     g.rowvec = rowvec.data_ptr() if rowvec is not None else None
     g.residual = residual.data_ptr() if residual is not None else None
-    g.a_plane_stride = a.rows * a.K
+    g.a_plane_stride = a.plane
     g.ldc = out.stride(0) if keep_c else N
     g.ldv = rowvec.stride(0) if rowvec is not None else 0
     g.ldr = residual.stride(0) if residual is not None else 0

@@ -100,9 +100,25 @@ def test_install_swaps_hot_path_inside_unmodified_reference(dropin, task, rel):
     new_model.load_state_dict(ref_model.state_dict(), strict=True)
     assert [n for n, _ in new_model.named_parameters()] == [n for n, _ in ref_model.named_parameters()]
     assert any('dm_decoder' in n for n, _ in new_model.named_parameters())      # img_based/method.py:251-257
-    # everything else is still the reference's own code
+    # the image encoder and the frozen VQ-VAE first stage are the B200 modules too ...
+    from slotdiffusion_b200 import resnet as b200_resnet, vqvae as b200_vqvae
+    assert type(new_model.encoder) is b200_resnet.ResNet and type(ref_model.encoder) is not b200_resnet.ResNet
+    assert type(new_model.dm_decoder.vae.vqvae.encoder) is b200_vqvae.Encoder
+    assert type(new_model.dm_decoder.vae.vqvae.decoder) is b200_vqvae.Decoder
+    assert not any(p.requires_grad for p in new_model.dm_decoder.vae.parameters())      # frozen (VQVAE.py:172-176)
+    # ... everything else is still the reference's own code
     assert type(new_model.dm_decoder) is type(ref_model.dm_decoder)
-    assert type(new_model.encoder) is type(ref_model.encoder)
+    assert type(new_model.dm_decoder.vae) is type(ref_model.dm_decoder.vae)
+    assert type(new_model.dm_decoder.vae.vqvae.quantize) is type(ref_model.dm_decoder.vae.vqvae.quantize)
+    assert type(new_model.encoder_out_layer) is type(ref_model.encoder_out_layer)
+    # a partial install leaves the rest alone
+    dropin.uninstall()
+    dropin.install(encoder=False, vqvae=False, boundary=False)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        part = mods.build_model(_fresh_params(ri, task, rel))
+    assert type(part.encoder) is type(ref_model.encoder) and type(part.slot_attention) is SlotAttentionWMask
+    assert type(part.dm_decoder.vae.vqvae.encoder) is type(ref_model.dm_decoder.vae.vqvae.encoder)
     dropin.uninstall()
     with warnings.catch_warnings():
         warnings.simplefilter('ignore')

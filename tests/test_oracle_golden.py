@@ -114,3 +114,39 @@ def test_dpm_sampler_oracle_matches_reference():
         assert rel_l2(y, g['sample_novq']) < 1e-5
         y = dpm_ref.dpm_sample(fn, betas, xT, ctx, cb)
         assert rel_l2(y, g['sample_vq']) < 1e-5
+
+
+def test_vqvae_oracle_matches_reference_golden():
+    """oracle/vqvae_ref.py pinned to the unmodified reference Encoder / Decoder (tests/golden/vqvae.npz); small config on
+    every run, the full 128x128 config too (a few seconds of CPU)."""
+    import numpy as np
+    from helpers import golden, seeded
+    from oracle import vqvae_ref
+    g = golden('vqvae')
+    for tag, over, B in (('small', dict(resolution=32, ch_mult=(1, 2)), 3), ('full', {}, 2)):
+        cfg = dict(vqvae_ref.DEFAULT_CFG, **over)
+        esd, dsd = vqvae_ref.random_state_dicts(cfg, seed=61)
+        R = cfg['resolution']
+        r = R // 2 ** (len(cfg['ch_mult']) - 1)
+        x = seeded((B, 3, R, R), 62).clamp(-1, 1)
+        z = seeded((B, 3, r, r), 63)
+        with torch.no_grad():
+            np.testing.assert_allclose(vqvae_ref.encoder_forward(esd, x, cfg).numpy(), g[tag + '_enc'], rtol=1e-4, atol=1e-5)
+            np.testing.assert_allclose(vqvae_ref.decoder_forward(dsd, z, cfg).numpy(), g[tag + '_dec'], rtol=1e-4, atol=1e-5)
+
+
+def test_resnet_oracle_matches_reference_golden():
+    """oracle/resnet_ref.py pinned to the unmodified reference resnet18(small_inputs=True, use_layer4=False)"""
+    from helpers import golden, seeded
+    from oracle import resnet_ref
+    g = golden('resnet')
+    sd = resnet_ref.random_state_dict('resnet18', False, seed=71)
+    x = seeded((2, 3, 64, 64), 73).clamp(-1, 1)
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    y = resnet_ref.resnet_forward(sdg, x)
+    assert rel_l2(y, g['y64']) < 1e-6
+    (y * seeded(tuple(y.shape), 74)).sum().backward()
+    for k in ('bn1.weight', 'layer2.0.downsample.1.bias', 'layer3.1.bn2.weight'):
+        assert rel_l2(sdg[k].grad, g['grad.' + k]) < 1e-5, k
+    assert abs(checksum(sdg['layer1.0.conv1.weight'].grad)[1] - g['grad.layer1.0.conv1.weight'][1]) \
+        / g['grad.layer1.0.conv1.weight'][1] < 1e-5

@@ -217,6 +217,56 @@ def gen_dpm_plan():
     print('dpm_plan ok', len(out))
 
 
+def gen_vqvae():
+    """Encoder / Decoder of the frozen VQ-VAE (modules.py:168-362) at the shipped CLEVRTex config (128x128, ch 64,
+    ch_mult [1,2,4], mid attention at 32x32) and a small ragged config; weights from oracle.vqvae_ref.random_state_dicts."""
+    import contextlib
+    import io
+    from slotdiffusion.video_based.models.vqvae.modules import Encoder, Decoder
+    from oracle import vqvae_ref
+    out = {}
+    for tag, over, B in (('full', {}, 2), ('small', dict(resolution=32, ch_mult=(1, 2)), 3)):
+        cfg = dict(vqvae_ref.DEFAULT_CFG, **over)
+        esd, dsd = vqvae_ref.random_state_dicts(cfg, seed=61)
+        with contextlib.redirect_stdout(io.StringIO()):
+            enc, dec = Encoder(dropout=0.0, **cfg).eval(), Decoder(dropout=0.0, **cfg).eval()
+        enc.load_state_dict(esd, strict=True)
+        dec.load_state_dict(dsd, strict=True)
+        R = cfg['resolution']
+        r = R // 2 ** (len(cfg['ch_mult']) - 1)
+        x = seeded((B, 3, R, R), 62).clamp(-1, 1)
+        z = seeded((B, 3, r, r), 63)
+        with torch.no_grad():
+            out[tag + '_enc'] = enc(x).numpy()
+            out[tag + '_dec'] = dec(z).numpy()
+        out[tag + '_x_sum'], out[tag + '_z_sum'] = checksum(x), checksum(z)
+    np.savez_compressed(os.path.join(OUT, 'vqvae.npz'), **out)
+    print('vqvae.npz', {k: v.shape for k, v in out.items()})
+
+
+def gen_resnet():
+    """ResNet18-GN encoder (resnet.py:150-315, small_inputs=True, use_layer4=False): forward at 128x128 (B=1) and
+    forward + parameter gradients of a fixed linear functional at 64x64 (B=2); weights: oracle.resnet_ref.random_state_dict."""
+    from slotdiffusion.video_based.models.resnet import resnet18
+    from oracle import resnet_ref
+    sd = resnet_ref.random_state_dict('resnet18', False, seed=71)
+    net = resnet18(small_inputs=True, use_layer4=False)
+    net.load_state_dict(sd, strict=True)
+    out = {}
+    x128 = seeded((1, 3, 128, 128), 72).clamp(-1, 1)
+    with torch.no_grad():
+        out['y128'] = net(x128).numpy()
+    x64 = seeded((2, 3, 64, 64), 73).clamp(-1, 1)
+    y = net(x64)
+    gw = seeded(tuple(y.shape), 74)
+    (y * gw).sum().backward()
+    out['y64'] = y.detach().numpy()
+    for k, v in net.named_parameters():
+        out['grad.' + k] = v.grad.numpy() if v.grad.dim() == 1 else checksum(v.grad)
+    np.savez_compressed(os.path.join(OUT, 'resnet.npz'), **out)
+    print('resnet.npz', out['y128'].shape, out['y64'].shape, len(out))
+
+
 def gen_layout():
     """state_dict layout (ordered key -> shape) of the hot-path sub-modules inside the full reference models
     (build_model of the shipped configs): the checkpoint contract of the drop-in modules."""
@@ -269,7 +319,11 @@ def gen_layout():
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['sa', 'unet', 'dpm', 'layout', 'dpm_plan']
+    which = sys.argv[1:] or ['sa', 'unet', 'dpm', 'layout', 'dpm_plan', 'vqvae', 'resnet']
+    if 'vqvae' in which:
+        gen_vqvae()
+    if 'resnet' in which:
+        gen_resnet()
     if 'sa' in which:
         gen_sa()
     if 'unet' in which:
