@@ -17,20 +17,33 @@ def _gn(x, sd, name):
     return F.group_norm(x, 32, sd[name + '.weight'], sd[name + '.bias'], 1e-5)       # _gn, resnet.py:8-9
 
 
-def basic_block(sd, pre, x, stride):
-    out = F.relu(_gn(F.conv2d(x, sd[pre + 'conv1.weight'], None, stride=stride, padding=1), sd, pre + 'bn1'))
+def _relu(z, rec):
+    """ReLU; `rec` (optional) = dict(masks=iterator | None, seen=list): with `masks` the activation pattern is FORCED
+    (z * mask) -- gradient checks against an fp32 implementation compare like with like: an element within round-off of
+    zero may legitimately fall on either side, and a single flipped element moves every upstream gradient by O(1e-3) --
+    and `seen` collects this run's own patterns so the caller can count the disagreements."""
+    if rec is None:
+        return F.relu(z)
+    rec['seen'].append(z.detach() > 0)
+    if rec.get('masks') is None:
+        return F.relu(z)
+    return z * next(rec['masks']).to(z.dtype)
+
+
+def basic_block(sd, pre, x, stride, rec=None):
+    out = _relu(_gn(F.conv2d(x, sd[pre + 'conv1.weight'], None, stride=stride, padding=1), sd, pre + 'bn1'), rec)
     out = _gn(F.conv2d(out, sd[pre + 'conv2.weight'], None, stride=1, padding=1), sd, pre + 'bn2')
     if pre + 'downsample.0.weight' in sd:
         x = _gn(F.conv2d(x, sd[pre + 'downsample.0.weight'], None, stride=stride), sd, pre + 'downsample.1')
-    return F.relu(out + x)
+    return _relu(out + x, rec)
 
 
-def resnet_forward(sd, x, arch='resnet18', use_layer4=False):
+def resnet_forward(sd, x, arch='resnet18', use_layer4=False, rec=None):
     sd = {k: v.to(x.dtype) for k, v in sd.items()}
-    h = F.relu(_gn(F.conv2d(x, sd['conv1.weight'], None, stride=1, padding=1), sd, 'bn1'))
+    h = _relu(_gn(F.conv2d(x, sd['conv1.weight'], None, stride=1, padding=1), sd, 'bn1'), rec)
     for li, n in enumerate(LAYERS[arch][:4 if use_layer4 else 3]):
         for bi in range(n):
-            h = basic_block(sd, f'layer{li + 1}.{bi}.', h, 2 if (li > 0 and bi == 0) else 1)
+            h = basic_block(sd, f'layer{li + 1}.{bi}.', h, 2 if (li > 0 and bi == 0) else 1, rec)
     return h
 
 

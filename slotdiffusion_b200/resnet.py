@@ -196,6 +196,9 @@ class ResNet(nn.Module):
         blocks = [b for layer in layers for b in layer]
         nxt_s2 = blocks[0].stride == 2
         cur, cur_p = self._block_end(tp, h, st, self.bn1, None, None, None, B, H * W, want_packed=not nxt_s2)
+        trace = getattr(self, '_relu_trace', None)      # tests: the activation pattern of every ReLU, in forward order
+        if trace is not None:
+            trace.append((cur > 0, (B, 64, H, W)))
         C = 64
         for bi, blk in enumerate(blocks):
             key = id(blk)
@@ -221,11 +224,15 @@ class ResNet(nn.Module):
                 p1 = ops.groupnorm_pack_fused(h1, None, blk.bn1.weight, blk.bn1.bias, B, HW, 32, blk.bn1.eps, 2, stats=st1)
             else:
                 p1 = groupnorm_node(tp, h1, None, blk.bn1, G, B, HW, 2, st1)          # act 2 = ReLU
+            if trace is not None:
+                trace.append((p1.unpack() > 0, (B, Cout, H, W)))
             h2, gs2 = self._conv(tp, p1, blk.conv2, (key, 'c2'), B, H, W, Cout)
             st2 = self._stats(h2, gs2, blk.bn2, B, HW)
             last = bi == len(blocks) - 1
             nxt_s2 = (not last) and blocks[bi + 1].stride == 2
             cur, cur_p = self._block_end(tp, h2, st2, blk.bn2, idn, st_i, gn_i, B, HW, want_packed=not (last or nxt_s2))
+            if trace is not None:
+                trace.append((cur > 0, (B, Cout, H, W)))
             C = Cout
         return cur, (B, C, H, W)
 

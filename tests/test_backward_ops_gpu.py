@@ -57,7 +57,8 @@ def test_linear_backward(ops, M, N, K):
 
 
 @pytest.mark.parametrize('B,H,W,C,Cout', [(2, 32, 32, 128, 128), (3, 16, 16, 256, 384), (5, 8, 8, 384, 128),
-                                          (4, 8, 8, 64, 256), (7, 4, 4, 512, 512), (3, 16, 16, 192, 64)])
+                                          (4, 8, 8, 64, 256), (7, 4, 4, 512, 512), (3, 16, 16, 192, 64),
+                                          (2, 64, 64, 64, 64), (1, 128, 128, 64, 64), (2, 16, 128, 64, 128)])   # ResNet stem / layer1
 def test_conv3_backward(ops, B, H, W, C, Cout):
     x = rnd(B, C, H, W, seed=6).double().requires_grad_()
     w = rnd(Cout, C, 3, 3, seed=7, scale=(9 * C) ** -0.5).double().requires_grad_()
@@ -74,7 +75,7 @@ def test_conv3_backward(ops, B, H, W, C, Cout):
     assert rel_l2(dw, w.grad) < TOLB
 
 
-@pytest.mark.parametrize('B,H,W,C', [(2, 32, 32, 128), (3, 16, 16, 256)])
+@pytest.mark.parametrize('B,H,W,C', [(2, 32, 32, 128), (3, 16, 16, 256), (2, 128, 128, 64)])
 def test_conv3_stride2_backward(ops, B, H, W, C):
     """H, W = input size; output H/2 x W/2."""
     x = rnd(B, C, H, W, seed=9).double().requires_grad_()

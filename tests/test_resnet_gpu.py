@@ -33,7 +33,10 @@ def test_forward_matches_reference_golden_128():
     assert y2.requires_grad and rel_l2(y2, g['y128']) < TIGHT
 
 
-def test_gradients_match_reference_golden_64():
+def test_gradients_vs_reference_golden_64():
+    """against the reference's own fp32 autograd (CPU).  Loose on purpose: two fp32 implementations put a handful of the
+    ~10^6 ReLU inputs that lie within round-off of zero on different sides, and ONE such element moves every upstream
+    gradient by O(1e-3) (measured, tools/debug/resnet_mask.py); the exact statement is the forced-pattern test below."""
     g = golden('resnet')
     net, sd = _net()
     x = seeded((2, 3, 64, 64), 73).clamp(-1, 1).cuda()
@@ -43,46 +46,58 @@ def test_gradients_match_reference_golden_64():
     worst = ('', 0.0)
     for k, p in net.named_parameters():
         ref = g['grad.' + k]
-        if p.grad.dim() == 1:
-            e = rel_l2(p.grad, ref)
-        else:
-            e = abs(checksum(p.grad)[1] - ref[1]) / ref[1]           # sum of squares of the gradient tensor
+        e = rel_l2(p.grad, ref) if p.grad.dim() == 1 else abs(checksum(p.grad)[1] - ref[1]) / ref[1]
         worst = max(worst, (k, e), key=lambda t: t[1])
-        assert e < 1e-3, (k, e)
+        assert e < 1e-2, (k, e)
     print('worst parameter gradient vs reference golden', worst)
 
 
-def test_gradients_match_fp64_oracle_full_tensors():
-    """every parameter-gradient tensor element-wise against fp64 autograd of the oracle (128x128 stem / layer1 included:
-    the 128-wide feature maps take the 64-pixel-segment form of the wgrad GEMM)"""
-    net, sd = _net(seed=5)
-    x = seeded((2, 3, 128, 128), 81).clamp(-1, 1)
-    y = net(x.cuda())
-    gw = seeded(tuple(y.shape), 82)
-    (y * gw.cuda()).sum().backward()
+def _check_forced_pattern(arch, use_layer4, seed, xs, gws):
+    """Gradients of sum_i <net(x_i), gw_i> for EVERY parameter tensor, element-wise, against fp64 autograd of the oracle
+    run with the ReLU activation patterns of OUR forward (oracle.resnet_ref._relu); the patterns themselves may differ
+    from the oracle's own only in a few elements per million."""
+    net, sd = _net(arch, use_layer4, seed=seed)
+    traces, ys = [], []
+    for x in xs:
+        net._relu_trace = []
+        ys.append(net(x.cuda()))
+        traces.append(net._relu_trace)
+    net._relu_trace = None
+    sum((y * gw.cuda()).sum() for y, gw in zip(ys, gws)).backward()
     sd64 = {k: v.double().clone().requires_grad_(True) for k, v in sd.items()}
-    ref = resnet_ref.resnet_forward(sd64, x.double())
-    (ref * gw.double()).sum().backward()
-    assert rel_l2(y, ref) < TIGHT
-    for k, p in net.named_parameters():
-        assert rel_l2(p.grad, sd64[k].grad) < GTOL, (k, rel_l2(p.grad, sd64[k].grad))
+    total = 0.0
+    flips = elems = 0
+    for x, gw, y, tr in zip(xs, gws, ys, traces):
+        masks = [m.view(B, H, W, C).permute(0, 3, 1, 2).cpu() for m, (B, C, H, W) in tr]
+        rec = dict(masks=iter(masks), seen=[])
+        ref = resnet_ref.resnet_forward(sd64, x.double(), arch, use_layer4, rec=rec)
+        assert rel_l2(y, ref) < TIGHT
+        total = total + (ref * gw.double()).sum()
+        assert len(rec['seen']) == len(masks)
+        flips += sum(int((a != b).sum()) for a, b in zip(rec['seen'], masks))
+        elems += sum(m.numel() for m in masks)
+    total.backward()
+    print(arch, 'ReLU pattern disagreements with the fp64 oracle: %d of %d' % (flips, elems))
+    assert flips <= max(2, 2e-5 * elems)
+    worst = max(((k, rel_l2(p.grad, sd64[k].grad)) for k, p in net.named_parameters()), key=lambda t: t[1])
+    print('worst parameter gradient (forced pattern)', worst)
+    assert worst[1] < GTOL, worst
+
+
+def test_gradients_match_fp64_oracle_full_tensors_128():
+    """128x128 input, batch 2: the stem / layer1 feature maps are 128 wide (64-pixel-segment form of the wgrad GEMM)"""
+    _check_forced_pattern('resnet18', False, 5, [seeded((2, 3, 128, 128), 81).clamp(-1, 1)], [seeded((2, 256, 32, 32), 82)])
+
+
+def test_gradients_seed_with_a_boundary_element():
+    """seed 71 / 64x64: one output element sits within 2e-5 of the ReLU boundary (the case that motivated forced patterns)"""
+    _check_forced_pattern('resnet18', False, 71, [seeded((2, 3, 64, 64), 81).clamp(-1, 1)], [seeded((2, 256, 16, 16), 82)])
 
 
 def test_resnet34_layer4_and_two_calls_one_backward():
     """the other factory / use_layer4=True, and two forward calls before one backward (per-call gradient buffers)"""
-    net, sd = _net('resnet34', True, seed=9)
-    xa, xb = seeded((1, 3, 64, 64), 91).clamp(-1, 1), seeded((1, 3, 64, 64), 92).clamp(-1, 1)
-    ya, yb = net(xa.cuda()), net(xb.cuda())
-    assert ya.shape == (1, 512, 8, 8)
-    ga, gb = seeded(tuple(ya.shape), 93), seeded(tuple(ya.shape), 94)
-    ((ya * ga.cuda()).sum() + (yb * gb.cuda()).sum()).backward()
-    sd64 = {k: v.double().clone().requires_grad_(True) for k, v in sd.items()}
-    ra = resnet_ref.resnet_forward(sd64, xa.double(), 'resnet34', True)
-    rb = resnet_ref.resnet_forward(sd64, xb.double(), 'resnet34', True)
-    ((ra * ga.double()).sum() + (rb * gb.double()).sum()).backward()
-    assert rel_l2(ya, ra) < TIGHT and rel_l2(yb, rb) < TIGHT
-    for k, p in net.named_parameters():
-        assert rel_l2(p.grad, sd64[k].grad) < GTOL, k
+    _check_forced_pattern('resnet34', True, 9, [seeded((1, 3, 64, 64), 91).clamp(-1, 1), seeded((1, 3, 64, 64), 92).clamp(-1, 1)],
+                          [seeded((1, 512, 8, 8), 93), seeded((1, 512, 8, 8), 94)])
 
 
 def test_no_cpu_fallback_and_unsupported_configs():
