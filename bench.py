@@ -192,7 +192,7 @@ def run_ours(args):
     gpu_base = None
     if world == 1 and not args.no_gpu_baseline:
         try:
-            gpu_base = gpu_baseline(dev, B)
+            gpu_base = gpu_baseline(dev, B, 0 if args.no_train else args.train_batch)
             gpu_base['speedup_vs_tf32_stock'] = (B * NFE * args.steps / (ms / 1e3)) / gpu_base['tf32_stock']['value'] \
                 if 'tf32_stock' in gpu_base else None
             gpu_base['speedup_vs_tf32_all'] = (B * NFE * args.steps / (ms / 1e3)) / gpu_base['tf32_all']['value'] \
@@ -201,12 +201,18 @@ def run_ours(args):
             gpu_base = {'unavailable': repr(e)[:300]}
             torch.cuda.empty_cache()
 
-    train = None
+    train = train_hot = None
     if not args.no_train:
         del feats_d, noise_d
         torch.cuda.empty_cache()
-        train = train_bench(args, dev, world, rank)
+        train = train_bench(args, dev, world, rank, full=True)
+        torch.cuda.empty_cache()
+        train_hot = train_bench(args, dev, world, rank, full=False)
+        torch.cuda.empty_cache()
 
+    if gpu_base and train and 'train_tf32_stock' in gpu_base:
+        gpu_base['train_speedup_vs_tf32_stock'] = train['value'] / gpu_base['train_tf32_stock']['value']
+        gpu_base['train_speedup_vs_tf32_all'] = train['value'] / gpu_base['train_tf32_all']['value']
     if rank == 0:
         peaks, peak_src = load_peaks()
         units = B * NFE * world * args.steps
@@ -244,59 +250,145 @@ def run_ours(args):
             'cpu_baseline': cpu_baseline(sample_nfe=NFE, batch=4) if world == 1 else None,   # rank 0, N=1 only
             'gpu_baseline': gpu_base,
             'train': train,
+            'train_hot_modules': train_hot,
         }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
-def train_bench(args, dev, world, rank):
-    """One TRAINING step of the hot path (LDM.loss_function shape, ldm.py:59-83): slots = SlotAttention(features);
-    x_t = q_sample(x0, t, eps); loss = mse(UNet(x_t, t, slots), eps); backward through both modules (hand-written
-    kernels), data-parallel gradient all-reduce, Adam step.  Encoder features and VQ-VAE latents are synthetic inputs
-    (both encoders are out of scope)."""
+class FullImageModel(torch.nn.Module):
+    """SADiffusion + LDM of the reference (CLEVRTex config, sa_ldm_clevrtex_params-res128.py) assembled from the B200 modules:
+    ResNet18-GN encoder, Slot Attention, frozen VQ-VAE encoder, slot-conditioned UNet, q_sample / eps-MSE kernels.  What
+    stays PyTorch is what the reference also runs as a handful of small eager ops between them: SoftPositionEmbed
+    (utils.py: x + Linear(4 -> 256)(grid)), the per-token LayerNorm-MLP (slot_attention.py:228-233) and the 1x1 quant_conv
+    (VQVAE.py:97-98).  Mirrors SADiffusion.forward + calc_train_loss -> LDM.loss_function (sa_diffusion.py:185-213,
+    ldm.py:59-83)."""
+
+    def __init__(self, dev):
+        super().__init__()
+        from slotdiffusion_b200 import resnet, vqvae
+        from slotdiffusion_b200.slot_attention import SlotAttentionWMask
+        from slotdiffusion_b200.unet import UNetModel
+        nn = torch.nn
+        self.encoder = resnet.resnet18(small_inputs=True, use_layer4=False)
+        self.pos_dense = nn.Linear(4, 256)
+        self.encoder_out_layer = nn.Sequential(nn.LayerNorm(256), nn.Linear(256, D), nn.ReLU(), nn.Linear(D, D))
+        self.init_latents = nn.Parameter(torch.randn(1, S, D))
+        self.slot_attention = SlotAttentionWMask(D, SA_ITERS, S, D, 2 * D)
+        self.vq_encoder = vqvae.Encoder(ch=64, out_ch=3, ch_mult=(1, 2, 4), num_res_blocks=2, attn_resolutions=[], dropout=0.0,
+                                        in_channels=3, resolution=128, z_channels=3)
+        self.quant_conv = nn.Conv2d(3, 3, 1)
+        self.unet = UNetModel(in_channels=3, model_channels=128, out_channels=3, num_res_blocks=2,
+                              attention_resolutions=(8, 4, 2), dropout=0.1, channel_mult=(1, 2, 3, 4), dims=2,
+                              use_checkpoint=False, num_head_channels=32, resblock_updown=False, conv_resample=True,
+                              transformer_depth=1, context_dim=D, n_embed=None)
+        for p in list(self.vq_encoder.parameters()) + list(self.quant_conv.parameters()):
+            p.requires_grad_(False)                                    # frozen first stage (VQVAE.py:172-176)
+        with torch.no_grad():
+            for p in self.unet.parameters():
+                if p.abs().max() == 0:
+                    p.normal_(0, 0.02)
+        ys, xs = torch.meshgrid(torch.linspace(0., 1., 32), torch.linspace(0., 1., 32), indexing='ij')
+        grid = torch.stack([ys, xs], -1).reshape(1024, 2)
+        self.register_buffer('grid', torch.cat([grid, 1. - grid], -1))          # build_grid, utils.py
+        betas = (torch.linspace(0.0015 ** 0.5, 0.0195 ** 0.5, 1000, dtype=torch.float64) ** 2)
+        acp = torch.cumprod(1 - betas, 0)
+        self.register_buffer('sqrt_abar', acp.sqrt().float())
+        self.register_buffer('sqrt_1m_abar', (1 - acp).sqrt().float())
+        self.to(dev)
+
+    def trainable(self):
+        return [p for p in self.parameters() if p.requires_grad]
+
+    def eager_params(self):
+        """parameters whose gradients come from torch autograd (not from a module's own all-reduced flat buffer)"""
+        return list(self.pos_dense.parameters()) + list(self.encoder_out_layer.parameters()) + [self.init_latents]
+
+    def loss(self, img):
+        from slotdiffusion_b200 import boundary
+        B = img.shape[0]
+        with torch.no_grad():
+            x0 = self.quant_conv(self.vq_encoder(img))                 # ldm.py:62-64
+        t = torch.randint(0, 1000, (B,), device=img.device)
+        eps = torch.randn_like(x0)
+        xt = boundary.q_sample(x0, t, eps, self.sqrt_abar, self.sqrt_1m_abar)   # ddpm.py:161-165
+        f = self.encoder(img)                                          # [B, 256, 32, 32]
+        f = f + self.pos_dense(self.grid).t().reshape(1, 256, 32, 32)
+        feats = self.encoder_out_layer(f.flatten(2).permute(0, 2, 1).contiguous())
+        slots, _ = self.slot_attention(feats, self.init_latents.expand(B, -1, -1))
+        return boundary.mse_loss(self.unet(xt, t, context=slots), eps)        # ldm.py:76-77
+
+
+# algorithmic work of the full training step per sample: fwd + bwd (3x) of the trainable modules, fwd of the frozen VQ-VAE
+RESNET_FLOP_PER_SAMPLE = 13.45e9
+VQENC_FLOP_PER_SAMPLE = 19.5e9
+FULL_TRAIN_FLOP_PER_SAMPLE = 3 * (UNET_FLOP_PER_SAMPLE + 203.7e6 + RESNET_FLOP_PER_SAMPLE) + VQENC_FLOP_PER_SAMPLE
+
+
+def train_bench(args, dev, world, rank, full=True):
+    """One TRAINING step.  full=True: the whole image model of BASELINE configs[1] (FullImageModel: images in, loss out,
+    backward through UNet, Slot Attention and the ResNet encoder, data-parallel gradient all-reduce, fused Adam) -- the
+    'train-step samples/s' of BASELINE.json.  full=False: the two hot modules alone on synthetic encoder features / latents
+    (round-1 number, kept for continuity)."""
     import torch.distributed as dist
     from slotdiffusion_b200 import parallel
     from slotdiffusion_b200.slot_attention import SlotAttentionWMask
     from slotdiffusion_b200.unet import UNetModel
     B = args.train_batch
     torch.manual_seed(rank)
-    sa = SlotAttentionWMask(D, SA_ITERS, S, D, 2 * D).to(dev).train()
-    unet = UNetModel(in_channels=3, model_channels=128, out_channels=3, num_res_blocks=2,
-                     attention_resolutions=(8, 4, 2), dropout=0.1, channel_mult=(1, 2, 3, 4), dims=2,
-                     use_checkpoint=False, num_head_channels=32, resblock_updown=False, conv_resample=True,
-                     transformer_depth=1, context_dim=D, n_embed=None).to(dev).train()
-    with torch.no_grad():
-        for p in unet.parameters():
-            if p.abs().max() == 0:
-                p.normal_(0, 0.02)
-    init_slots = torch.nn.Parameter(torch.randn(1, S, D, device=dev))
-    params = list(sa.parameters()) + list(unet.parameters()) + [init_slots]
+    g = torch.Generator().manual_seed(4321 + rank)
+    if full:
+        model = FullImageModel(dev).train()
+        model.vq_encoder.eval()
+        params = model.trainable()
+        img_h = torch.randn(B, 3, 128, 128, generator=g).clamp_(-1, 1).pin_memory()
+        inputs_h = (img_h,)
+        wcaches = [model.slot_attention._wcache, model.unet._exec.wc, model.encoder._wc]
+    else:
+        sa = SlotAttentionWMask(D, SA_ITERS, S, D, 2 * D).to(dev).train()
+        unet = UNetModel(in_channels=3, model_channels=128, out_channels=3, num_res_blocks=2,
+                         attention_resolutions=(8, 4, 2), dropout=0.1, channel_mult=(1, 2, 3, 4), dims=2,
+                         use_checkpoint=False, num_head_channels=32, resblock_updown=False, conv_resample=True,
+                         transformer_depth=1, context_dim=D, n_embed=None).to(dev).train()
+        with torch.no_grad():
+            for p in unet.parameters():
+                if p.abs().max() == 0:
+                    p.normal_(0, 0.02)
+        init_slots = torch.nn.Parameter(torch.randn(1, S, D, device=dev))
+        params = list(sa.parameters()) + list(unet.parameters()) + [init_slots]
+        betas = (torch.linspace(0.0015 ** 0.5, 0.0195 ** 0.5, 1000, dtype=torch.float64) ** 2)
+        acp = torch.cumprod(1 - betas, 0).float().to(dev)
+        inputs_h = (torch.randn(B, N_TOK, D, generator=g).pin_memory(), torch.randn(B, 3, 32, 32, generator=g).pin_memory())
+        wcaches = [sa._wcache, unet._exec.wc]
     if world > 1:
         for p in params:
             dist.broadcast(p.data, 0)
         parallel.enable_grad_allreduce()
     use_graph = not args.no_train_graph
     opt = torch.optim.Adam(params, lr=1e-4, fused=True, capturable=use_graph)
-    betas = (torch.linspace(0.0015 ** 0.5, 0.0195 ** 0.5, 1000, dtype=torch.float64) ** 2)
-    acp = torch.cumprod(1 - betas, 0).float().to(dev)
-    g = torch.Generator().manual_seed(4321 + rank)
-    feats_h = torch.randn(B, N_TOK, D, generator=g).pin_memory()
-    x0_h = torch.randn(B, 3, 32, 32, generator=g).pin_memory()
-    feats_d, x0_d = feats_h.to(dev), x0_h.to(dev)
+    inputs_d = tuple(t.to(dev) for t in inputs_h)
     from slotdiffusion_b200 import _lib, ops
 
-    def step(feats, x0):
+    def step(*inp):
         ops.dropout_step_counter(dev).add_(1)                        # new dropout masks every step (also under replay)
-        t = torch.randint(0, 1000, (B,), device=dev)
-        eps = torch.randn_like(x0)
-        a = acp[t].view(B, 1, 1, 1)
-        xt = a.sqrt() * x0 + (1 - a).sqrt() * eps                    # q_sample, ddpm.py:161-165 (caller side)
-        slots, _ = sa(feats, init_slots.expand(B, -1, -1))
-        loss = torch.nn.functional.mse_loss(unet(xt, t, context=slots), eps)
+        if full:
+            loss = model.loss(inp[0])
+            eager = model.eager_params()
+        else:
+            feats, x0 = inp
+            t = torch.randint(0, 1000, (B,), device=dev)
+            eps = torch.randn_like(x0)
+            a = acp[t].view(B, 1, 1, 1)
+            xt = a.sqrt() * x0 + (1 - a).sqrt() * eps                # q_sample, ddpm.py:161-165 (caller side)
+            slots, _ = sa(feats, init_slots.expand(B, -1, -1))
+            loss = torch.nn.functional.mse_loss(unet(xt, t, context=slots), eps)
+            eager = [init_slots]
         loss.backward()
-        if world > 1 and init_slots.grad is not None:
-            dist.all_reduce(init_slots.grad, op=dist.ReduceOp.AVG)
+        if world > 1:                                                # the few torch-autograd parameters (the modules reduce their own)
+            for p in eager:
+                if p.grad is not None:
+                    dist.all_reduce(p.grad, op=dist.ReduceOp.AVG)
         opt.step()
         opt.zero_grad(set_to_none=True)
         return loss
@@ -322,10 +414,10 @@ def train_bench(args, dev, world, rank):
 
     # launches per step: counted on eager steps (graph replays do not pass through the C ABI again)
     for _ in range(2):
-        step(feats_d, x0_d)
+        step(*inputs_d)
     torch.cuda.synchronize()
     n0 = _lib.launch_count()
-    step(feats_d, x0_d)
+    step(*inputs_d)
     torch.cuda.synchronize()
     launches = _lib.launch_count() - n0
     mode = 'eager'
@@ -334,55 +426,56 @@ def train_bench(args, dev, world, rank):
         # the caller captures the WHOLE step (forward, backward, all-reduce, Adam) in one CUDA graph: every kernel of
         # the library is enqueue-only and allocation-free, weight re-packing is part of the captured step
         try:
-            sf, sx = feats_d.clone(), x0_d.clone()
+            static_in = tuple(t.clone() for t in inputs_d)
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 for _ in range(2):
-                    step(sf, sx)
+                    step(*static_in)
             torch.cuda.current_stream().wait_stream(side)
-            sa._wcache.clear()
-            unet._exec.wc.clear()
+            for wc in wcaches:
+                wc.clear()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                static_loss = step(sf, sx)
+                static_loss = step(*static_in)
 
-            def run(feats, x0):
-                if feats is not sf:
-                    sf.copy_(feats, non_blocking=True)
-                    sx.copy_(x0, non_blocking=True)
+            def run(*inp):
+                if inp[0] is not static_in[0]:
+                    for dst, src in zip(static_in, inp):
+                        dst.copy_(src, non_blocking=True)
                 graph.replay()
                 return static_loss
-            run(sf, sx)
+            run(*static_in)
             torch.cuda.synchronize()
             mode = 'cuda-graph (whole step captured by the caller)'
         except Exception as e:                                         # noqa: BLE001
             print('train: CUDA-graph capture failed, timing the eager step:', repr(e)[:300], file=sys.stderr)
             torch.cuda.synchronize()
             run, mode = step, 'eager'
-            feats_d2, x0_d2 = feats_d, x0_d
-    first = run(feats_d, x0_d) if mode == 'eager' else None
     for _ in range(max(args.warmup, 3)):
-        run(feats_d, x0_d)
-    ms = timed(lambda: run(feats_d, x0_d), args.train_steps)
+        run(*inputs_d)
+    ms = timed(lambda: run(*inputs_d), args.train_steps)
     out = {}
 
     def e2e_step():
-        loss = run(feats_h.to(dev, non_blocking=True), x0_h.to(dev, non_blocking=True)) if mode == 'eager' \
-            else run(feats_h, x0_h)
+        loss = run(*[t.to(dev, non_blocking=True) for t in inputs_h]) if mode == 'eager' else run(*inputs_h)
         out['loss'] = loss.item()                                    # device -> host read of the step result
     ms_e2e = timed(e2e_step, args.train_steps)
     if world > 1:
         parallel.disable_grad_allreduce()
-    fl = B * (3 * UNET_FLOP_PER_SAMPLE + 3 * 203.7e6)                # fwd + bwd (dgrad + wgrad) of the two hot modules
+    fl = B * (FULL_TRAIN_FLOP_PER_SAMPLE if full else (3 * UNET_FLOP_PER_SAMPLE + 3 * 203.7e6))
+    what = ('FULL image model (CLEVRTex config): ResNet18-GN encoder fwd+bwd, SlotAttention(3 it), frozen VQ-VAE encoder, '
+            'q_sample, UNet(134M) fwd+bwd (dropout 0.1), eps-MSE, gradient all-reduce (bucketed, overlapped), fused Adam; '
+            'synthetic images; pos-embed / token MLP / quant_conv are the small PyTorch ops the reference also uses'
+            if full else 'SlotAttention(3 it) + UNet(134M) forward+backward (dropout 0.1) + gradient all-reduce + fused Adam; '
+            'encoder features / VQ latents synthetic (hot modules only)')
     return {'metric': 'train_step_samples_per_sec', 'value': B * world * args.train_steps / (ms / 1e3), 'unit': 'samples/s',
             'ms_per_step': ms / args.train_steps, 'per_gpu_batch': B, 'global_batch': B * world,
             'e2e_value': B * world * args.train_steps / (ms_e2e / 1e3),
-            'h2d_bytes_per_step': (feats_h.numel() + x0_h.numel()) * 4, 'd2h_bytes_per_step': 4,
+            'h2d_bytes_per_step': sum(t.numel() for t in inputs_h) * 4, 'd2h_bytes_per_step': 4,
             'gpu_launches_per_step': launches, 'loss': out.get('loss'), 'mode': mode,
             'algorithmic_tflops': fl * args.train_steps / (ms / 1e3) / 1e12,
-            'what': 'SlotAttention(3 it) + UNet(134M) forward+backward (dropout 0.1) + gradient all-reduce + fused Adam; '
-                    'encoder features / VQ latents synthetic'}
+            'what': what}
 
 
 def profile_once(args):
@@ -633,7 +726,7 @@ def reference_step(model, feats, slots0, batch):
         return model.dm_decoder.generate_imgs(cond=slots, batch_size=batch, use_dpm=True, verbose=False)
 
 
-def gpu_baseline(dev, batch):
+def gpu_baseline(dev, batch, train_batch=0):
     """The honest bar: the reference's eager PyTorch path on THIS GPU, same step, same batch; PyTorch's stock
     TF32 policy (cuDNN convolutions TF32, matmul fp32) and TF32 everywhere (the fastest setting a user can pick)."""
     model = load_reference_model(dev)
@@ -658,6 +751,33 @@ def gpu_baseline(dev, batch):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 2
         out[name] = {'value': batch * NFE / (ms / 1e3), 'ms_per_step': ms}
+    if train_batch > 0:
+        # the reference's own full training step (SADiffusion.forward -> calc_train_loss -> backward, Adam over every
+        # trainable parameter; img_based/method.py, nerv trainer: eager, no graph capture), same batch as our `train` block
+        model.train()
+        img = torch.randn(train_batch, 3, 128, 128, generator=g).clamp_(-1, 1).to(dev)
+        opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=1e-4)
+
+        def ref_train_step():
+            data = {'img': img}
+            loss = model.calc_train_loss(data, model(data))['denoise_loss']
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            opt.step()
+        for name, mm, cd in (('train_tf32_stock', False, True), ('train_tf32_all', True, True)):
+            torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = mm, cd
+            for _ in range(2):
+                ref_train_step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                ref_train_step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 3
+            out[name] = {'value': train_batch / (ms / 1e3), 'unit': 'samples/s', 'ms_per_step': ms, 'per_gpu_batch': train_batch}
+        del opt
     torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = saved
     del model
     torch.cuda.empty_cache()
