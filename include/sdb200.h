@@ -96,9 +96,19 @@ typedef struct SdbGemm {
                              sdb_pack_zero_up2: fp32 exponent range, ~16 mantissa bits) instead of the FP16 split.
                              tcgen05 kind::f16 takes ONE input format: a_bf16 must equal w_bf16 */
   float corr_scale;       /* passes == 2: 2^-s with s = el(A) + eh(W) = eh(A) + el(W) (= 12 + wexp of the packed weight) */
-  int32_t reserved0;
+  int32_t gsum_cb;        /* channels per GroupNorm partial-sum block of `gsum`: 0 or 4 = [M/rows_per_group][N/4][2]; 2 =
+                             [..][N/2][2] (64-channel layers with 32 groups: ResNet stem / layer1, VQ-VAE 64-channel levels) */
   int64_t w_plane_stride; /* halves between the hi and lo plane of W; 0 = N*K (a whole packed tensor).  Non-zero when W is
                              a row range of a larger packed tensor (per-sample K / V^T operands of the VQ-VAE AttnBlock) */
+  /* block-diagonal ("batched") products in one launch: rows [b*batch_rows, (b+1)*batch_rows) of A meet the W operand
+   * shifted by b*w_row_step rows and b*w_k_step columns; W is then a [w_rows, w_cols] packed tensor (N, K = the per-batch
+   * extents).  S_b = q_b k_b^T: w_row_step = N; O_b = P_b v_b with v^T stored [C, B*L]: w_k_step = K.  batch_rows = 0: off;
+   * batch_rows % 256 == 0. */
+  int32_t batch_rows, w_row_step, w_k_step;
+  float alpha;            /* C = alpha * (A W^T) + bias + ...; 0 means 1.  Power-of-two operand scalings are undone here: the
+                             softmax probabilities of the VQ-VAE AttnBlock are packed as 2^12 P (sdb_softmax_pack out_scale) so
+                             that their fp16 lo plane stays out of the subnormal range, O = 2^-12 (2^12 P) V */
+  int64_t w_rows, w_cols;
 } SdbGemm;
 
 int sdb_gemm(const SdbGemm* p, void* stream);
@@ -152,9 +162,11 @@ int sdb_groupnorm_apply_pack_dropout(const float* x1, int64_t C1, const float* x
  * [B, C/4, 2] (zero it first) -- the same partial sums sdb_gemm's `gsum` epilogue emits, for activations that no GEMM
  * produced (output of sdb_conv3_in, unet.py:408), so their GroupNorm consumers can use the fused statistics path */
 int sdb_channel_block_sums(const float* x, int64_t C, float* gsum, int64_t B, int64_t HW, void* stream);
-/* partial sums -> stats [B,G,2] (mean, rstd) */
+/* partial sums -> stats [B,G,2] (mean, rstd); sdb_groupnorm_finalize_cb: sums in blocks of cb channels (2 or 4) */
 int sdb_groupnorm_finalize(const float* gsum1, int64_t C1, const float* gsum2, int64_t C2, float* stats, int64_t B,
                            int64_t HW, int G, float eps, void* stream);
+int sdb_groupnorm_finalize_cb(const float* gsum, int64_t C, float* stats, int64_t B, int64_t HW, int G, float eps, int cb,
+                              void* stream);
 /* GEGLU.proj weight [2F,K] (+ bias [2F]) -> packed rows interleaved [16 a | 16 g] per 32-row chunk (+ permuted bias),
  * the operand layout of sdb_gemm's `geglu` epilogue (attention.py:39-48) */
 int sdb_pack_weight_geglu(const float* w, const float* bias, void* out, float* bias_out, int64_t F, int64_t K,
@@ -358,8 +370,10 @@ int sdb_groupnorm_add_relu(const float* h, const float* stats_h, const float* ga
                            void* out_packed, int64_t B, int64_t HW, int64_t C, int G, void* stream);
 
 /* softmax over the last dim of x [M, N] (ldx) * scale, then pack: the P operand of the single-head attention of the
- * VQ-VAE AttnBlock (modules.py:136-139: w_ = softmax(q k^T * C^-0.5)); N <= 4096, N % 4 == 0 */
-int sdb_softmax_pack(const float* x, int64_t ldx, float scale, void* out, int64_t M, int64_t N, void* stream);
+ * VQ-VAE AttnBlock (modules.py:136-139: w_ = softmax(q k^T * C^-0.5)), multiplied by out_scale (a power of two) before
+ * the fp16 hi/lo split; N <= 4096, N % 4 == 0 */
+int sdb_softmax_pack(const float* x, int64_t ldx, float scale, float out_scale, void* out, int64_t M, int64_t N,
+                     void* stream);
 
 /* ------------------------------------------------------------------ boundary fusions (csrc/boundary.cu)
  * q_sample: x_t[b] = sqrt_abar[t[b]] * x0[b] + sqrt_1m_abar[t[b]] * eps[b], rows of n = C*H*W floats (n % 4 == 0); the two

@@ -22,7 +22,9 @@ class SdbGemm(Structure):
         ('M', c_int32), ('N', c_int32), ('K', c_int32), ('mode', c_int32), ('B', c_int32), ('H', c_int32),
         ('W', c_int32), ('C', c_int32), ('rows_per_group', c_int32), ('passes', c_int32), ('relu', c_int32),
         ('out_packed', c_void_p), ('gsum', c_void_p), ('out_plane_stride', c_int64), ('out_act', c_int32),
-        ('geglu', c_int32), ('a_bf16', c_int32), ('w_bf16', c_int32), ('corr_scale', c_float), ('reserved0', c_int32), ('w_plane_stride', c_int64),
+        ('geglu', c_int32), ('a_bf16', c_int32), ('w_bf16', c_int32), ('corr_scale', c_float), ('gsum_cb', c_int32), ('w_plane_stride', c_int64),
+        ('batch_rows', c_int32), ('w_row_step', c_int32), ('w_k_step', c_int32), ('alpha', c_float),
+        ('w_rows', c_int64), ('w_cols', c_int64),
     ]
 
 
@@ -46,7 +48,7 @@ SIGNATURES = {
     'sdb_pack_weight_conv3_fmt': (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p]),
     'sdb_set_pack_mode': (c_int, [c_int, c_void_p]),
     'sdb_groupnorm_add_relu': (c_int, [c_void_p] * 10 + [c_int64, c_int64, c_int64, c_int, c_void_p]),
-    'sdb_softmax_pack': (c_int, [c_void_p, c_int64, c_float, c_void_p, c_int64, c_int64, c_void_p]),
+    'sdb_softmax_pack': (c_int, [c_void_p, c_int64, c_float, c_float, c_void_p, c_int64, c_int64, c_void_p]),
     'sdb_q_sample': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     'sdb_mse_loss_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     'sdb_mse_loss_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
@@ -66,6 +68,7 @@ SIGNATURES = {
     'sdb_channel_block_sums': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p]),
     'sdb_groupnorm_finalize': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int,
                                        c_float, c_void_p]),
+    'sdb_groupnorm_finalize_cb': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_float, c_int, c_void_p]),
     'sdb_pack_weight_geglu': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     'sdb_pack_nhwc': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int64,
                               c_int, c_void_p]),

@@ -176,13 +176,13 @@ def linear_node(tp, a, w, wT_fn, dW, db, bias=None, residual=None, relu=False, n
 
 
 def conv3_node(tp, a, w, wdg_fn, dWp, db, geo, bias=None, rowvec=None, demb=None, residual=None, need_da=True,
-               stride2=False, gsum=None, cin_w=None):
+               stride2=False, gsum=None, cin_w=None, gsum_cb=4):
     """3x3 conv as implicit GEMM.  a: packed NHWC operand (phase split for stride 2); geo = (B, H, W, C) OUTPUT size and
     input channels.  dWp: gradient view of the conv weight [Cout, Cin_w, 3, 3]."""
     B, H, W, C = geo
     mode = SDB_A_CONV3S2 if stride2 else SDB_A_CONV3
     y = ops.gemm(a, w, bias=bias, rowvec=rowvec, rows_per_group=H * W, residual=residual, conv=(mode, B, H, W, C),
-                 gsum=gsum)
+                 gsum=gsum, gsum_cb=gsum_cb)
 
     def bw():
         dy = tp.pop(y)

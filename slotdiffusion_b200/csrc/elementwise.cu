@@ -379,6 +379,25 @@ __global__ void groupnorm_finalize_kernel(const float* __restrict__ gsum1, int C
   stats[i * 2 + 1] = rsqrtf(fmaxf(ss * inv_n - mean * mean, 0.f) + eps);
 }
 
+// the same for sums kept in blocks of cb channels (2: the 64-channel levels with 32 groups)
+__global__ void groupnorm_finalize_cb_kernel(const float* __restrict__ gsum, int C, float* __restrict__ stats, int64_t B,
+                                             int HW, int G, float eps, int cb) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= B * G) return;
+  const int64_t b = i / G;
+  const int g = (int)(i % G);
+  const int cpg = C / G, nb = C / cb;
+  float s = 0.f, ss = 0.f;
+  for (int kb = g * cpg / cb; kb < (g + 1) * cpg / cb; ++kb) {
+    s += gsum[(b * nb + kb) * 2];
+    ss += gsum[(b * nb + kb) * 2 + 1];
+  }
+  const float inv_n = 1.f / ((float)HW * cpg);
+  const float mean = s * inv_n;
+  stats[i * 2] = mean;
+  stats[i * 2 + 1] = rsqrtf(fmaxf(ss * inv_n - mean * mean, 0.f) + eps);
+}
+
 // GEGLU weight layout: output row r' (chunk j = r'/32) <- a-row 16j + r'%32 (r'%32 < 16) or g-row F + 16j + r'%32 - 16
 __global__ void pack_weight_geglu_kernel(const float* __restrict__ w, __half* __restrict__ out, int64_t F, int64_t K) {
   const int64_t k4 = K / 4, total = 2 * F * k4, plane = 2 * F * K;
@@ -502,8 +521,8 @@ __global__ void timestep_embedding_pack_kernel(const float* __restrict__ t, __ha
 
 // ------------------------------------------------------------------ row softmax (+ scale) -> packed operand
 // one warp per row, N <= 4096: the row lives in registers (up to 32 float4 per lane)
-__global__ void softmax_pack_kernel(const float* __restrict__ x, int64_t ldx, float scale, __half* __restrict__ out,
-                                    int64_t M, int N) {
+__global__ void softmax_pack_kernel(const float* __restrict__ x, int64_t ldx, float scale, float out_scale,
+                                    __half* __restrict__ out, int64_t M, int N) {
   const int lane = threadIdx.x & 31;
   const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -530,7 +549,7 @@ __global__ void softmax_pack_kernel(const float* __restrict__ x, int64_t ldx, fl
     }
   }
   sum = warp_sum(sum);
-  const float inv = 1.f / sum;
+  const float inv = out_scale / sum;
   const int64_t plane = M * (int64_t)N;
 #pragma unroll
   for (int i = 0; i < 32; ++i) {
@@ -945,6 +964,16 @@ extern "C" int sdb_timestep_embedding_pack(const float* t, void* out, int64_t B,
   return 0;
 }
 
+extern "C" int sdb_groupnorm_finalize_cb(const float* gsum, int64_t C, float* stats, int64_t B, int64_t HW, int G, float eps,
+                                         int cb, void* stream) {
+  SDB_REQUIRE(gsum && stats && B > 0 && HW > 0 && G > 0 && C % G == 0 && (cb == 2 || cb == 4) && (C / G) % cb == 0,
+              "sdb_groupnorm_finalize_cb: bad args C=%lld G=%d cb=%d", (long long)C, G, cb);
+  groupnorm_finalize_cb_kernel<<<(unsigned)cdiv(B * G, 128), 128, 0, as_stream(stream)>>>(gsum, (int)C, stats, B, (int)HW, G,
+                                                                                          eps, cb);
+  SDB_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int sdb_groupnorm_add_relu(const float* h, const float* stats_h, const float* gamma_h, const float* beta_h,
                                       const float* idn, const float* stats_i, const float* gamma_i, const float* beta_i,
                                       float* out, void* out_packed, int64_t B, int64_t HW, int64_t C, int G, void* stream) {
@@ -958,11 +987,13 @@ extern "C" int sdb_groupnorm_add_relu(const float* h, const float* stats_h, cons
   return 0;
 }
 
-extern "C" int sdb_softmax_pack(const float* x, int64_t ldx, float scale, void* out, int64_t M, int64_t N, void* stream) {
+extern "C" int sdb_softmax_pack(const float* x, int64_t ldx, float scale, float out_scale, void* out, int64_t M, int64_t N,
+                                void* stream) {
   SDB_REQUIRE(x && out && M > 0 && N > 0 && N % 4 == 0 && N <= 4096 && ldx % 4 == 0,
               "sdb_softmax_pack: bad args M=%lld N=%lld (N %% 4 == 0, N <= 4096)", (long long)M, (long long)N);
   const int wpb = 4;
-  softmax_pack_kernel<<<(unsigned)cdiv(M, wpb), wpb * 32, 0, as_stream(stream)>>>(x, ldx, scale, (__half*)out, M, (int)N);
+  softmax_pack_kernel<<<(unsigned)cdiv(M, wpb), wpb * 32, 0, as_stream(stream)>>>(x, ldx, scale, out_scale, (__half*)out, M,
+                                                                                  (int)N);
   SDB_LAUNCH_CHECK();
   return 0;
 }

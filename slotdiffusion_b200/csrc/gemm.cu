@@ -90,6 +90,9 @@ struct GemmArgs {
   int ctiles;           // WGRAD modes: channel blocks per tap
   int a_bf16, w_bf16;   // operand planes hold bf16 (gradient operands) instead of fp16
   float corr_scale;     // passes == 2: C = D1 + corr_scale * D2
+  float alpha;          // accumulator scale (1 unless the caller pre-scaled an operand by a power of two)
+  int gsum_cb;          // channels per GroupNorm partial-sum block (4, or 2 for the 64-channel / 32-group layers)
+  int batch_rows, w_row_step, w_k_step;   // block-diagonal batching (sdb200.h)
   int acc_two;          // two accumulator stages (epilogue of tile i overlaps the main loop of tile i+1); 0: passes == 2
                         // with bn > 128, where D1 | D2 fill all 512 TMEM columns (long-K tiles: the exposed epilogue costs
                         // less than the shared-memory traffic of narrower tiles)
@@ -179,7 +182,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
           b0 = int(m0 / rows_per_img);
           y0 = int((m0 % rows_per_img) / g.W);
         }
-        const int nrow = tn * g.bn + (int)rank * g.bnl;
+        const int bidx = g.batch_rows ? (int)(((long long)tm * g.tile_rows) / g.batch_rows) : 0;
+        const int nrow = tn * g.bn + (int)rank * g.bnl + bidx * g.w_row_step;
+        const int wk0 = bidx * g.w_k_step;
         for (int ks = ks_begin; ks < ks_end; ++ks) {
           mbar_wait(&ctl.empty[stage], phase ^ 1);
           uint8_t* base = ring + (size_t)stage * g.stage_bytes;
@@ -248,25 +253,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
             }
           } else if (CG == 2) {
             tma_load_5d_pair(a_hi, &map_a_hi, &ctl.full[stage], c0, cx, cy, c3, c4);
-            tma_load_2d_pair(b_hi, &map_b_hi, &ctl.full[stage], ks * BK, nrow);
+            tma_load_2d_pair(b_hi, &map_b_hi, &ctl.full[stage], wk0 + ks * BK, nrow);
             if (three) {
               tma_load_5d_pair(a_lo, &map_a_lo, &ctl.full[stage], c0, cx, cy, c3, c4);
-              tma_load_2d_pair(b_lo, &map_b_lo, &ctl.full[stage], ks * BK, nrow);
+              tma_load_2d_pair(b_lo, &map_b_lo, &ctl.full[stage], wk0 + ks * BK, nrow);
             }
             if (f8c) {   // second e4m3 half-plane: half a 16-bit tile further on
               tma_load_5d_pair(a_lo + TILE_A_BYTES / 2, &map_a_l8, &ctl.full[stage], c0, cx, cy, c3, c4);
-              tma_load_2d_pair(b_lo + b_tile_bytes / 2, &map_b_l8, &ctl.full[stage], ks * BK, nrow);
+              tma_load_2d_pair(b_lo + b_tile_bytes / 2, &map_b_l8, &ctl.full[stage], wk0 + ks * BK, nrow);
             }
           } else {
             tma_load_5d(a_hi, &map_a_hi, &ctl.full[stage], c0, cx, cy, c3, c4);
-            tma_load_2d(b_hi, &map_b_hi, &ctl.full[stage], ks * BK, nrow);
+            tma_load_2d(b_hi, &map_b_hi, &ctl.full[stage], wk0 + ks * BK, nrow);
             if (three) {
               tma_load_5d(a_lo, &map_a_lo, &ctl.full[stage], c0, cx, cy, c3, c4);
-              tma_load_2d(b_lo, &map_b_lo, &ctl.full[stage], ks * BK, nrow);
+              tma_load_2d(b_lo, &map_b_lo, &ctl.full[stage], wk0 + ks * BK, nrow);
             }
             if (f8c) {
               tma_load_5d(a_lo + TILE_A_BYTES / 2, &map_a_l8, &ctl.full[stage], c0, cx, cy, c3, c4);
-              tma_load_2d(b_lo + b_tile_bytes / 2, &map_b_l8, &ctl.full[stage], ks * BK, nrow);
+              tma_load_2d(b_lo + b_tile_bytes / 2, &map_b_l8, &ctl.full[stage], wk0 + ks * BK, nrow);
             }
           }
           if (++stage == g.stages) { stage = 0; phase ^= 1; }
@@ -451,6 +456,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
           for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(fmaf(g.corr_scale, __uint_as_float(r2[k]), __uint_as_float(r[k])));
         }
         tmem_ld_wait();
+        if (g.alpha != 1.f) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(__uint_as_float(r[k]) * g.alpha);
+        }
         if (rows_valid <= 0) continue;       // warp-uniform
         // thread `lane` holds row (q*32+lane), columns cb..cb+31 -> stage (swizzled) so that 8 lanes cover one
         // 128-B row segment on the way out
@@ -491,6 +500,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
           float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
           if (col_ok && first && g.bias) bias4 = *reinterpret_cast<const float4*>(g.bias + n);
           float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;   // GroupNorm partial sums of rows 0..15 / 16..31
+          float s0b = 0.f, q0b = 0.f, s1b = 0.f, q1b = 0.f;   // gsum_cb == 2: second channel pair (.z, .w) of the float4
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int rr = i * 4 + rsub;
@@ -505,9 +515,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
                 else *reinterpret_cast<float4*>(dst) = v;
               }
               if (g.gsum) {
-                const float s = (v.x + v.y) + (v.z + v.w);
-                const float qq = (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
-                if (i < 4) { s0 += s; q0 += qq; } else { s1 += s; q1 += qq; }
+                if (g.gsum_cb == 2) {
+                  const float sa = v.x + v.y, qa = v.x * v.x + v.y * v.y, sb = v.z + v.w, qb = v.z * v.z + v.w * v.w;
+                  if (i < 4) { s0 += sa; q0 += qa; s0b += sb; q0b += qb; } else { s1 += sa; q1 += qa; s1b += sb; q1b += qb; }
+                } else {
+                  const float s = (v.x + v.y) + (v.z + v.w);
+                  const float qq = (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+                  if (i < 4) { s0 += s; q0 += qq; } else { s1 += s; q1 += qq; }
+                }
               }
               if (g.out_packed) {
                 if (g.out_act == 1) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
@@ -522,20 +537,32 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
             s1 += __shfl_xor_sync(0xffffffffu, s1, 8);  q1 += __shfl_xor_sync(0xffffffffu, q1, 8);
             s0 += __shfl_xor_sync(0xffffffffu, s0, 16); q0 += __shfl_xor_sync(0xffffffffu, q0, 16);
             s1 += __shfl_xor_sync(0xffffffffu, s1, 16); q1 += __shfl_xor_sync(0xffffffffu, q1, 16);
+            if (g.gsum_cb == 2) {
+              s0b += __shfl_xor_sync(0xffffffffu, s0b, 8);  q0b += __shfl_xor_sync(0xffffffffu, q0b, 8);
+              s1b += __shfl_xor_sync(0xffffffffu, s1b, 8);  q1b += __shfl_xor_sync(0xffffffffu, q1b, 8);
+              s0b += __shfl_xor_sync(0xffffffffu, s0b, 16); q0b += __shfl_xor_sync(0xffffffffu, q0b, 16);
+              s1b += __shfl_xor_sync(0xffffffffu, s1b, 16); q1b += __shfl_xor_sync(0xffffffffu, q1b, 16);
+            }
             if (rsub == 0 && col_ok) {
               const unsigned b0 = (unsigned)row0 / g.rows_per_group;
               const unsigned b1 = (unsigned)(row0 + 16) / g.rows_per_group;
+              // block index of this thread's first channel: n / cb; blocks per row: N / cb
+              const unsigned nb = g.gsum_cb == 2 ? ((unsigned)g.N >> 1) : n4;
+              const unsigned ib = g.gsum_cb == 2 ? ((unsigned)n >> 1) : ((unsigned)n >> 2);
               if (b1 == b0 || rows_valid <= 16) {
-                float* p = g.gsum + ((long long)b0 * n4 + (n >> 2)) * 2;
+                float* p = g.gsum + ((long long)b0 * nb + ib) * 2;
                 atomicAdd(p, s0 + s1);
                 atomicAdd(p + 1, q0 + q1);
+                if (g.gsum_cb == 2) { atomicAdd(p + 2, s0b + s1b); atomicAdd(p + 3, q0b + q1b); }
               } else {
-                float* p = g.gsum + ((long long)b0 * n4 + (n >> 2)) * 2;
+                float* p = g.gsum + ((long long)b0 * nb + ib) * 2;
                 atomicAdd(p, s0);
                 atomicAdd(p + 1, q0);
-                p = g.gsum + ((long long)b1 * n4 + (n >> 2)) * 2;
+                if (g.gsum_cb == 2) { atomicAdd(p + 2, s0b); atomicAdd(p + 3, q0b); }
+                p = g.gsum + ((long long)b1 * nb + ib) * 2;
                 atomicAdd(p, s1);
                 atomicAdd(p + 1, q1);
+                if (g.gsum_cb == 2) { atomicAdd(p + 2, s1b); atomicAdd(p + 3, q1b); }
               }
             }
           }
@@ -696,6 +723,18 @@ extern "C" int sdb_gemm(const SdbGemm* p, void* stream) {
   g.out_plane = p->out_plane_stride; g.out_act = p->out_act;
   g.a_bf16 = p->a_bf16 != 0; g.w_bf16 = p->w_bf16 != 0;
   g.corr_scale = p->corr_scale;
+  g.alpha = p->alpha == 0.f ? 1.f : p->alpha;
+  g.gsum_cb = p->gsum_cb == 2 ? 2 : 4;
+  SDB_REQUIRE(p->gsum_cb == 0 || p->gsum_cb == 2 || p->gsum_cb == 4, "sdb_gemm: gsum_cb must be 0, 2 or 4");
+  g.batch_rows = p->batch_rows; g.w_row_step = p->w_row_step; g.w_k_step = p->w_k_step;
+  if (p->batch_rows) {
+    SDB_REQUIRE(p->mode == SDB_A_PLAIN && p->batch_rows % 256 == 0 && p->M % p->batch_rows == 0 && p->w_rows > 0 && p->w_cols > 0 &&
+                    p->w_cols % 8 == 0 && p->passes != 2 && p->w_plane_stride == 0,
+                "sdb_gemm: batched form needs plain mode, batch_rows %% 256 == 0, M %% batch_rows == 0, w_rows / w_cols");
+    const long long nb = p->M / p->batch_rows;
+    SDB_REQUIRE((nb - 1) * p->w_row_step + p->N <= p->w_rows && (nb - 1) * p->w_k_step + p->K <= p->w_cols,
+                "sdb_gemm: batched W extents exceed the [w_rows, w_cols] tensor");
+  }
   g.debug = env_int("SDB_GEMM_DEBUG", 0);
   g.ldc = p->ldc; g.ldv = p->ldv; g.ldr = p->ldr;
   g.M = p->M; g.N = p->N; g.K = p->K; g.mode = p->mode; g.passes = p->passes; g.relu = p->relu;
@@ -790,7 +829,7 @@ extern "C" int sdb_gemm(const SdbGemm* p, void* stream) {
   g.n_tiles_m = (int)cdiv(n_tiles_m1, cg);
   const int ksteps = g.kblocks * g.ntaps;
   const int units = sms / cg;
-  const bool can_split = !p->relu && !p->out_packed && !p->gsum;   // those epilogues need the complete sum
+  const bool can_split = !p->relu && !p->out_packed && !p->gsum && !p->batch_rows;   // those epilogues need the complete sum
   if (!wgrad_mode && !can_split && env_int("SDB_GEMM_NARROW", 1)) {
     // under-filled grid that cannot use split-K (the GroupNorm-sum / packed / ReLU epilogues need complete sums): narrower
     // N tiles put more SMs to work.  Cost model: waves * (bn + fixed per-tile overhead worth ~64 columns).
@@ -830,7 +869,9 @@ extern "C" int sdb_gemm(const SdbGemm* p, void* stream) {
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo, ma_l8, mb_l8;   // *_lo: fp16 lo plane, or (passes 2) the e4m3 h8 half-plane
   const __half* a = reinterpret_cast<const __half*>(p->a);
   const __half* w = reinterpret_cast<const __half*>(p->w);
-  const long long w_plane = p->w_plane_stride > 0 ? (long long)p->w_plane_stride : (long long)p->N * p->K;
+  const long long w_rows = p->batch_rows ? (long long)p->w_rows : (long long)p->N;
+  const long long w_cols = p->batch_rows ? (long long)p->w_cols : (long long)p->K;
+  const long long w_plane = p->w_plane_stride > 0 ? (long long)p->w_plane_stride : w_rows * w_cols;
   int rc;
   if (p->mode == SDB_A_PLAIN) {
     uint64_t dims[5] = {(uint64_t)p->K, (uint64_t)p->M, 1, 1, 1};
@@ -882,8 +923,8 @@ extern "C" int sdb_gemm(const SdbGemm* p, void* stream) {
     if ((rc = make_map(&mb_lo, w + w_plane, 2, dims, st, box))) return rc;
     mb_l8 = mb_lo;
   } else {
-    uint64_t dims[2] = {(uint64_t)p->K, (uint64_t)p->N};
-    uint64_t st[1] = {(uint64_t)p->K * 2};
+    uint64_t dims[2] = {(uint64_t)w_cols, (uint64_t)w_rows};
+    uint64_t st[1] = {(uint64_t)w_cols * 2};
     uint32_t box[2] = {BK, (uint32_t)g.bnl};
     if ((rc = make_map(&mb_hi, w, 2, dims, st, box))) return rc;
     if (f8c) {

@@ -276,13 +276,18 @@ def groupnorm_add_relu(h, stats_h, gn_h, B, HW, idn=None, stats_i=None, gn_i=Non
     return out, pk
 
 
-def softmax_pack(x, scale=1.0):
-    """softmax(x * scale) over the last dim of x [M, N] (strided rows ok) -> Packed [M, N]."""
+SOFTMAX_PACK_SCALE = 4096.0     # probabilities of ~1e-3 would put their fp16 lo plane (2^-11 of the value) into subnormals
+
+
+def softmax_pack(x, scale=1.0, out_scale=SOFTMAX_PACK_SCALE):
+    """out_scale * softmax(x * scale) over the last dim of x [M, N] (strided rows ok) -> Packed [M, N]; the consumer GEMM
+    undoes the power-of-two out_scale with alpha = 1 / out_scale."""
     _f32(x)
     assert x.dim() == 2 and x.stride(1) == 1
     M, N = x.shape
     out = Packed.empty(M, N, x.device)
-    check(lib().sdb_softmax_pack(_p(x), x.stride(0), float(scale), _p(out.t), M, N, _stream()), 'sdb_softmax_pack')
+    check(lib().sdb_softmax_pack(_p(x), x.stride(0), float(scale), float(out_scale), _p(out.t), M, N, _stream()),
+          'sdb_softmax_pack')
     return out
 
 
@@ -351,14 +356,19 @@ _ACTS = {None: 0, 'none': 0, 'silu': 1, 'relu': 2}
 
 
 def gemm(a, w, bias=None, rowvec=None, rows_per_group=0, residual=None, relu=False, conv=None, passes=None,
-         out=None, pack_out=None, keep_c=True, gsum=None, geglu=False):
+         out=None, pack_out=None, keep_c=True, gsum=None, geglu=False, gsum_cb=4, batch=None, alpha=1.0):
     """C = A W^T (+bias)(+rowvec[row // rows_per_group])(+residual); A, W Packed.
     conv: None (plain) or (mode, B, H, W, C) with H, W the OUTPUT size (see sdb200.h).
     pack_out: None, or 'none' / 'silu' / 'relu' -- the epilogue ALSO emits act(C) as a Packed operand for the next
               GEMM; returns (C or None, Packed); keep_c=False drops the fp32 copy.
     gsum:     fp32 [M // rows_per_group, N // 4, 2] zero-initialised buffer that receives GroupNorm partial sums of C.
-    geglu:    W/bias packed by pack_weight_geglu; returns Packed [M, N/2] = a * gelu(g)."""
+    geglu:    W/bias packed by pack_weight_geglu; returns Packed [M, N/2] = a * gelu(g).
+    gsum_cb:  channels per partial-sum block of gsum (4, or 2: buffer [M // rows_per_group, N // 2, 2]).
+    batch:    (batch_rows, N, w_row_step, w_k_step): block-diagonal product in one launch -- rows [b*batch_rows, ...) of A
+              meet the [N, a.K] block of the packed tensor w at row b*w_row_step, column b*w_k_step (sdb200.h)."""
     N, K = w.rows, w.K
+    if batch is not None:
+        N, K = batch[1], a.K
     if conv is None:
         M, mode, geo = a.rows, SDB_A_PLAIN, (0, 0, 0, 0)
         assert a.K == K, (a.K, K)
@@ -401,6 +411,11 @@ def gemm(a, w, bias=None, rowvec=None, rows_per_group=0, residual=None, relu=Fal
         g.out_plane_stride = packed.rows * packed.K
         g.out_act = _ACTS[pack_out]
     g.gsum = gsum.data_ptr() if gsum is not None else None
+    g.gsum_cb = gsum_cb
+    g.alpha = float(alpha)
+    if batch is not None:
+        g.batch_rows, g.w_row_step, g.w_k_step = batch[0], batch[2], batch[3]
+        g.w_rows, g.w_cols = w.rows, w.K
     g.geglu = int(geglu)
     g.a_bf16, g.w_bf16 = int(a.bf16), int(w.bf16)
     check(lib().sdb_gemm(ctypes.byref(g), _stream()), 'sdb_gemm')
@@ -451,6 +466,13 @@ def groupnorm_finalize(gsum1, gsum2, C1, C2, B, HW, G, eps):
     stats = torch.empty(B, G, 2, dtype=torch.float32, device=gsum1.device)
     check(lib().sdb_groupnorm_finalize(_p(gsum1), C1, _p(gsum2), C2, _p(stats), B, HW, G, eps, _stream()),
           'sdb_groupnorm_finalize')
+    return stats
+
+
+def groupnorm_finalize_cb(gsum, C, B, HW, G, eps, cb):
+    """partial sums in blocks of cb channels (sdb_gemm gsum_cb) -> stats [B, G, 2] (mean, rstd)"""
+    stats = torch.empty(B, G, 2, dtype=torch.float32, device=gsum.device)
+    check(lib().sdb_groupnorm_finalize_cb(_p(gsum), C, _p(stats), B, HW, G, eps, cb, _stream()), 'sdb_groupnorm_finalize_cb')
     return stats
 
 

@@ -107,16 +107,17 @@ class ResNet(nn.Module):
     # ------------------------------------------------------------------------------------------------ schedule
     def _stats(self, t, gs, gn, B, HW):
         if gs is not None:
-            return ops.groupnorm_finalize(gs, None, t.shape[1], 0, B, HW, gn.num_groups, gn.eps)
+            return ops.groupnorm_finalize_cb(gs[0], t.shape[1], B, HW, gn.num_groups, gn.eps, gs[1])
         return ops.groupnorm_stats(t, None, B, HW, gn.num_groups, gn.eps)
 
     @staticmethod
     def _gs(B, HW, C, dev):
-        """GroupNorm partial sums from the producing GEMM epilogue (4-channel blocks: C % 128 == 0, i.e. layer2+);
-        the 64-channel levels (2 channels per group) take the exact statistics kernel."""
-        if B * HW < 4096 or HW % 16 or C % 128:
+        """(GroupNorm partial sums accumulated by the producing GEMM epilogue, channels per block): blocks of 4 channels,
+        or of 2 for the 64-channel stem / layer1 (32 groups of 2 channels).  None: the exact two-pass statistics kernel."""
+        if B * HW < 4096 or HW % 16 or C % 64:
             return None
-        return torch.zeros(B * (C // 4) * 2, dtype=torch.float32, device=dev)
+        cb = 4 if C % 128 == 0 else 2
+        return torch.zeros(B * (C // cb) * 2, dtype=torch.float32, device=dev), cb
 
     def _block_end(self, tp, h, st_h, gn_h, idn, st_i, gn_i, B, HW, want_packed):
         """out = relu(GN(h) + identity) as fp32 rows (+ packed operand); backward through both normalisations."""
@@ -150,10 +151,11 @@ class ResNet(nn.Module):
         gs = self._gs(B, H * W, Cout, a.t.device)
         if G is None:
             mode = ops.SDB_A_CONV3S2 if stride2 else ops.SDB_A_CONV3
-            y = ops.gemm(a, wc.conv3(key, conv.weight), conv=(mode, B, H, W, Cin), gsum=gs, rows_per_group=H * W)
+            y = ops.gemm(a, wc.conv3(key, conv.weight), conv=(mode, B, H, W, Cin), gsum=gs[0] if gs else None,
+                         gsum_cb=gs[1] if gs else 4, rows_per_group=H * W)
         else:
             y = conv3_node(tp, a, wc.conv3(key, conv.weight), lambda: _conv_dgrad(wc, key, conv.weight), G.view(conv.weight),
-                           None, (B, H, W, Cin), stride2=stride2, gsum=gs)
+                           None, (B, H, W, Cin), stride2=stride2, gsum=gs[0] if gs else None, gsum_cb=gs[1] if gs else 4)
         return y, gs
 
     def _downsample(self, tp, xp, ds, key, B, H, W, Cin):
@@ -169,14 +171,15 @@ class ResNet(nn.Module):
         w_fwd = wc._get((key, 'ds'), (conv.weight,), lambda: ops.pack_weight_conv3(expand()))
         gs = self._gs(B, H * W, Cout, xp.t.device)
         if G is None:
-            y = ops.gemm(xp, w_fwd, conv=(ops.SDB_A_CONV3S2, B, H, W, Cin), gsum=gs, rows_per_group=H * W)
+            y = ops.gemm(xp, w_fwd, conv=(ops.SDB_A_CONV3S2, B, H, W, Cin), gsum=gs[0] if gs else None,
+                         gsum_cb=gs[1] if gs else 4, rows_per_group=H * W)
         else:
             dw3 = torch.empty(Cout, Cin, 3, 3, dtype=torch.float32, device=conv.weight.device)
             # pushed BEFORE the conv node: runs after its wgrad in the reversed replay
             tp.push(lambda: G.view(conv.weight).view(Cout, Cin).copy_(dw3[:, :, 1, 1]))
             y = conv3_node(tp, xp, w_fwd, lambda: wc._get((key, 'ds_dg'), (conv.weight,),
                                                            lambda: ops.pack_weight_conv3_dgrad(expand())),
-                           dw3, None, (B, H, W, Cin), stride2=True, gsum=gs)
+                           dw3, None, (B, H, W, Cin), stride2=True, gsum=gs[0] if gs else None, gsum_cb=gs[1] if gs else 4)
         return y, self._stats(y, gs, gn, B, H * W), gn
 
     def _run(self, tp, x):
@@ -184,14 +187,17 @@ class ResNet(nn.Module):
         B, _, H, W = x.shape
         dev = x.device
         # ---- stem: conv1 -> bn1 -> relu (resnet.py:288-291; maxpool is the identity for small inputs)
+        gs0 = None
         if G is None:
             zero_b = wc._get('stem_b', (self.conv1.weight,), lambda: torch.zeros(64, dtype=torch.float32, device=dev))
             h = ops.conv3_in(x.float(), self.conv1.weight, zero_b)
         else:       # training: channels zero-padded to 64 so that the stem's wgrad is the common implicit-GEMM launch
             xpk = ops.pack_nchw_pad(x.float(), 64)
             w_in = wc._get('stem_pad', (self.conv1.weight,), lambda: ops.pack_weight_conv3(_pad_conv(self.conv1.weight, 64, 64)))
-            h = conv3_node(tp, xpk, w_in, None, G.view(self.conv1.weight), None, (B, H, W, 64), need_da=False)
-        st = self._stats(h, None, self.bn1, B, H * W)
+            gs0 = self._gs(B, H * W, 64, dev)
+            h = conv3_node(tp, xpk, w_in, None, G.view(self.conv1.weight), None, (B, H, W, 64), need_da=False,
+                           gsum=gs0[0] if gs0 else None, gsum_cb=gs0[1] if gs0 else 4)
+        st = self._stats(h, gs0, self.bn1, B, H * W)
         layers = [self.layer1, self.layer2, self.layer3] + ([self.layer4] if self.use_layer4 else [])
         blocks = [b for layer in layers for b in layer]
         nxt_s2 = blocks[0].stride == 2

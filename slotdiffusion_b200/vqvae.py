@@ -96,27 +96,36 @@ class _Exec:
         self._off = 0
 
     def gs(self, B, HW, C):
-        if B * HW < 4096 or HW % 16 or C % 128:
+        """(partial-sum buffer, channels per block) for an activation a GEMM epilogue produces: blocks of 4 channels, or of 2
+        for the 64-channel levels (32 groups of 2 channels)."""
+        if B * HW < 4096 or HW % 16 or C % 64:
             return None
-        n = B * (C // 4) * 2
+        cb = 4 if C % 128 == 0 else 2
+        n = B * (C // cb) * 2
         if self._off + n > self._arena.numel():
             return None
         v = self._arena[self._off:self._off + n]
         self._off += n
-        return v
+        return v, cb
+
+    def stats(self, x, gn, B):
+        HW = x.H * x.W
+        if x.gs is not None:
+            return ops.groupnorm_finalize_cb(x.gs[0], x.C, B, HW, gn.num_groups, gn.eps, x.gs[1])
+        return ops.groupnorm_stats(x.t, None, B, HW, gn.num_groups, gn.eps)
 
     def norm(self, x, gn, B, silu):
         HW = x.H * x.W
-        if x.gs is not None:
-            return ops.groupnorm_pack_fused(x.t, None, gn.weight, gn.bias, B, HW, gn.num_groups, gn.eps, silu, gsum1=x.gs)
-        stats = ops.groupnorm_stats(x.t, None, B, HW, gn.num_groups, gn.eps)
-        return ops.groupnorm_pack_fused(x.t, None, gn.weight, gn.bias, B, HW, gn.num_groups, gn.eps, silu, stats=stats)
+        if x.gs is not None and x.gs[1] == 4:
+            return ops.groupnorm_pack_fused(x.t, None, gn.weight, gn.bias, B, HW, gn.num_groups, gn.eps, silu, gsum1=x.gs[0])
+        return ops.groupnorm_pack_fused(x.t, None, gn.weight, gn.bias, B, HW, gn.num_groups, gn.eps, silu,
+                                        stats=self.stats(x, gn, B))
 
     def conv3(self, p, conv, key, B, H, W, Cin, residual=None, mode=SDB_A_CONV3):
         Cout = conv.weight.shape[0]
         gs = self.gs(B, H * W, Cout)
         y = ops.gemm(p, self.wc.conv3(key, conv.weight), bias=conv.bias, residual=residual, conv=(mode, B, H, W, Cin),
-                     gsum=gs, rows_per_group=H * W)
+                     gsum=gs[0] if gs else None, gsum_cb=gs[1] if gs else 4, rows_per_group=H * W)
         return Act(y, H, W, Cout, gs)
 
     def conv1(self, p, conv, key, residual=None):
@@ -137,35 +146,38 @@ class _Exec:
         return self.conv3(self.norm(h, m.norm2, B, True), m.conv2, (key, 'c2'), B, H, W, m.out_channels, residual=xs)
 
     def attn(self, m, x, B):
-        """modules.py:130-153: single-head attention over the H*W tokens with head dim C.  q | k in one GEMM over the whole
-        batch; per sample: S = q k^T and O = softmax(S C^-0.5) v as tcgen05 GEMMs (the other sample's packed rows are the
-        'weight' operand), v^T produced directly as W_v GN(x)^T so no transpose pass exists; v's bias is added after the
-        weighted sum (softmax rows sum to one)."""
+        """modules.py:130-153: single-head attention over the H*W tokens with head dim C.  q | k | v in one GEMM over the
+        whole batch, then S = q k^T, softmax(S C^-0.5) and O = P v as tcgen05 GEMMs."""
         if not isinstance(m, AttnBlock):
             return x
         key, C, L = id(m), x.C, x.H * x.W
         pn = self.norm(x, m.norm, B, False)
-        wqk = self.wc.linear((key, 'qk'), m.q.weight, m.k.weight)
-        qk = ops.gemm(pn, wqk, bias=self.wc.cat((key, 'qkb'), m.q.bias, m.k.bias))
-        qp, kp = ops.pack_rows(qk[:, :C]), ops.pack_rows(qk[:, C:])
-        wv_a = self.wc._get((key, 'vA'), (m.v.weight,), lambda: ops.pack_weight(m.v.weight.detach().reshape(C, C).contiguous()))
-        o = torch.empty(B * L, C, dtype=torch.float32, device=x.t.device)
-        s = torch.empty(L, L, dtype=torch.float32, device=x.t.device)
-        vt = torch.empty(C, L, dtype=torch.float32, device=x.t.device)
+        wqkv = self.wc.linear((key, 'qkv'), m.q.weight, m.k.weight, m.v.weight)
+        qkv = ops.gemm(pn, wqkv, bias=self.wc.cat((key, 'qkvb'), m.q.bias, m.k.bias, m.v.bias))
         scale = float(C) ** -0.5
-        for b in range(B):
-            r0, r1 = b * L, (b + 1) * L
-            ops.gemm(qp.row_range(r0, r1), kp.row_range(r0, r1), out=s)
-            ops.gemm(wv_a, pn.row_range(r0, r1), out=vt)
-            ops.gemm(ops.softmax_pack(s, scale), ops.pack_rows(vt), bias=m.v.bias, out=o[r0:r1])
+        if L % 256 == 0:
+            # all samples in ONE launch per product: block-diagonal tcgen05 GEMMs (sdb200.h SdbGemm.batch_rows) --
+            # S_b = q_b k_b^T (the W operand advances L rows per sample), O_b = P_b v_b with v^T stored [C, B*L] (the W
+            # operand advances L columns per sample)
+            qp, kp = ops.pack_rows(qkv[:, :C]), ops.pack_rows(qkv[:, C:2 * C])
+            vt = ops.transpose_packed(ops.pack_rows(qkv[:, 2 * C:]))                 # [C, B*L]
+            s = ops.gemm(qp, kp, batch=(L, L, L, 0))                                 # [B*L, L]
+            o = ops.gemm(ops.softmax_pack(s, scale), vt, batch=(L, C, 0, L), alpha=1.0 / ops.SOFTMAX_PACK_SCALE)   # [B*L, C]
+        else:       # ragged token counts: one sample at a time, the other sample's packed rows as the 'weight' operand
+            qp, kp = ops.pack_rows(qkv[:, :C]), ops.pack_rows(qkv[:, C:2 * C])
+            o = torch.empty(B * L, C, dtype=torch.float32, device=x.t.device)
+            s = torch.empty(L, L, dtype=torch.float32, device=x.t.device)
+            for b in range(B):
+                r0, r1 = b * L, (b + 1) * L
+                ops.gemm(qp.row_range(r0, r1), kp.row_range(r0, r1), out=s)
+                vt = ops.transpose_packed(ops.pack_rows(qkv[r0:r1, 2 * C:]))         # [C, L]
+                ops.gemm(ops.softmax_pack(s, scale), vt, out=o[r0:r1], alpha=1.0 / ops.SOFTMAX_PACK_SCALE)
         y = self.conv1(ops.pack_rows(o), m.proj_out, (key, 'po'), residual=x.t)
         return Act(y, x.H, x.W, C, None)
 
     def head(self, x, gn, conv, B):
         """norm_out -> swish -> conv_out (3 output channels: too thin for tensor tiles) -> NCHW"""
-        stats = ops.groupnorm_finalize(x.gs, None, x.C, 0, B, x.H * x.W, gn.num_groups, gn.eps) if x.gs is not None \
-            else ops.groupnorm_stats(x.t, None, B, x.H * x.W, gn.num_groups, gn.eps)
-        return ops.conv3_out(x.t, stats, gn.weight, gn.bias, conv.weight, conv.bias, B, x.H, x.W, gn.num_groups)
+        return ops.conv3_out(x.t, self.stats(x, gn, B), gn.weight, gn.bias, conv.weight, conv.bias, B, x.H, x.W, gn.num_groups)
 
 
 def _check_input(mod, x):

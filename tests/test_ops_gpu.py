@@ -388,3 +388,36 @@ def test_dpm_glue(ops):
     m0, m1 = rnd(B, 3, 32, 32, seed=44), rnd(B, 3, 32, 32, seed=45)
     y = ops.lincomb(x, m0, m1, 0.5, -0.25, 2.0)
     assert rel_l2(y, 0.5 * x - 0.25 * m0 + 2.0 * (m1 - m0)) < 1e-6
+
+
+@pytest.mark.parametrize('cg', [1, 2])
+def test_gemm_groupnorm_sums_two_channel_blocks(ops, gemm_env, cg):
+    """gsum_cb = 2: per-(sample, channel PAIR) sums for the 64-channel / 32-group layers (ResNet stem, VQ-VAE level 0)"""
+    gemm_env(cg, None)
+    B, HW, K, C = 3, 4096, 64, 64
+    a, w, bias = rnd(B * HW, K, seed=61), rnd(C, K, seed=62, scale=K ** -0.5), rnd(C, seed=63) * 2
+    gs = torch.zeros(B, C // 2, 2, device='cuda')
+    x = ops.gemm(ops.pack_rows(a), ops.pack_weight(w), bias=bias, gsum=gs, gsum_cb=2, rows_per_group=HW)
+    st = ops.groupnorm_finalize_cb(gs, C, B, HW, 32, 1e-5, 2)
+    assert rel_l2(st, ops.groupnorm_stats(x, None, B, HW, 32, 1e-5)) < 1e-5
+    xr = x.view(B, HW, C // 2, 2).double()
+    assert rel_l2(gs[..., 0], xr.sum((1, 3))) < 1e-5 and rel_l2(gs[..., 1], (xr * xr).sum((1, 3))) < 1e-5
+
+
+@pytest.mark.parametrize('cg', [1, 2])
+def test_gemm_block_diagonal_batches(ops, gemm_env, cg):
+    """SdbGemm.batch_rows: S_b = q_b k_b^T (W advances by rows) and O_b = P_b v_b with v^T stored [C, B*L] (W advances by
+    columns) in one launch each -- the single-head attention of the VQ-VAE AttnBlock"""
+    gemm_env(cg, None)
+    B, L, C = 3, 512, 256
+    q, k, v = rnd(B * L, C, seed=64), rnd(B * L, C, seed=65), rnd(B * L, C, seed=66)
+    s = ops.gemm(ops.pack_rows(q), ops.pack_rows(k), batch=(L, L, L, 0))
+    ref_s = torch.einsum('blc,bmc->blm', q.view(B, L, C).double(), k.view(B, L, C).double()).reshape(B * L, L)
+    assert s.shape == (B * L, L) and rel_l2(s, ref_s) < 5e-6
+    p = ops.softmax_pack(s, C ** -0.5)                       # 2^12 P: keeps the lo plane of ~1e-3 probabilities normal
+    ref_p = torch.softmax(ref_s * C ** -0.5, dim=-1)
+    assert rel_l2(p.unpack() / ops.SOFTMAX_PACK_SCALE, ref_p) < 5e-6
+    vt = ops.transpose_packed(ops.pack_rows(v))
+    o = ops.gemm(p, vt, batch=(L, C, 0, L), alpha=1.0 / ops.SOFTMAX_PACK_SCALE)
+    ref_o = torch.einsum('blm,bmc->blc', ref_p.view(B, L, L), v.view(B, L, C).double()).reshape(B * L, C)
+    assert o.shape == (B * L, C) and rel_l2(o, ref_o) < 5e-6
