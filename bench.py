@@ -185,6 +185,26 @@ def run_ours(args):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
 
+    # the same step at the other batch sizes SURVEY 8d asks for (B = 4: weight-traffic / latency bound; B = 64: the reference's
+    # evaluation batch); fewer steps, device-resident inputs
+    other = {}
+    if world == 1 and not args.no_other_batches:
+        for ob in (4, 64):
+            if ob == B:
+                continue
+            f_o, n_o = feats_d[:ob].contiguous(), noise_d[:ob].contiguous()
+            s_o = init_slots.expand(ob, -1, -1).contiguous()
+
+            def step_o():
+                with torch.no_grad():
+                    sl, _ = sa(f_o, s_o)
+                    return sampler.sample(n_o, sl)
+            for _ in range(3):
+                step_o()
+            ms_o = timed(step_o, 3)
+            other['B%d' % ob] = {'value': ob * NFE * 3 / (ms_o / 1e3), 'unit': UNIT, 'ms_per_step': ms_o / 3,
+                                 'images_per_sec': ob * 3 / (ms_o / 1e3)}
+
     # roofline of the dominant kernel (sdb200 gemm_kernel), measured live with CUDA events around every launch
     roof = gemm_roofline(unet, sampler, B, dev)
     sa_stat = time_sa(sa, feats_d, slots0, load_peaks()[0])
@@ -201,7 +221,7 @@ def run_ours(args):
             gpu_base = {'unavailable': repr(e)[:300]}
             torch.cuda.empty_cache()
 
-    train = train_hot = None
+    train = train_hot = train_video = None
     if not args.no_train:
         del feats_d, noise_d
         torch.cuda.empty_cache()
@@ -209,6 +229,9 @@ def run_ours(args):
         torch.cuda.empty_cache()
         train_hot = train_bench(args, dev, world, rank, full=False)
         torch.cuda.empty_cache()
+        if not args.no_video:
+            train_video = train_bench(args, dev, world, rank, full=True, video=6)
+            torch.cuda.empty_cache()
 
     if gpu_base and train and 'train_tf32_stock' in gpu_base:
         gpu_base['train_speedup_vs_tf32_stock'] = train['value'] / gpu_base['train_tf32_stock']['value']
@@ -249,8 +272,10 @@ def run_ours(args):
             'roofline_slot_attention': sa_stat['attend_kernel'],
             'cpu_baseline': cpu_baseline(sample_nfe=NFE, batch=4) if world == 1 else None,   # rank 0, N=1 only
             'gpu_baseline': gpu_base,
+            'other_batches': other,
             'train': train,
             'train_hot_modules': train_hot,
+            'train_video': train_video,
         }
         print(json.dumps(line))
     if world > 1:
@@ -320,13 +345,51 @@ class FullImageModel(torch.nn.Module):
         return boundary.mse_loss(self.unet(xt, t, context=slots), eps)        # ldm.py:76-77
 
 
+class FullVideoModel(FullImageModel):
+    """SAViDiffusion of BASELINE configs[2] (MOVi-D 128x128, T = 6 frames per clip, 11 slots, 2 Slot-Attention iterations per
+    frame): the image model applied per frame with the slots carried from frame to frame through the TransformerPredictor
+    (savi_diffusion.py:169-216, predictor.py:20-44: 2 layers, 4 heads, ffn 4 D, norm_first -- the reference's own
+    nn.TransformerEncoder, kept as PyTorch) and the LDM loss over all B*T frames (savi_diffusion.py: flatten(0, 1))."""
+
+    def __init__(self, dev, frames=6, iters=2):
+        super().__init__(dev)
+        from slotdiffusion_b200.slot_attention import SlotAttentionWMask
+        self.frames = frames
+        self.slot_attention = SlotAttentionWMask(D, iters, S, D, 2 * D).to(dev)
+        layer = torch.nn.TransformerEncoderLayer(d_model=D, nhead=4, dim_feedforward=4 * D, norm_first=True, batch_first=True)
+        self.predictor = torch.nn.TransformerEncoder(layer, num_layers=2, enable_nested_tensor=False).to(dev)
+
+    def eager_params(self):
+        return super().eager_params() + list(self.predictor.parameters())
+
+    def loss(self, video):
+        from slotdiffusion_b200 import boundary
+        B, T = video.shape[:2]
+        img = video.flatten(0, 1)
+        with torch.no_grad():
+            x0 = self.quant_conv(self.vq_encoder(img))
+        t = torch.randint(0, 1000, (B * T,), device=img.device)
+        eps = torch.randn_like(x0)
+        xt = boundary.q_sample(x0, t, eps, self.sqrt_abar, self.sqrt_1m_abar)
+        f = self.encoder(img)
+        f = f + self.pos_dense(self.grid).t().reshape(1, 256, 32, 32)
+        feats = self.encoder_out_layer(f.flatten(2).permute(0, 2, 1).contiguous()).unflatten(0, (B, T))
+        prev, per_frame = None, []
+        for k in range(T):                                             # savi_diffusion.py:183-196
+            latents = self.init_latents.expand(B, -1, -1) if prev is None else self.predictor(prev)
+            prev, _ = self.slot_attention(feats[:, k].contiguous(), latents)
+            per_frame.append(prev)
+        slots = torch.stack(per_frame, 1).flatten(0, 1)               # [B*T, S, D], clip-major like the frames
+        return boundary.mse_loss(self.unet(xt, t, context=slots), eps)
+
+
 # algorithmic work of the full training step per sample: fwd + bwd (3x) of the trainable modules, fwd of the frozen VQ-VAE
 RESNET_FLOP_PER_SAMPLE = 13.45e9
 VQENC_FLOP_PER_SAMPLE = 19.5e9
 FULL_TRAIN_FLOP_PER_SAMPLE = 3 * (UNET_FLOP_PER_SAMPLE + 203.7e6 + RESNET_FLOP_PER_SAMPLE) + VQENC_FLOP_PER_SAMPLE
 
 
-def train_bench(args, dev, world, rank, full=True):
+def train_bench(args, dev, world, rank, full=True, video=0):
     """One TRAINING step.  full=True: the whole image model of BASELINE configs[1] (FullImageModel: images in, loss out,
     backward through UNet, Slot Attention and the ResNet encoder, data-parallel gradient all-reduce, fused Adam) -- the
     'train-step samples/s' of BASELINE.json.  full=False: the two hot modules alone on synthetic encoder features / latents
@@ -339,10 +402,15 @@ def train_bench(args, dev, world, rank, full=True):
     torch.manual_seed(rank)
     g = torch.Generator().manual_seed(4321 + rank)
     if full:
-        model = FullImageModel(dev).train()
+        if video:
+            B = args.video_clips
+            model = FullVideoModel(dev, frames=video).train()
+            img_h = torch.randn(B, video, 3, 128, 128, generator=g).clamp_(-1, 1).pin_memory()
+        else:
+            model = FullImageModel(dev).train()
+            img_h = torch.randn(B, 3, 128, 128, generator=g).clamp_(-1, 1).pin_memory()
         model.vq_encoder.eval()
         params = model.trainable()
-        img_h = torch.randn(B, 3, 128, 128, generator=g).clamp_(-1, 1).pin_memory()
         inputs_h = (img_h,)
         wcaches = [model.slot_attention._wcache, model.unet._exec.wc, model.encoder._wc]
     else:
@@ -463,15 +531,23 @@ def train_bench(args, dev, world, rank, full=True):
     ms_e2e = timed(e2e_step, args.train_steps)
     if world > 1:
         parallel.disable_grad_allreduce()
-    fl = B * (FULL_TRAIN_FLOP_PER_SAMPLE if full else (3 * UNET_FLOP_PER_SAMPLE + 3 * 203.7e6))
+    units = B * max(video, 1)          # frames for the video model
+    fl = units * (FULL_TRAIN_FLOP_PER_SAMPLE if full else (3 * UNET_FLOP_PER_SAMPLE + 3 * 203.7e6))
     what = ('FULL image model (CLEVRTex config): ResNet18-GN encoder fwd+bwd, SlotAttention(3 it), frozen VQ-VAE encoder, '
             'q_sample, UNet(134M) fwd+bwd (dropout 0.1), eps-MSE, gradient all-reduce (bucketed, overlapped), fused Adam; '
             'synthetic images; pos-embed / token MLP / quant_conv are the small PyTorch ops the reference also uses'
             if full else 'SlotAttention(3 it) + UNet(134M) forward+backward (dropout 0.1) + gradient all-reduce + fused Adam; '
             'encoder features / VQ latents synthetic (hot modules only)')
-    return {'metric': 'train_step_samples_per_sec', 'value': B * world * args.train_steps / (ms / 1e3), 'unit': 'samples/s',
+    if video:
+        what = ('SAViDiffusion, BASELINE configs[2] (MOVi-D shape): %d clips x %d frames 128x128 per GPU, 11 slots, 2 Slot-Attention '
+                'iterations per frame with the slots carried through the TransformerPredictor (PyTorch), ResNet18-GN encoder '
+                'fwd+bwd, frozen VQ-VAE encoder, UNet fwd+bwd over all frames, gradient all-reduce, fused Adam; value = frames/s'
+                % (B, video))
+    return {'metric': 'train_step_frames_per_sec' if video else 'train_step_samples_per_sec',
+            'value': units * world * args.train_steps / (ms / 1e3), 'unit': 'frames/s' if video else 'samples/s',
             'ms_per_step': ms / args.train_steps, 'per_gpu_batch': B, 'global_batch': B * world,
-            'e2e_value': B * world * args.train_steps / (ms_e2e / 1e3),
+            'frames_per_clip': video or None,
+            'e2e_value': units * world * args.train_steps / (ms_e2e / 1e3),
             'h2d_bytes_per_step': sum(t.numel() for t in inputs_h) * 4, 'd2h_bytes_per_step': 4,
             'gpu_launches_per_step': launches, 'loss': out.get('loss'), 'mode': mode,
             'algorithmic_tflops': fl * args.train_steps / (ms / 1e3) / 1e12,
@@ -843,7 +919,10 @@ def main():
     ap.add_argument('--train-batch', type=int, default=64, help='per-GPU batch of the training-step measurement')
     ap.add_argument('--train-steps', type=int, default=5)
     ap.add_argument('--no-train', action='store_true', help='skip the training-step measurement')
+    ap.add_argument('--no-video', action='store_true', help='skip the video-model (BASELINE configs[2]) training-step line')
+    ap.add_argument('--video-clips', type=int, default=8, help='per-GPU clips of the video training step (x 6 frames)')
     ap.add_argument('--no-train-graph', action='store_true', help='time the eager training step (no CUDA graph)')
+    ap.add_argument('--no-other-batches', action='store_true', help='skip the B = 4 / B = 64 sampling lines')
     ap.add_argument('--no-gpu-baseline', action='store_true', help='skip timing the unmodified reference on the same GPU')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--profile-train-once', action='store_true', help='ncu helper: one eager training step')

@@ -88,6 +88,7 @@ struct GemmArgs {
   unsigned rows_per_group;
   int H, W;             // output H, W (conv modes)
   int ctiles;           // WGRAD modes: channel blocks per tap
+  int tap_pair;         // WGRAD modes with C == 64: an M tile holds TWO taps (rows 0..63 = tap 2 tm, 64..127 = tap 2 tm + 1)
   int a_bf16, w_bf16;   // operand planes hold bf16 (gradient operands) instead of fp16
   float corr_scale;     // passes == 2: C = D1 + corr_scale * D2
   float alpha;          // accumulator scale (1 unless the caller pre-scaled an operand by a power of two)
@@ -243,8 +244,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
               uint8_t* ap = pl ? a_lo : a_hi;
               uint8_t* bp = pl ? b_lo : b_hi;
               for (int j = 0; j < na; ++j) {
-                if (CG == 2) tma_load_5d_pair(ap + j * 8192, ma, &ctl.full[stage], c0 + j * 64, cx, cy, c3, c4);
-                else tma_load_5d(ap + j * 8192, ma, &ctl.full[stage], c0 + j * 64, cx, cy, c3, c4);
+                int jc0 = c0 + j * 64, jcx = cx, jcy = cy, jc3 = c3;
+                if (g.tap_pair) {      // block j = tap 2 tm + j of the 64 channels (output row = tap * 64 + ci stays contiguous);
+                  const int tj = min(2 * tm + j, 8);     // the odd ninth tap repeats: its rows lie beyond M and are dropped
+                  const int m0 = ks * BK, hw = g.H * g.W, bimg = m0 / hw;
+                  const int yrow = (m0 - bimg * hw) / g.W, xoff = (m0 - bimg * hw) - yrow * g.W;
+                  jc0 = 0;
+                  if (g.mode == SDB_A_WGRAD) {
+                    jcx = tj % 3 - 1 + xoff; jcy = yrow + tj / 3 - 1; jc3 = 0;
+                  } else {
+                    const int ky = tj / 3, kx = tj % 3;
+                    jcx = ((kx == 0) ? -1 : 0) + xoff; jcy = yrow + ((ky == 0) ? -1 : 0);
+                    jc3 = ((ky != 1) ? 2 : 0) + ((kx != 1) ? 1 : 0);
+                  }
+                }
+                if (CG == 2) tma_load_5d_pair(ap + j * 8192, ma, &ctl.full[stage], jc0, jcx, jcy, jc3, c4);
+                else tma_load_5d(ap + j * 8192, ma, &ctl.full[stage], jc0, jcx, jcy, jc3, c4);
               }
               for (int j = 0; j < nb; ++j) {
                 if (CG == 2) tma_load_2d_pair(bp + j * 8192, mb, &ctl.full[stage], nrow + j * 64, ks * BK);
@@ -787,6 +802,12 @@ extern "C" int sdb_gemm(const SdbGemm* p, void* stream) {
     g.ctiles = p->C / g.tile_rows;
     g.ntaps = 1; g.kblocks = (int)cdiv(p->K, BK);
     n_tiles_m1 = 9 * g.ctiles;
+    if (p->C == 64 && env_int("SDB_WGRAD_TAP_PAIR", 1)) {   // ResNet stem / layer1, VQ-VAE level 0: two taps per 128-row tile
+      g.tap_pair = 1;
+      g.tile_rows = 128;
+      g.ctiles = 1;
+      n_tiles_m1 = 5;
+    }
   } else {
     SDB_REQUIRE(p->mode == SDB_A_CONV3 || p->mode == SDB_A_CONV3S2 || p->mode == SDB_A_CONV3S2A, "sdb_gemm: bad mode %d",
                 p->mode);

@@ -170,7 +170,22 @@ def _make_adapters(ref_dpm):
     return NoiseScheduleVP, model_wrapper, DPM_Solver
 
 
-def install(tasks=_TASKS, sampler=True, boundary=True, vqvae=True, encoder=True):
+_GRAPH = False
+
+
+def _graphed_class(cls):
+    """Subclass whose instances run their training forward / backward from CUDA graphs (graphed.enable at construction)."""
+    from . import graphed
+
+    class Graphed(cls):
+        def __init__(self, *a, **kw):
+            super().__init__(*a, **kw)
+            graphed.enable(self)
+    Graphed.__name__, Graphed.__qualname__ = cls.__name__, cls.__qualname__
+    return Graphed
+
+
+def install(tasks=_TASKS, sampler=True, boundary=True, vqvae=True, encoder=True, graph=False):
     """Rebind the reference's hot-path names to the B200 implementations (idempotent).  The reference package
     `slotdiffusion` must be importable (on sys.path / installed).
     boundary: also route q_sample (DDPM._sample_xt_from_x0, ddpm.py:161-165), F.mse_loss of LDM / CondDDPM.loss_function
@@ -182,6 +197,12 @@ def install(tasks=_TASKS, sampler=True, boundary=True, vqvae=True, encoder=True)
     from .slot_attention import SlotAttention, SlotAttentionWMask
     from .unet import UNetModel
     from . import boundary as _bd
+    if graph:
+        # graph=True: the modules the reference constructs replay their training forward / backward schedules from CUDA
+        # graphs (graphed.py) -- for the reference's eager nerv loop, where ~36 ms of Python per un-captured UNet step
+        # would otherwise be on the critical path.  isinstance() checks of the sampler adapters still hold (subclasses).
+        SlotAttention, SlotAttentionWMask = _graphed_class(SlotAttention), _graphed_class(SlotAttentionWMask)
+        UNetModel = _graphed_class(UNetModel)
     if vqvae:
         # the frozen first stage of the LDM (VQVAEWrapper, VQVAE.py:155-194): Encoder / Decoder are looked up as module
         # globals of vqvae/VQVAE.py when VQVAE.__init__ runs (VQVAE.py:9,66-67); img_based re-exports the same module.
@@ -206,9 +227,14 @@ def install(tasks=_TASKS, sampler=True, boundary=True, vqvae=True, encoder=True)
             # the image encoder is built by eval(enc_dict['resnet'])(...) in the namespace of slot_attention.py / savi.py
             # (slot_attention.py:8,185-188; savi.py:8,200-206)
             from . import resnet as _rn
+            from . import graphed as _gr
             m = importlib.import_module(base + sa_mod)
-            _rebind(m, 'resnet18', _rn.resnet18)
-            _rebind(m, 'resnet34', _rn.resnet34)
+            if graph:
+                _rebind(m, 'resnet18', lambda *a, **kw: _gr.enable(_rn.resnet18(*a, **kw)))
+                _rebind(m, 'resnet34', lambda *a, **kw: _gr.enable(_rn.resnet34(*a, **kw)))
+            else:
+                _rebind(m, 'resnet18', _rn.resnet18)
+                _rebind(m, 'resnet34', _rn.resnet34)
         if adapters is not None:
             m = importlib.import_module(base + 'ddpm.cond_ddpm')
             for name, obj in zip(('NoiseScheduleVP', 'model_wrapper', 'DPM_Solver'), adapters):

@@ -147,8 +147,11 @@ class WeightCache:
 
     def __init__(self):
         self._c = {}
+        self.nocache = False        # graphed training (graphed.py): pack inside every captured forward, never reuse
 
     def _get(self, key, tensors, fn):
+        if self.nocache and torch.is_grad_enabled():
+            return fn()
         key = (key, _FMT)           # packed weights exist per operand format
         sig = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in tensors)
         hit = self._c.get(key)

@@ -95,6 +95,7 @@ class ResNet(nn.Module):
         d = self.__dict__.copy()
         d.pop('_wc', None)
         d.pop('_layout', None)
+        d.pop('_sdb_graphs', None)
         return d
 
     def __setstate__(self, d):
@@ -250,6 +251,10 @@ class ResNet(nn.Module):
             if x.requires_grad:
                 raise NotImplementedError('slotdiffusion_b200.resnet: gradient w.r.t. the input image is not built '
                                           '(the reference never asks for it)')
+            from . import graphed
+            if graphed.enabled(self):       # eager training loops: schedules replayed from CUDA graphs (graphed.py)
+                g = graphed.graphs_of(self, lambda a: _ResNetFn.apply(self, a, *tuple(self.parameters())), lambda: [self._wc])
+                return g(x)
             return _ResNetFn.apply(self, x, *params)
         with torch.no_grad(), ops.pack_format(ops.SDB_FMT_F16X2):
             rows, (B, C, H, W) = self._run(_NoTape(), x)

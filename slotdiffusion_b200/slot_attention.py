@@ -48,6 +48,7 @@ class SlotAttention(nn.Module):
         d = self.__dict__.copy()
         d.pop('_wcache', None)
         d.pop('_gradbuf', None)      # gradient layout is keyed by id(parameter) of THIS instance
+        d.pop('_sdb_graphs', None)   # captured training graphs address this instance's parameters
         return d
 
     def __setstate__(self, d):
@@ -63,6 +64,13 @@ class SlotAttention(nn.Module):
         if not inputs.is_cuda:
             raise RuntimeError('slotdiffusion_b200.SlotAttention runs on CUDA (sm_100a) only; no CPU fallback')
         assert slots.dim() == 3 and inputs.dim() == 3
+        from . import graphed
+        if graphed.enabled(self) and torch.is_grad_enabled() and (
+                inputs.requires_grad or slots.requires_grad or any(p.requires_grad for p in self.parameters())):
+            # eager training loops: forward / backward schedules replayed from CUDA graphs (graphed.py)
+            g = graphed.graphs_of(self, lambda i, s: slot_attention_apply(self, i, s, True), lambda: [self._wcache])
+            out, mask = g(inputs, slots)
+            return out, (mask if want_mask else None)
         return slot_attention_apply(self, inputs, slots, want_mask)
 
     def forward(self, inputs, slots):

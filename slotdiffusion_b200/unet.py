@@ -223,6 +223,7 @@ class UNetModel(nn.Module):
         d = self.__dict__.copy()
         d.pop('_exec', None)
         d.pop('_sdb_samplers', None)
+        d.pop('_sdb_graphs', None)
         return d
 
     def __setstate__(self, d):
@@ -244,6 +245,12 @@ class UNetModel(nn.Module):
         """x [N,C,h,w], timesteps [N] (int or fractional float), context [N,S,Dc] -> [N,C,h,w]."""
         if not x.is_cuda:
             raise RuntimeError('slotdiffusion_b200.UNetModel runs on CUDA (sm_100a) only; no CPU fallback')
+        from . import graphed
+        if graphed.enabled(self) and torch.is_grad_enabled() and context is not None and torch.is_tensor(timesteps) and (
+                x.requires_grad or context.requires_grad or any(p.requires_grad for p in self.parameters())):
+            # eager training loops: forward / backward schedules replayed from CUDA graphs (graphed.py)
+            g = graphed.graphs_of(self, lambda a, t, c: self._exec(a, t, c), lambda: [self._exec.wc])
+            return g(x, timesteps, context)
         return self._exec(x, timesteps, context)
 
     @property

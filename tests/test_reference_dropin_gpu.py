@@ -178,3 +178,40 @@ def test_reference_savidiffusion_video_train_step_stock_vs_dropin(dropin):
     print('video: global grad rel', (tot_d / tot_r) ** 0.5, 'slot_attention grad rel', (sa_d / sa_r) ** 0.5)
     assert (tot_d / tot_r) ** 0.5 < 1e-3
     assert (sa_d / sa_r) ** 0.5 < 1e-3
+
+
+def test_reference_training_loop_with_graphed_dropin(dropin):
+    """dropin.install(graph=True) under a nerv-style eager loop (forward -> loss.backward() -> optimizer.step()) on the
+    unmodified reference model: three steps stay in lock-step with the un-graphed drop-in (same weights, same RNG seed)."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    dev = torch.device('cuda')
+    B = 2
+    dropin.install()
+    plain = _build(*CFG)
+    _nonzero_init(plain)
+    plain = plain.to(dev)
+    dropin.uninstall()
+    dropin.install(graph=True)
+    fast = _build(*CFG)
+    fast.load_state_dict(plain.state_dict(), strict=True)
+    fast = fast.to(dev)
+    assert fast.slot_attention.__dict__.get('_sdb_graphed') and fast.encoder.__dict__.get('_sdb_graphed')
+    opts = [torch.optim.SGD([p for p in m.parameters() if p.requires_grad], lr=1e-3) for m in (plain, fast)]
+    for step in range(3):
+        img = torch.randn(B, 3, 128, 128, generator=torch.Generator().manual_seed(50 + step)).clamp(-1, 1).to(dev)
+        losses = []
+        for m, opt in zip((plain, fast), opts):
+            m.train()
+            torch.manual_seed(1000 + step)
+            data = {'img': img}
+            loss = m.calc_train_loss(data, m(data))['denoise_loss']
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            opt.step()
+            losses.append(loss.item())
+        assert abs(losses[0] - losses[1]) / abs(losses[0]) < 2e-3, (step, losses)
+    pa, pb = dict(plain.named_parameters()), dict(fast.named_parameters())
+    drift = max(rel_l2(pb[k], pa[k]) for k in pa)
+    assert drift < 1e-3, drift
+    assert fast.dm_decoder.model.diffusion_model.__dict__['_sdb_graphs'].graphs
