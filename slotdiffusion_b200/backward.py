@@ -577,7 +577,8 @@ class UNetFn(torch.autograd.Function):
     def forward(ctx, trainer, x, timesteps, context, *params):
         tp = Tape()
         need_dx = x.requires_grad
-        y = trainer.forward(tp, x.detach(), timesteps, context.detach(), need_dx)
+        with ops.training_scope():
+            y = trainer.forward(tp, x.detach(), timesteps, context.detach(), need_dx)
         ctx.trainer, ctx.tape, ctx.need_dx = trainer, tp, need_dx
         ctx.x_shape, ctx.ctx_shape = tuple(x.shape), tuple(context.shape)
         ctx.params = params
@@ -588,7 +589,8 @@ class UNetFn(torch.autograd.Function):
         tr, tp = ctx.trainer, ctx.tape
         if tp is None:
             raise RuntimeError('slotdiffusion_b200: UNet backward called twice on the same graph (retain_graph is not supported)')
-        dx, dctx = tr.backward(tp, dy, ctx.x_shape, ctx.need_dx)
+        with ops.training_scope():
+            dx, dctx = tr.backward(tp, dy, ctx.x_shape, ctx.need_dx)
         G = tp.G
         ctx.tape = None
         if parallel.enabled():              # data parallel: what the buckets have not covered yet, then join
@@ -615,6 +617,11 @@ class SlotAttentionFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, mod, want_mask, inputs, slots, *params):
+        with ops.training_scope():
+            return SlotAttentionFn._forward(ctx, mod, want_mask, inputs, slots, *params)
+
+    @staticmethod
+    def _forward(ctx, mod, want_mask, inputs, slots, *params):
         tp = Tape()
         layout = getattr(mod, '_gradbuf', None)
         if layout is None or layout.params_ids != tuple(id(p) for p in mod.parameters()):
@@ -709,7 +716,8 @@ class SlotAttentionFn(torch.autograd.Function):
             raise RuntimeError('slotdiffusion_b200: Slot Attention backward called twice on the same graph (retain_graph is not supported)')
         B, S, D = ctx.shapes[1]
         tp.set(ctx.out, dslots.contiguous().float().reshape(B * S, D))
-        tp.run()
+        with ops.training_scope():
+            tp.run()
         dx = tp.pop(ctx.x)
         ds0 = tp.pop(ctx.s0)
         ctx.tape = None

@@ -308,7 +308,14 @@ __global__ void __launch_bounds__(256) groupnorm_bwd_kernel(const GnBwdArgs a) {
       float dz = d[j];
       if (a.drop_p > 0.f) dz *= dropout_scale(seed, (unsigned long long)(row * C + c + j), a.drop_p, inv_keep);
       if (a.silu == 1) dz *= silu_grad_f(xh * gm[j] + bt[j]);
-      else if (a.silu == 2) dz = (xh * gm[j] + bt[j] > 0.f) ? dz : 0.f;      // ReLU (ResNet18-GN encoder, resnet.py:76-78)
+      else if (a.silu == 2) {
+        // ReLU (ResNet18-GN encoder, resnet.py:76-78).  The mask must be the FORWARD's: the same expression as the operand
+        // producer (elementwise.cu: v * (rstd gamma) + (beta - mean rstd gamma)), not an algebraically equal one -- an
+        // input within round-off of zero would otherwise pass in one direction and be blocked in the other
+        const float scj = rs[j] * gm[j];
+        const float shj = bt[j] - mu[j] * scj;
+        dz = (x[j] * scj + shj > 0.f) ? dz : 0.f;
+      }
       if (APPLY) {
         o[j] = rs[j] * (dz * gm[j] - m1[j] - xh * m2[j]);
       } else {

@@ -37,12 +37,11 @@ class _Core(nn.Module):
         dev = tensors[0].device
         ops.dropout_step_counter(dev).add_(1)          # inside the capture: a new dropout mask stream per replay
         for wc in self._caches():
-            wc.nocache = True                           # (re)pack the weights inside this forward, also under replay
-        try:
-            return self._fn(*tensors)
-        finally:
-            for wc in self._caches():
-                wc.nocache = False
+            # (re)pack the weights inside the training schedules -- forward AND backward (transposed / rotated operands of
+            # the dgrad GEMMs) -- so that the captured graphs contain the packing kernels.  Honoured only inside
+            # ops.training_scope(): the no-grad inference paths of the same module keep their cache.
+            wc.nocache = True
+        return self._fn(*tensors)
 
 
 class GraphedTraining:

@@ -66,6 +66,20 @@ def pack_format(fmt):
             _FMT = prev
 
 
+_TRAIN_DEPTH = [0]
+
+
+@contextlib.contextmanager
+def training_scope():
+    """Marks the forward / backward schedules of the autograd Functions (backward.py, resnet.py): WeightCache.nocache is
+    honoured only here (grad mode cannot tell: autograd.Function.forward runs under no_grad like the inference paths)."""
+    _TRAIN_DEPTH[0] += 1
+    try:
+        yield
+    finally:
+        _TRAIN_DEPTH[0] -= 1
+
+
 def unet_inference_format():
     return SDB_FMT_F8C if (_UNET_INFERENCE == 'fp8c' and _PASSES == 3) else SDB_FMT_F16X2
 
@@ -147,10 +161,12 @@ class WeightCache:
 
     def __init__(self):
         self._c = {}
-        self.nocache = False        # graphed training (graphed.py): pack inside every captured forward, never reuse
+        self.nocache = False        # graphed training (graphed.py): inside a training schedule, pack every time -- the
+        #                             packing kernels become part of the captured forward / backward, so a replay after
+        #                             optimizer.step() sees the new parameter values
 
     def _get(self, key, tensors, fn):
-        if self.nocache and torch.is_grad_enabled():
+        if self.nocache and _TRAIN_DEPTH[0] > 0:
             return fn()
         key = (key, _FMT)           # packed weights exist per operand format
         sig = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in tensors)

@@ -271,7 +271,7 @@ class _ResNetFn(torch.autograd.Function):
             net._layout = GradBuffer(net)
             net._layout.params_ids = tuple(id(p) for p in params)
         tp.G = net._layout.instance(x.device)        # per call (never on the module)
-        with ops.pack_format(ops.SDB_FMT_F16X2):
+        with ops.pack_format(ops.SDB_FMT_F16X2), ops.training_scope():
             rows, geo = net._run(tp, x.detach())
         ctx.tape, ctx.rows, ctx.geo, ctx.params = tp, rows, geo, params
         B, C, H, W = geo
@@ -283,7 +283,7 @@ class _ResNetFn(torch.autograd.Function):
         if tp is None:
             raise RuntimeError('slotdiffusion_b200: ResNet backward called twice on the same graph (retain_graph is not supported)')
         B, C, H, W = ctx.geo
-        with ops.pack_format(ops.SDB_FMT_F16X2):
+        with ops.pack_format(ops.SDB_FMT_F16X2), ops.training_scope():
             tp.set(ctx.rows, ops.nchw_to_nhwc_pad(dy.contiguous().float(), C))
             tp.run()
         G = tp.G

@@ -70,7 +70,7 @@ class SlotAttention(nn.Module):
             # eager training loops: forward / backward schedules replayed from CUDA graphs (graphed.py)
             g = graphed.graphs_of(self, lambda i, s: slot_attention_apply(self, i, s, True), lambda: [self._wcache])
             out, mask = g(inputs, slots)
-            return out, (mask if want_mask else None)
+            return out, (mask.detach() if want_mask else None)      # the segmentation mask carries no gradient (sa_diffusion.py:50-51)
         return slot_attention_apply(self, inputs, slots, want_mask)
 
     def forward(self, inputs, slots):
