@@ -288,6 +288,47 @@ typedef struct SdbSlotUpdate {
 int sdb_slot_update_supported(int64_t S, int64_t Din, int64_t D, int64_t M);
 int sdb_slot_update(const SdbSlotUpdate* args, void* stream);
 
+/* ------------------------------------------------------------------ Slot Attention, the whole iterative update as ONE
+ * persistent kernel (slot_attention.py:67-104, SlotAttentionWMask: sa_diffusion.py:28-70; inference path).
+ * A thread-block cluster of 4 / 8 CTAs owns a sample: its raw features x [N, Din] are read from HBM once, LayerNorm-ed and
+ * split into fp16 hi/lo tcgen05 operand tiles in shared memory, and all `iterations` run from that resident copy (logits and
+ * weighted-sum contractions on the tensor cores, softmax over slots, GRU / MLP / next q projection on the CUDA cores,
+ * column-split over the CTAs of the cluster and exchanged through distributed shared memory).  Same folded algebra as
+ * sdb_slot_attend_fused + sdb_slot_update.  Weights fp32, TRANSPOSED and k-quad interleaved, w4[K/4][ncols][4]:
+ * w_iv4 [Din/4][3D][4], w_hh4 [D/4][3D][4], w1_4 [D/4][M][4], w2_4 [M/4][D][4], w_qa4 [D/4][ldq][4] (column Din = logit bias).
+ * slots_in / slots_out [B, S, D]; seg_mask [B, S, N] (last-iteration softmax over slots) or NULL.
+ * Supported (sdb_slot_attention_resident_supported): D == Din in {128,192,256}, S <= 32, N up to 8 x 256 (Din <= 192) /
+ * 8 x 128 tokens, M % 64 == 0. */
+typedef struct SdbSlotAttentionResident {
+  const float* x;
+  const float* slots_in;
+  float* slots_out;
+  float* seg_mask;
+  const float* w_iv4;
+  const float* b_iv;
+  const float* w_hh4;
+  const float* b_hh;
+  const float* ln_m_g;
+  const float* ln_m_b;
+  const float* w1_4;
+  const float* b1;
+  const float* w2_4;
+  const float* b2;
+  const float* ln_q_g;
+  const float* ln_q_b;
+  const float* w_qa4;
+  int64_t B;
+  int32_t N, S, Din, D, M, ldq, iterations;
+  float ln_in_eps, attn_eps, ln_m_eps, ln_q_eps;
+} SdbSlotAttentionResident;
+int sdb_slot_attention_resident_supported(int64_t N, int64_t S, int64_t Din, int64_t D, int64_t M);
+int sdb_slot_attention_resident(const SdbSlotAttentionResident* args, void* stream);
+/* number of samples processed concurrently (resident clusters) for this geometry on the current device; the persistent
+ * kernel loops over the batch in waves of this size.  0 = unsupported geometry. */
+int64_t sdb_slot_attention_resident_wave(int64_t N, int64_t S, int64_t Din, int64_t D, int64_t M);
+/* debug aid: device buffer of 256 int64 receiving the phase timeline (SM cycles) of thread 0 of CTA 0; NULL switches it off */
+int sdb_slot_attention_resident_debug(void* buf);
+
 /* GRUCell pointwise part (PyTorch gate order r,z,n; slot_attention.py:97-100): gi = x W_ih^T + b_ih and
  * gh = h W_hh^T + b_hh come from sdb_gemm; h_new = (1-z) n + z h.  All [R, 3D] / [R, D]. */
 int sdb_gru_gates(const float* gi, const float* gh, const float* h, float* h_new, int64_t R, int64_t D,

@@ -36,6 +36,15 @@ class SdbSlotUpdate(Structure):
         ('chunks', c_int32), ('ascale', c_float), ('ln_m_eps', c_float), ('ln_q_eps', c_float), ('do_update', c_int32)]
 
 
+class SdbSlotAttentionResident(Structure):
+    _fields_ = [(n, c_void_p) for n in (
+        'x', 'slots_in', 'slots_out', 'seg_mask', 'w_iv4', 'b_iv', 'w_hh4', 'b_hh', 'ln_m_g', 'ln_m_b', 'w1_4', 'b1', 'w2_4',
+        'b2', 'ln_q_g', 'ln_q_b', 'w_qa4')] + [
+        ('B', c_int64), ('N', c_int32), ('S', c_int32), ('Din', c_int32), ('D', c_int32), ('M', c_int32), ('ldq', c_int32),
+        ('iterations', c_int32), ('ln_in_eps', c_float), ('attn_eps', c_float), ('ln_m_eps', c_float),
+        ('ln_q_eps', c_float)]
+
+
 # name -> (restype, argtypes); must list every symbol declared in include/sdb200.h
 SIGNATURES = {
     'sdb_version': (c_int, []),
@@ -99,6 +108,10 @@ SIGNATURES = {
                                                c_int64, c_int64, c_float, c_float, c_void_p]),
     'sdb_slot_update_supported': (c_int, [c_int64, c_int64, c_int64, c_int64]),
     'sdb_slot_update': (c_int, [POINTER(SdbSlotUpdate), c_void_p]),
+    'sdb_slot_attention_resident_supported': (c_int, [c_int64, c_int64, c_int64, c_int64, c_int64]),
+    'sdb_slot_attention_resident': (c_int, [POINTER(SdbSlotAttentionResident), c_void_p]),
+    'sdb_slot_attention_resident_debug': (c_int, [c_void_p]),
+    'sdb_slot_attention_resident_wave': (c_int64, [c_int64, c_int64, c_int64, c_int64, c_int64]),
     'sdb_groupnorm_apply_pack_dropout': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
                                                  c_void_p, c_int64, c_int64, c_int, c_int, c_float, c_uint64, c_void_p, c_void_p]),
     'sdb_grad_pack': (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64,

@@ -21,6 +21,13 @@ FUSED_ATTEND = True   # inference: tensor-core attend over the raw features (no 
 # its arithmetic is checked on the CPU through the host emulation (tests/test_slot_update_emulation_cpu.py).
 FUSED_TAIL = os.environ.get('SDB_SA_FUSED_TAIL', '0') == '1'
 FUSED_TAIL_MAX_ROWS = 1024
+# Whole forward as ONE persistent cluster kernel (csrc/slot_attention_resident.cu): features read from HBM once and kept
+# in shared memory over all iterations.  SDB_SA_RESIDENT=0 falls back to the per-iteration kernels above.
+RESIDENT = os.environ.get('SDB_SA_RESIDENT', '1') == '1'
+# Measured (profiles/README.md, round 2): one wave (= one sample per resident cluster, 33 on a B200 for N = 1024, D = 192)
+# takes ~180 us whatever its fill, the per-iteration path 240 us at B = 33 and 270 us at B = 64 -- so the persistent kernel
+# is used up to RESIDENT_WAVES waves; SDB_SA_RESIDENT_WAVES=1000000 forces it for every batch size.
+RESIDENT_WAVES = int(os.environ.get('SDB_SA_RESIDENT_WAVES', '1'))
 
 
 def _needs_grad(*ts):
@@ -35,6 +42,12 @@ def slot_attention_forward(mod, inputs, slots, want_mask, save=None):
     wc = mod._wcache
     inputs = inputs.contiguous().float()
     slots = slots.contiguous().float().reshape(B * S, D)
+    if (save is None and RESIDENT and ops.slot_attention_resident_supported(N, S, Din, D, mod.mlp_hidden_size)
+            and B <= RESIDENT_WAVES * ops.slot_attention_resident_wave(N, S, Din, D, mod.mlp_hidden_size)):
+        w = wc.slot_resident_weights(mod)                                     # :67-104 in one launch
+        out, mask = ops.slot_attention_resident(w, inputs, slots.view(B, S, D), mod.num_iterations, mod.norm_inputs.eps,
+                                                mod.eps, mod.mlp_hidden_size, want_mask)
+        return out, mask
     if save is None and FUSED_ATTEND and ops.slot_attend_fused_supported(S, Din):
         if FUSED_TAIL and B * S <= FUSED_TAIL_MAX_ROWS and ops.slot_update_supported(S, Din, D, mod.mlp_hidden_size):
             return slot_attention_forward_fused_tail(mod, inputs, slots, want_mask, B, N, Din, S, D)

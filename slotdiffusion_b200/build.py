@@ -12,7 +12,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
-SOURCES = ['api.cu', 'gemm.cu', 'elementwise.cu', 'attention.cu', 'attention_tc.cu', 'slot_attention.cu', 'slot_attention_fused.cu', 'slot_update.cu', 'backward.cu', 'boundary.cu']
+SOURCES = ['api.cu', 'gemm.cu', 'elementwise.cu', 'attention.cu', 'attention_tc.cu', 'slot_attention.cu', 'slot_attention_fused.cu', 'slot_attention_resident.cu', 'slot_update.cu', 'backward.cu', 'boundary.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '--use_fast_math=false']
 # Build variants live next to the product library under their own names (they travel to the GPU box with it and are
@@ -26,6 +26,10 @@ if os.environ.get('SDB_SF_EXPERIMENTAL', '0') == '1':
 if os.environ.get('SDB_GEMM_TIMING', '0') == '1':
     NVCC_FLAGS.append('-DSDB_GEMM_TIMING=1')
     VARIANT += '_gtiming'
+# ad-hoc experiment builds: SDB_DEFINES="-DFOO=1 -DBAR" SDB_VARIANT=name -> libsdb200_name.so
+if os.environ.get('SDB_DEFINES') and os.environ.get('SDB_VARIANT'):
+    NVCC_FLAGS += os.environ['SDB_DEFINES'].split()
+    VARIANT += '_' + os.environ['SDB_VARIANT']
 LIB = os.path.join(HERE, f'libsdb200{VARIANT}.so')
 STAMP = os.path.join(HERE, f'.libsdb200{VARIANT}.stamp')
 BUILD_DIR = os.path.join(HERE, 'build' + VARIANT)

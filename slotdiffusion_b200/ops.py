@@ -10,7 +10,7 @@ import torch
 
 from . import _lib
 from ._lib import (SDB_A_CONV3, SDB_A_CONV3S2, SDB_A_CONV3S2A, SDB_A_PLAIN, SDB_PACK_PHASE2, SDB_PACK_PLAIN, SDB_PACK_UP2,
-                   SdbGemm, SdbSlotUpdate, check, lib)
+                   SdbGemm, SdbSlotAttentionResident, SdbSlotUpdate, check, lib)
 
 import contextlib
 import math
@@ -227,6 +227,22 @@ class WeightCache:
                         b2=b2.contiguous(), ln_q_g=gq.contiguous(), ln_q_b=bq.contiguous(), w_qaT=T(wqa),
                         ldq=int(wqa.shape[0]), ln_m_eps=float(mod.mlp[0].eps), ln_q_eps=float(mod.project_q[0].eps))
         return self._get('sa_update', ps + rest, make)
+
+    def slot_resident_weights(self, mod):
+        """Weights of the persistent Slot-Attention kernel (csrc/slot_attention_resident.cu): the fold of
+        slot_update_weights, each matrix additionally k-quad interleaved -- w4[K/4][ncols][4] -- so that a thread reads
+        four consecutive K elements of its output column with one 16-byte load and a warp reads 128 contiguous bytes."""
+        base = self.slot_update_weights(mod)
+
+        def make():
+            def k4(wT):                               # [K][N] -> [K/4][N][4]
+                K, N = wT.shape
+                return wT.reshape(K // 4, 4, N).permute(0, 2, 1).contiguous()
+            out = dict(base)
+            for src, dst in (('w_ivT', 'w_iv4'), ('w_hhT', 'w_hh4'), ('w1T', 'w1_4'), ('w2T', 'w2_4'), ('w_qaT', 'w_qa4')):
+                out[dst] = k4(base[src])
+            return out
+        return self._get('sa_resident', tuple(base[k] for k in ('w_ivT', 'w_hhT', 'w1T', 'w2T', 'w_qaT')), make)
 
     def cat(self, key, *vs):
         """Concatenation of fp32 vectors (fused biases)."""
@@ -606,6 +622,49 @@ def slot_update(w, parts, slots_in, S, Din, D, M, want_q):
     a = slot_update_args(w, parts, slots_in, slots_out, qa, S, Din, D, M)
     check(lib().sdb_slot_update(ctypes.byref(a), _stream()), 'sdb_slot_update')
     return (slots_out if parts is not None else slots_in), qa
+
+
+def slot_attention_resident_supported(N, S, Din, D, M):
+    return bool(lib().sdb_slot_attention_resident_supported(N, S, Din, D, M))
+
+
+_RESIDENT_WAVE = {}
+
+
+def slot_attention_resident_wave(N, S, Din, D, M):
+    """Samples the persistent kernel processes at the same time on this device (0: geometry unsupported)."""
+    key = (torch.cuda.current_device(), N, S, Din, D, M)
+    if key not in _RESIDENT_WAVE:
+        _RESIDENT_WAVE[key] = int(lib().sdb_slot_attention_resident_wave(N, S, Din, D, M))
+    return _RESIDENT_WAVE[key]
+
+
+def slot_attention_resident_args(w, x, slots_in, slots_out, mask, iterations, ln_in_eps, attn_eps, M):
+    """SdbSlotAttentionResident for one call (only data_ptr()s and shapes)."""
+    B, N, Din = x.shape
+    S, D = slots_in.shape[1], slots_in.shape[2]
+    a = SdbSlotAttentionResident()
+    for k in ('w_iv4', 'b_iv', 'w_hh4', 'b_hh', 'ln_m_g', 'ln_m_b', 'w1_4', 'b1', 'w2_4', 'b2', 'ln_q_g', 'ln_q_b', 'w_qa4'):
+        setattr(a, k, w[k].data_ptr())
+    a.x, a.slots_in, a.slots_out = x.data_ptr(), slots_in.data_ptr(), slots_out.data_ptr()
+    a.seg_mask = mask.data_ptr() if mask is not None else None
+    a.B, a.N, a.S, a.Din, a.D, a.M, a.ldq, a.iterations = B, N, S, Din, D, M, w['ldq'], iterations
+    a.ln_in_eps, a.attn_eps, a.ln_m_eps, a.ln_q_eps = ln_in_eps, attn_eps, w['ln_m_eps'], w['ln_q_eps']
+    return a
+
+
+def slot_attention_resident(w, x, slots_in, iterations, ln_in_eps, attn_eps, M, want_mask):
+    """The whole Slot-Attention forward in one launch: x [B,N,Din] raw features, slots_in [B,S,D] ->
+    (slots [B,S,D], seg mask [B,S,N] or None)."""
+    _f32(x)
+    _f32(slots_in)
+    B, N, _ = x.shape
+    S = slots_in.shape[1]
+    slots_out = torch.empty_like(slots_in)
+    mask = torch.empty(B, S, N, dtype=torch.float32, device=x.device) if want_mask else None
+    a = slot_attention_resident_args(w, x, slots_in, slots_out, mask, iterations, ln_in_eps, attn_eps, M)
+    check(lib().sdb_slot_attention_resident(ctypes.byref(a), _stream()), 'sdb_slot_attention_resident')
+    return slots_out, mask
 
 
 def gru_gates(gi, gh, h):

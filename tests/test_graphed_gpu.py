@@ -31,7 +31,10 @@ def _compare_three_steps(make, run, lr=1e-4):
         lb.backward()
         ga, gb = _grads(a), _grads(b)
         assert set(ga) == set(gb)
-        worst = max((rel_l2(gb[k], ga[k]) for k in ga if ga[k].norm() > 1e-12), default=0.0)
+        # parameters whose gradient is zero up to round-off (LayerNorm_q's bias: the softmax over slots ignores a per-token
+        # shift of the logits) carry only noise -- 1e-6 against gradients of 1e+1 elsewhere -- and are not compared
+        floor = 1e-5 * max(float(g.norm()) for g in ga.values())
+        worst = max((rel_l2(gb[k], ga[k]) for k in ga if ga[k].norm() > floor), default=0.0)
         assert worst < 1e-3, (step, worst)
         oa.step()
         ob.step()

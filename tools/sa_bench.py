@@ -64,6 +64,11 @@ def main():
         s0 = torch.randn(B, S, D, device=dev)
         with torch.no_grad():
             res = {}
+            t_res = None
+            if ops.slot_attention_resident_supported(N, S, D, D, 2 * D):
+                autograd.RESIDENT, autograd.RESIDENT_WAVES = True, 1 << 20
+                t_res = graph_time(lambda: mod(x, s0), flush=flush)
+            autograd.RESIDENT = False
             for fused in (True, False):
                 autograd.FUSED_ATTEND = fused
                 res[fused] = graph_time(lambda: mod(x, s0), flush=flush)
@@ -86,6 +91,8 @@ def main():
         it_bytes = B * 4 * (N * D + S * N + 2 * S * D)
         print(json.dumps({
             'B': B, 'N': N, 'S': S, 'D': D, 'iters': args.iters,
+            'module_us_resident': None if t_res is None else round(t_res, 1),
+            'module_hbm_frac_resident': None if t_res is None else round(mod_bytes / t_res / 1e3 / hbm, 4),
             'module_us_fused': round(res[True], 1), 'module_us_kv_path': round(res[False], 1),
             'module_us_fused_one_launch_tail': None if t_tail is None else round(t_tail, 1),
             'module_hbm_frac_fused': round(mod_bytes / res[True] / 1e3 / hbm, 4),
