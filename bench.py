@@ -257,6 +257,7 @@ def run_ours(args):
                 'images_per_sec': B * args.steps * world / (ms / 1e3),
                 'slot_attention_ms_B%d' % B: sa_stat['module_ms'],
                 'slot_attention_hbm_frac': sa_stat['module_hbm_frac'],
+                'slot_attention_persistent_kernel': sa_stat['resident'],
             },
             'clocks': clocks,
             'e2e': {'value': units / (ms_e2e / 1e3), 'unit': UNIT,
@@ -717,8 +718,21 @@ def time_sa(sa, feats, slots0, peaks):
         att_us = _graph_us(lambda: ops.slot_attend_fused(feats, qa, B, N_TOK, S, D, 1e-5, 1e-6, True), flush=flush)
     it_bytes = B * 4 * (N_TOK * D + S * N_TOK + 2 * S * D)            # features in, seg mask + partial updates out
     mod_bytes = B * SA_BYTES_PER_SAMPLE + SA_WEIGHT_BYTES
+    # the persistent cluster kernel (whole forward in ONE launch, features read from HBM once): timed at one full wave
+    # of resident clusters, the largest batch the module routes to it (autograd.RESIDENT_WAVES)
+    resident = None
+    wave = ops.slot_attention_resident_wave(N_TOK, S, D, D, 2 * D)
+    if wave > 0:
+        bw = min(wave, B)
+        with torch.no_grad():
+            res_us = _graph_us(lambda: sa(feats[:bw], slots0[:bw]), flush=flush)
+        res_bytes = bw * SA_BYTES_PER_SAMPLE + SA_WEIGHT_BYTES
+        resident = {'batch': bw, 'samples_per_wave': wave, 'us': res_us, 'launches': 1,
+                    'hbm_frac': res_bytes / (res_us * 1e-6) / 1e9 / peaks['hbm_gbs'],
+                    'kernel': 'sdb::sr::slot_attention_resident_kernel (3 iterations + GRU/MLP update, one launch, L2 flushed)'}
     return {'module_ms': mod_us / 1e3,
             'module_hbm_frac': mod_bytes / (mod_us * 1e-6) / 1e9 / peaks['hbm_gbs'],
+            'resident': resident,
             'attend_kernel': {'bound': 'hbm', 'us': att_us, 'achieved': it_bytes / (att_us * 1e-6) / 1e9,
                               'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
                               'frac': it_bytes / (att_us * 1e-6) / 1e9 / peaks['hbm_gbs'],

@@ -215,50 +215,41 @@ struct Args {
 // shared-memory pipe: RS broadcast LDS.128 (512 B of write-back each) per 4 NG RS FMAs.  All 32 lanes hold the full sums
 // on return.  Rows >= S read whatever follows the region (inside the CTA's allocation, checked by the entry point); their
 // sums are discarded by the caller.
-template <int RS, int NG, int UNR, int PD, int LDX>
+#ifndef SR_FENCE
+#define SR_FENCE() __syncwarp()   /* a warp barrier: ptxas does not sink the loads above it towards their uses */
+#endif
+template <int RS, int NG, int BATCH, int RH, int LDX>
 __device__ __forceinline__ void dot_ks(const float* __restrict__ x, int ks, const float4* __restrict__ w4, int ncols,
                                        const int (&col)[NG], int kq0, int kq1, float (&acc)[NG][RS]) {
 #pragma unroll
   for (int g = 0; g < NG; ++g)
 #pragma unroll
     for (int r = 0; r < RS; ++r) acc[g][r] = 0.f;
-  const int nb = (kq1 - kq0) / (4 * UNR);            // bodies; lane quad index of (body, u): kq0 + 4 (body UNR + u) + ks
   const float4* wl = w4 + (size_t)(kq0 + ks) * ncols;
   const float* xl = x + 4 * (kq0 + ks);
-  float4 buf[PD][UNR][NG];
+  const int nbatch = (kq1 - kq0) / (4 * BATCH);      // lane quad index of (batch, u): kq0 + 4 (batch BATCH + u) + ks
+#pragma unroll 1
+  for (int bt = 0; bt < nbatch; ++bt) {
+    float4 buf[BATCH][NG];
 #pragma unroll
-  for (int s = 0; s < PD; ++s) {
-    const int body = s < nb ? s : nb - 1;
+    for (int u = 0; u < BATCH; ++u)
 #pragma unroll
-    for (int u = 0; u < UNR; ++u)
+      for (int g = 0; g < NG; ++g) buf[u][g] = __ldg(wl + (size_t)(4 * (bt * BATCH + u)) * ncols + col[g]);
+    SR_FENCE();
 #pragma unroll
-      for (int g = 0; g < NG; ++g) buf[s][u][g] = __ldg(wl + (size_t)(4 * (body * UNR + u)) * ncols + col[g]);
-  }
-  for (int b0 = 0; b0 < nb; b0 += PD) {
+    for (int u = 0; u < BATCH; ++u) {
+      const float* xk = xl + 16 * (bt * BATCH + u);
 #pragma unroll
-    for (int s = 0; s < PD; ++s) {
-      const int body = b0 + s;
-      if (body < nb) {                               // warp-uniform
+      for (int r0 = 0; r0 < RS; r0 += RH) {
+        float4 xv[RH];
 #pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-          const float* xk = xl + 16 * (body * UNR + u);
-#pragma unroll
-          for (int r = 0; r < RS; ++r) {
-            const float4 xv = *reinterpret_cast<const float4*>(xk + r * LDX);
-#pragma unroll
-            for (int g = 0; g < NG; ++g) {
-              acc[g][r] = fmaf(xv.x, buf[s][u][g].x, acc[g][r]);
-              acc[g][r] = fmaf(xv.y, buf[s][u][g].y, acc[g][r]);
-              acc[g][r] = fmaf(xv.z, buf[s][u][g].z, acc[g][r]);
-              acc[g][r] = fmaf(xv.w, buf[s][u][g].w, acc[g][r]);
-            }
-          }
-        }
-        const int nxt = body + PD < nb ? body + PD : nb - 1;   // tail: reload the last body (no branch, result unused)
-#pragma unroll
-        for (int u = 0; u < UNR; ++u)
-#pragma unroll
-          for (int g = 0; g < NG; ++g) buf[s][u][g] = __ldg(wl + (size_t)(4 * (nxt * UNR + u)) * ncols + col[g]);
+        for (int r = 0; r < RH; ++r) xv[r] = *reinterpret_cast<const float4*>(xk + (r0 + r) * LDX);
+        SR_FENCE();
+#define SR_FMA_COMP(C)                                                                             \
+  _Pragma("unroll") for (int r = 0; r < RH; ++r) _Pragma("unroll") for (int g = 0; g < NG; ++g)    \
+      acc[g][r0 + r] = fmaf(xv[r].C, buf[u][g].C, acc[g][r0 + r]);
+        SR_FMA_COMP(x) SR_FMA_COMP(y) SR_FMA_COMP(z) SR_FMA_COMP(w)
+#undef SR_FMA_COMP
       }
     }
   }
@@ -324,7 +315,11 @@ slot_attention_resident_kernel(const Args args) {
   constexpr int NWT = NWORK * 32;                    // worker threads
   constexpr int SOFT_WARPS = 4 * NT;
   constexpr int NV = DIN / 32;                       // float4 per lane per token (conversion)
-  constexpr int HR = (SP * D + NWT - 1) / NWT;       // registers that carry the slots across the attend phase
+  // output columns per lane in the MLP / projection stages (c, c + 8, ...).  Measured (profiles/README.md, round 2): a warp's
+  // product is a serial chain of shared-memory and L2 latencies (~10 k cycles for K = 192 whatever runs beside it), so more
+  // warps with one column each beat fewer warps with three.
+  constexpr int NGC = 1;
+  constexpr int GW0 = SOFT_WARPS;                    // first GRU warp (the softmax warps carry no GRU state through the attend phase)
   const SdbSlotAttentionResident& p = args.p;
   constexpr int M = 2 * D;                           // mlp_hidden_size == 2 * slot_size (checked by the entry point)
   constexpr int LDM = M + 4;                         // row stride of the MLP hidden rows
@@ -336,8 +331,7 @@ slot_attention_resident_kernel(const Args args) {
   uint8_t* qop = scr;                                // [NKB][q_hi SP rows | q_lo SP rows][128 B]
   uint8_t* aop = scr + C::QBYTES;                    // NT x [2 token blocks][a_hi SP rows | a_lo SP rows][128 B]
   Ctl& ctl = *reinterpret_cast<Ctl*>(scr + C::SCR);
-  float* R0 = reinterpret_cast<float*>(scr);                     // own partial U [S][DIN] | GRU hidden-side scratch | MLP hidden [S][LDM] (with R1)
-  float* R1 = reinterpret_cast<float*>(scr + args.rsz);          // previous slots [S][LD]
+  float* R0 = reinterpret_cast<float*>(scr);                     // own partial U [S][DIN] | MLP hidden [S][LDM] (spans regions 0 and 1)
   float* R2 = reinterpret_cast<float*>(scr + 2 * args.rsz);      // U (cluster sum) | LayerNorm(h') | split-K scratch | new slots, all [S][LD]
   float* R3 = reinterpret_cast<float*>(scr + 3 * args.rsz);      // h' | LayerNorm_q(slots) [S][LD]
 
@@ -395,9 +389,16 @@ slot_attention_resident_kernel(const Args args) {
   const uint32_t tmem = ctl.tmem_base;
   cluster_barrier();                                 // every CTA of the cluster is resident before the first DSMEM access
 
-  float hreg[HR];                                    // slots carried across the attend phase (its operands overwrite R1..R3)
+  // GRU state of warp GW0 + jg (hidden units 8 jg .. 8 jg + 7 of this CTA's slice), rows ks, ks + 4, ... per lane: the hidden-side
+  // projection gh = slots W_hh^T + b_hh (r | z | n) and the previous slots.  Both are taken when the slots are produced,
+  // one stage BEFORE the attend phase whose operands overwrite the regions, so the GRU stage only adds the input side.
+  float ghv[3][RL], hprev[RL];
 #pragma unroll
-  for (int q = 0; q < HR; ++q) hreg[q] = 0.f;
+  for (int i = 0; i < RL; ++i) ghv[0][i] = ghv[1][i] = ghv[2][i] = hprev[i] = 0.f;
+  const int gw = warp - GW0;                         // GRU unit of this warp (valid: 0 <= gw < JH / 8)
+  const bool gru_warp = gw >= 0 && gw < JH / 8;
+  const int jl = 8 * gw + j8;                        // hidden unit within the CTA's slice ...
+  const int jgl = (int)rank * JH + (gru_warp ? jl : 0);   // ... and in the layer
 
   uint32_t itc = 0, smp = 0;                         // iteration / sample counters (mbarrier phase parities)
   const long long t_entry = clock64();
@@ -595,67 +596,44 @@ slot_attention_resident_kernel(const Args args) {
             a.x *= inv; a.y *= inv; a.z *= inv; a.w *= inv;
             for (uint32_t q = 0; q < CL; ++q) st_cluster_v4(mapa(scr_s + 2u * args.rsz + 4u * (s * LD + c), q), a);
           }
-#pragma unroll
-          for (int q = 0; q < HR; ++q) {                                 // previous slots back from registers
-            const int i = tid + q * NWT;
-            const int r = i / D;
-            if (i < S * D) R1[r * LD + (i - r * D)] = hreg[q];
-          }
         }
         SR_T();
-        cluster_barrier();                                               // (2) U complete in every CTA; R0 is free
+        cluster_barrier();                                               // (2) U complete in every CTA
         SR_T();                                                          // it+4,5: reduce | barrier 2
 
-        // ================================================================ GRU: this CTA's JH hidden units
-        // unit = (source, group of 8 hidden units): even units project U (folded input weights), odd units the previous slots
-        if (is_worker) {
-          const int nunits = 2 * (JH / 8);
-          for (int u0 = 0; u0 < nunits; u0 += NWORK) {
-            const int unit = u0 + warp;
-            const bool has = unit < nunits;
-            const int src = unit & 1, jg = unit >> 1;
-            const int jl = 8 * jg + j8;                                  // hidden unit within the CTA's slice
-            const int jgl = (int)rank * JH + jl;                         // ... and in the layer
-            float acc[3][RS];
-            float bia[3] = {0.f, 0.f, 0.f};
-            SR_TW(0);
-            if (has) {
-              const float* bsrc = src ? p.b_hh : p.b_iv;               // issued before the product: off its critical path
+        // ================================================================ GRU: this CTA's JH hidden units, input side + gates
+        SR_TW(0);
+        if (gru_warp) {
+          float bia[3];
 #pragma unroll
-              for (int g = 0; g < 3; ++g) bia[g] = __ldg(bsrc + g * D + jgl);
-              const int col[3] = {jgl, D + jgl, 2 * D + jgl};
-              dot_ks<RS, 3, 1, 3, LD>(src ? R1 : R2, ks, reinterpret_cast<const float4*>(src ? p.w_hh4 : p.w_iv4), 3 * D, col, 0,
-                                      D / 4, acc);
-              SR_TW(1);
-              if (src) {
-#pragma unroll
-                for (int g = 0; g < 3; ++g) {
-#pragma unroll
-                  for (int i = 0; i < RL; ++i) R0[(g * RS + ks + 4 * i) * JH + jl] = sel_row<RS>(acc[g], i, ks) + bia[g];
-                }
-              }
-            }
-            named_barrier(2, NWT);
+          for (int g = 0; g < 3; ++g) bia[g] = __ldg(p.b_iv + g * D + jgl);   // issued before the product: off its critical path
+          float acc[3][RS];
+          const int col[3] = {jgl, D + jgl, 2 * D + jgl};
+          dot_ks<RS, 3, 2, RS / 2, LD>(R2, ks, reinterpret_cast<const float4*>(p.w_iv4), 3 * D, col, 0, D / 4, acc);
+          SR_TW(1);
+#ifdef SR_REPEAT_GRU      // experiment: the same product again, now with its code in the instruction cache
+#pragma unroll 1
+          for (int rep = 0; rep < 2; ++rep) {
+            float acc2[3][RS];
+            dot_ks<RS, 3, 2, RS / 2, LD>(R2, ks, reinterpret_cast<const float4*>(p.w_iv4) + rep * (args.dbg ? 0 : 1), 3 * D, col, 0, D / 4, acc2);
+            if (acc2[0][0] == 12345.678f) acc[0][0] += acc2[1][1];
             SR_TW(2);
-            if (has && !src) {
+          }
+#endif
 #pragma unroll
-              for (int i = 0; i < RL; ++i) {
-                const int r = ks + 4 * i;
-                const float ar = sel_row<RS>(acc[0], i, ks), az = sel_row<RS>(acc[1], i, ks), an = sel_row<RS>(acc[2], i, ks);
-                if (r >= S) continue;
-                const float hr = R0[(0 * RS + r) * JH + jl], hz = R0[(1 * RS + r) * JH + jl], hn = R0[(2 * RS + r) * JH + jl];
-                const float rgate = 1.f / (1.f + expf(-(ar + bia[0] + hr)));
-                const float zgate = 1.f / (1.f + expf(-(az + bia[1] + hz)));
-                const float ngate = tanhf(an + bia[2] + rgate * hn);
-                const float hv = (1.f - zgate) * ngate + zgate * R1[r * LD + jgl];
-                const uint32_t dst = scr_s + 3u * args.rsz + 4u * (r * LD + jgl);
-                for (uint32_t q = 0; q < CL; ++q) st_cluster_f32(mapa(dst, q), hv);
-              }
-            }
-            SR_TW(3);
-            if (u0 + NWORK < nunits) named_barrier(2, NWT);              // scratch reuse by the next round
+          for (int i = 0; i < RL; ++i) {
+            const int r = ks + 4 * i;
+            const float ar = sel_row<RS>(acc[0], i, ks), az = sel_row<RS>(acc[1], i, ks), an = sel_row<RS>(acc[2], i, ks);
+            if (r >= S) continue;
+            const float rgate = 1.f / (1.f + expf(-(ar + bia[0] + ghv[0][i])));       // GRUCell, PyTorch gate order r | z | n
+            const float zgate = 1.f / (1.f + expf(-(az + bia[1] + ghv[1][i])));
+            const float ngate = tanhf(an + bia[2] + rgate * ghv[2][i]);
+            const float hv = (1.f - zgate) * ngate + zgate * hprev[i];
+            const uint32_t dst = scr_s + 3u * args.rsz + 4u * (r * LD + jgl);
+            for (uint32_t q = 0; q < CL; ++q) st_cluster_f32(mapa(dst, q), hv);
           }
         }
+        SR_TW(3);
         SR_T();
         cluster_barrier();                                               // (3) h' complete in every CTA (R3)
         SR_T();                                                          // it+6,7: GRU | barrier 3
@@ -664,19 +642,26 @@ slot_attention_resident_kernel(const Args args) {
         if (is_worker) {
           layernorm_rows<D>(R3, R2, LD, S, p.ln_m_g, p.ln_m_b, p.ln_m_eps, warp, NWORK, lane);
           named_barrier(2, NWT);
-          for (int g = warp; g < MC / 8; g += NWORK) {
-            const int c = (int)rank * MC + 8 * g + j8;
-            float acc[1][RS];
-            const int col[1] = {c};
-            const float bias = __ldg(p.b1 + c);
-            dot_ks<RS, 1, 2, 3, LD>(R2, ks, reinterpret_cast<const float4*>(p.w1_4), M, col, 0, D / 4, acc);
+          for (int u = warp; u < MC / (8 * NGC); u += NWORK) {
+            int col[NGC];
+            float bias[NGC];
 #pragma unroll
-            for (int i = 0; i < RL; ++i) {
-              const int r = ks + 4 * i;
-              const float v = fmaxf(sel_row<RS>(acc[0], i, ks) + bias, 0.f);
-              if (r >= S) continue;
-              const uint32_t dst = scr_s + 4u * (r * LDM + c);
-              for (uint32_t q = 0; q < CL; ++q) st_cluster_f32(mapa(dst, q), v);
+            for (int g = 0; g < NGC; ++g) {
+              col[g] = (int)rank * MC + 8 * (NGC * u + g) + j8;
+              bias[g] = __ldg(p.b1 + col[g]);
+            }
+            float acc[NGC][RS];
+            dot_ks<RS, NGC, 4, RS, LD>(R2, ks, reinterpret_cast<const float4*>(p.w1_4), M, col, 0, D / 4, acc);
+#pragma unroll
+            for (int g = 0; g < NGC; ++g) {
+#pragma unroll
+              for (int i = 0; i < RL; ++i) {
+                const int r = ks + 4 * i;
+                const float v = fmaxf(sel_row<RS>(acc[g], i, ks) + bias[g], 0.f);
+                if (r >= S) continue;
+                const uint32_t dst = scr_s + 4u * (r * LDM + col[g]);
+                for (uint32_t q = 0; q < CL; ++q) st_cluster_f32(mapa(dst, q), v);
+              }
             }
           }
         }
@@ -687,35 +672,43 @@ slot_attention_resident_kernel(const Args args) {
         // ================================================================ slots = h' + y1 W_2^T + b_2, this CTA's JH channels (split-K over warps)
         if (is_worker) {
           constexpr int nq = M / 4;
-          const int ngrp = JH / 8;
-          int ksp = 4;                                                   // warps per column group; partial sums meet in R2
-          while (ksp > 1 && (ngrp * ksp > NWORK || nq % (8 * ksp) || ksp * RS * JH * 4 > args.rsz)) --ksp;
-          const int unit = warp, g = unit / ksp, kpart = unit - g * ksp;
+          const int ngrp = JH / (8 * NGC);                               // column units of 8 NGC channels
+          int ksp = 4;                                                   // warps per column unit; partial sums meet in R2
+          while (ksp > 1 && (ngrp * ksp > NWORK || nq % (16 * ksp) || ksp * RS * JH * 4 > args.rsz)) --ksp;
+          const int unit = warp, u = unit / ksp, kpart = unit - u * ksp;
           const bool has = unit < ngrp * ksp;                            // (ngrp <= NWORK checked by the entry point)
-          const int c = (int)rank * JH + 8 * g + j8;
-          float acc[1][RS];
-          float mine[RL];                                                // rows ks, ks + 4, ... of this lane
-          const float bias2 = __ldg(p.b2 + (has ? c : 0));
-          if (has) {
-            const int col[1] = {c};
-            const int span = nq / ksp;
-            dot_ks<RS, 1, 2, 3, LDM>(R0, ks, reinterpret_cast<const float4*>(p.w2_4), D, col, kpart * span, (kpart + 1) * span, acc);
+          int col[NGC];
+          float bias2[NGC];
 #pragma unroll
-            for (int i = 0; i < RL; ++i) {
-              mine[i] = sel_row<RS>(acc[0], i, ks);
-              if (kpart) R2[((kpart - 1) * RS + ks + 4 * i) * JH + 8 * g + j8] = mine[i];
-            }
+          for (int g = 0; g < NGC; ++g) {
+            col[g] = (int)rank * JH + (has ? 8 * (NGC * u + g) + j8 : 0);
+            bias2[g] = __ldg(p.b2 + col[g]);
+          }
+          float mine[NGC][RL];                                           // rows ks, ks + 4, ... of this lane
+          if (has) {
+            float acc[NGC][RS];
+            const int span = nq / ksp;
+            dot_ks<RS, NGC, 4, RS, LDM>(R0, ks, reinterpret_cast<const float4*>(p.w2_4), D, col, kpart * span, (kpart + 1) * span, acc);
+#pragma unroll
+            for (int g = 0; g < NGC; ++g)
+#pragma unroll
+              for (int i = 0; i < RL; ++i) {
+                mine[g][i] = sel_row<RS>(acc[g], i, ks);
+                if (kpart) R2[((kpart - 1) * RS + ks + 4 * i) * JH + (col[g] - (int)rank * JH)] = mine[g][i];
+              }
           }
           named_barrier(2, NWT);
           if (has && !kpart) {
 #pragma unroll
-            for (int i = 0; i < RL; ++i) {
-              const int r = ks + 4 * i;
-              float v = mine[i];
-              if (r < S)
-                for (int k = 1; k < ksp; ++k) v += R2[((k - 1) * RS + r) * JH + 8 * g + j8];
-              mine[i] = v + bias2 + R3[(r < S ? r : 0) * LD + c];
-            }
+            for (int g = 0; g < NGC; ++g)
+#pragma unroll
+              for (int i = 0; i < RL; ++i) {
+                const int r = ks + 4 * i;
+                float v = mine[g][i];
+                if (r < S)
+                  for (int k = 1; k < ksp; ++k) v += R2[((k - 1) * RS + r) * JH + (col[g] - (int)rank * JH)];
+                mine[g][i] = v + bias2[g] + R3[(r < S ? r : 0) * LD + col[g]];
+              }
           }
           named_barrier(2, NWT);                                         // every partial sum in R2 has been consumed
           if (has && !kpart) {
@@ -723,12 +716,14 @@ slot_attention_resident_kernel(const Args args) {
             // a push could land in a peer's split-K scratch before that peer has consumed it)
             float* s_out = p.slots_out + (size_t)b * S * D;
 #pragma unroll
-            for (int i = 0; i < RL; ++i) {
-              const int r = ks + 4 * i;
-              if (r >= S) continue;
-              if (last) s_out[r * D + c] = mine[i];
-              else R2[r * LD + c] = mine[i];
-            }
+            for (int g = 0; g < NGC; ++g)
+#pragma unroll
+              for (int i = 0; i < RL; ++i) {
+                const int r = ks + 4 * i;
+                if (r >= S) continue;
+                if (last) s_out[r * D + col[g]] = mine[g][i];
+                else R2[r * LD + col[g]] = mine[g][i];
+              }
           }
         }
         SR_T();
@@ -754,41 +749,58 @@ slot_attention_resident_kernel(const Args args) {
           layernorm_rows<D>(R2, R3, LD, S, p.ln_q_g, p.ln_q_b, p.ln_q_eps, warp, NWORK, lane);
           named_barrier(2, NWT);
           const int DC = DIN / CL;                       // channels of the projection per CTA
-          const int ngrp = DC / 8 + (rank == 0 ? 1 : 0); // rank 0 also owns the bias column (Din)
-          for (int g = warp; g < ngrp; g += NWORK) {
-            const bool bias_grp = g == DC / 8;
-            const int c = bias_grp ? DIN + j8 : (int)rank * DC + 8 * g + j8;
-            float acc[1][RS];
-            const int col[1] = {c < ldq ? c : ldq - 1};
-            dot_ks<RS, 1, 2, 3, LD>(R3, ks, reinterpret_cast<const float4*>(p.w_qa4), ldq, col, 0, D / 4, acc);
+          const int nun = DC / (8 * NGC);                // units of 8 NGC channels; rank 0 also owns the bias column (Din)
+          if (gru_warp) {
+            // hidden-side GRU projection of the NEXT iteration and the slots it will gate, into registers
+            float bia[3];
+#pragma unroll
+            for (int g = 0; g < 3; ++g) bia[g] = __ldg(p.b_hh + g * D + jgl);
+            float acc[3][RS];
+            const int col[3] = {jgl, D + jgl, 2 * D + jgl};
+            dot_ks<RS, 3, 2, RS / 2, LD>(R2, ks, reinterpret_cast<const float4*>(p.w_hh4), 3 * D, col, 0, D / 4, acc);
 #pragma unroll
             for (int i = 0; i < RL; ++i) {
-              const int r = ks + 4 * i;                  // (warp-uniform trip count: shuffles below are executed by all lanes)
-              const float v = sel_row<RS>(acc[0], i, ks);
-              const __half h = __float2half_rn(v);
-              const __half l = __float2half_rn(v - __half2float(h));
-              const uint32_t mine = (uint32_t)__half_as_ushort(h) | ((uint32_t)__half_as_ushort(l) << 16);
-              const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 1);
-              if (r >= S) continue;
-              if (bias_grp) {
-                if (j8 == 0)
-                  for (uint32_t q = 0; q < CL; ++q) st_cluster_f32(mapa(ctl_s + (uint32_t)offsetof(Ctl, cb) + 4u * r, q), v);
-              } else {
-                // even lanes store the hi-plane word of channels (c, c + 1), odd lanes the lo-plane word of (c - 1, c)
-                const int ce = c & ~1;
-                const int kb = ce >> 6, cc = ce & 63;
-                const uint32_t word = (j8 & 1) ? ((other >> 16) | (mine & 0xffff0000u)) : ((mine & 0xffffu) | (other << 16));
-                const uint32_t off = kb * (2 * SP * 128) + (((cc >> 3) ^ (r & 7)) << 4) + (cc & 7) * 2 + r * 128 +
-                                     ((j8 & 1) ? SP * 128 : 0);
-                for (uint32_t q = 0; q < CL; ++q) st_cluster_u32(mapa(scr_s + off, q), word);
+              const int r = ks + 4 * i;
+#pragma unroll
+              for (int g = 0; g < 3; ++g) ghv[g][i] = sel_row<RS>(acc[g], i, ks) + bia[g];
+              hprev[i] = R2[(r < S ? r : 0) * LD + jgl];
+            }
+          } else if ((warp < GW0 ? warp : warp - JH / 8) < nun + (rank == 0 ? 1 : 0)) {   // projection units on the other workers
+            const int un = warp < GW0 ? warp : warp - JH / 8;
+            const bool bias_unit = un == nun;
+            int c[NGC], col[NGC];
+#pragma unroll
+            for (int g = 0; g < NGC; ++g) {
+              c[g] = bias_unit ? DIN + 8 * g + j8 : (int)rank * DC + 8 * (NGC * un + g) + j8;
+              col[g] = c[g] < ldq ? c[g] : ldq - 1;
+            }
+            float acc[NGC][RS];
+            dot_ks<RS, NGC, 4, RS, LD>(R3, ks, reinterpret_cast<const float4*>(p.w_qa4), ldq, col, 0, D / 4, acc);
+#pragma unroll
+            for (int g = 0; g < NGC; ++g) {
+#pragma unroll
+              for (int i = 0; i < RL; ++i) {
+                const int r = ks + 4 * i;                // (warp-uniform trip count: the shuffle is executed by all lanes)
+                const float v = sel_row<RS>(acc[g], i, ks);
+                const __half h = __float2half_rn(v);
+                const __half l = __float2half_rn(v - __half2float(h));
+                const uint32_t mine = (uint32_t)__half_as_ushort(h) | ((uint32_t)__half_as_ushort(l) << 16);
+                const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 1);
+                if (r >= S) continue;
+                if (bias_unit) {
+                  if (g == 0 && j8 == 0)
+                    for (uint32_t q = 0; q < CL; ++q) st_cluster_f32(mapa(ctl_s + (uint32_t)offsetof(Ctl, cb) + 4u * r, q), v);
+                } else {
+                  // even lanes store the hi-plane word of channels (c, c + 1), odd lanes the lo-plane word of (c - 1, c)
+                  const int ce = c[g] & ~1;
+                  const int kb = ce >> 6, cc = ce & 63;
+                  const uint32_t word = (j8 & 1) ? ((other >> 16) | (mine & 0xffff0000u)) : ((mine & 0xffffu) | (other << 16));
+                  const uint32_t off = kb * (2 * SP * 128) + (((cc >> 3) ^ (r & 7)) << 4) + (cc & 7) * 2 + r * 128 +
+                                       ((j8 & 1) ? SP * 128 : 0);
+                  for (uint32_t q = 0; q < CL; ++q) st_cluster_u32(mapa(scr_s + off, q), word);
+                }
               }
             }
-          }
-#pragma unroll
-          for (int q = 0; q < HR; ++q) {
-            const int i = tid + q * NWT;
-            const int r = i / D;
-            hreg[q] = i < S * D ? R2[r * LD + (i - r * D)] : 0.f;
           }
         }
         fence_proxy_async_all();                         // operand rows were written through the generic proxy (also remotely)
@@ -905,7 +917,8 @@ static bool geometry(int64_t N, int64_t S, int64_t Din, int64_t D, int64_t M, Ge
     if (scr < qbytes + nt * abytes) continue;
     const int cl = N <= 4 * nt * TILE ? 4 : 8;
     if (N > (int64_t)cl * nt * TILE) continue;
-    if (D % (8 * cl) || M % (8 * cl) || Din % (8 * cl) || D / (8 * cl) > g.nwork || M % 16) continue;
+    // one GRU warp per 8 hidden units after the softmax warps; the projection units (+ bias unit) take the other workers
+    if (D % (8 * cl) || 4 * nt + D / (8 * cl) > g.nwork || 2 * (D / (8 * cl)) + 1 > g.nwork || M % 16) continue;
     const int rsz = rsz_of(cl);
     if (4 * rsz > scr) continue;
     if (3 * rsz + g.rs * (int)(D + 4) * 4 > scr + 1024) continue;   // rows S..RS-1 of region 3 are read (and discarded)

@@ -48,7 +48,7 @@ def main():
         n = len(ITER_LABELS) - (2 if it == a.iters - 1 else 0)
         labels += ['it%d: %s' % (it, l) for l in ITER_LABELS[:n]]
     full = buf.cpu().tolist()
-    print('GRU phase of iteration 0, per worker warp: start | dot done | after barrier | gates + pushes done')
+    print('GRU phase of iteration 0, per worker warp: start | input-side product done | - | gates + pushes done')
     for w in range(18):
         print('  warp %2d  ' % w + '  '.join('%7d' % full[128 + 4 * w + k] for k in range(4)))
     prev = 0
