@@ -45,6 +45,15 @@ def load_peaks():
     return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0}, 'fallback'
 
 
+def gemm_traffic(batch):
+    """DRAM bytes per gemm_kernel launch from the committed ncu capture of the same workload (profiles/); None when the
+    capture does not match the benchmarked batch."""
+    p = os.path.join(ROOT, 'profiles', 'r2c_dram_traffic_per_kernel.json')
+    if batch != 256 or not os.path.exists(p):
+        return None
+    return json.load(open(p))['gemm_kernel_inference_b256']['dram_bytes_per_launch']
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
@@ -265,7 +274,9 @@ def run_ours(args):
                     'd2h_bytes_per_step': out_h.numel() * 4},
             'gpu_launches': int(launches_per_step * args.steps),
             'roofline': {'bound': 'tensor', 'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s',
-                         'frac': ach / peak_tf, 'traffic': None,
+                         'frac': ach / peak_tf, 'traffic': gemm_traffic(B),
+                         'traffic_source': 'profiles/r2c_dram_traffic_per_kernel.json: dram__bytes_read.sum + dram__bytes_write.sum '
+                                           'per gemm_kernel launch (average over the launches of one UNet evaluation at B=256, ncu)',
                          'kernel': 'sdb::gemm_kernel (tcgen05 kind::f16, 3 MMA passes per algorithmic product)',
                          'peak_source': peak_src + ' bf16 sustained', 'tensor_pipe_frac': 3 * ach / peak_tf,
                          'gemm_share_of_unet_time': roof['ms'] / (ms / args.steps / NFE), 'launches': roof['launches'],
