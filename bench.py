@@ -360,16 +360,17 @@ class FullImageModel(torch.nn.Module):
 class FullVideoModel(FullImageModel):
     """SAViDiffusion of BASELINE configs[2] (MOVi-D 128x128, T = 6 frames per clip, 11 slots, 2 Slot-Attention iterations per
     frame): the image model applied per frame with the slots carried from frame to frame through the TransformerPredictor
-    (savi_diffusion.py:169-216, predictor.py:20-44: 2 layers, 4 heads, ffn 4 D, norm_first -- the reference's own
-    nn.TransformerEncoder, kept as PyTorch) and the LDM loss over all B*T frames (savi_diffusion.py: flatten(0, 1))."""
+    (savi_diffusion.py:169-216, predictor.py:20-44: 2 layers, 4 heads, ffn 4 D, norm_first -- slotdiffusion_b200.predictor,
+    forward + backward on the library's kernels, dropout 0.1 active) and the LDM loss over all B*T frames
+    (savi_diffusion.py: flatten(0, 1))."""
 
     def __init__(self, dev, frames=6, iters=2):
         super().__init__(dev)
         from slotdiffusion_b200.slot_attention import SlotAttentionWMask
         self.frames = frames
         self.slot_attention = SlotAttentionWMask(D, iters, S, D, 2 * D).to(dev)
-        layer = torch.nn.TransformerEncoderLayer(d_model=D, nhead=4, dim_feedforward=4 * D, norm_first=True, batch_first=True)
-        self.predictor = torch.nn.TransformerEncoder(layer, num_layers=2, enable_nested_tensor=False).to(dev)
+        from slotdiffusion_b200.predictor import TransformerPredictor
+        self.predictor = TransformerPredictor(d_model=D, num_layers=2, num_heads=4, ffn_dim=4 * D, norm_first=True).to(dev)
 
     def eager_params(self):
         return super().eager_params() + list(self.predictor.parameters())
@@ -552,7 +553,7 @@ def train_bench(args, dev, world, rank, full=True, video=0):
             'encoder features / VQ latents synthetic (hot modules only)')
     if video:
         what = ('SAViDiffusion, BASELINE configs[2] (MOVi-D shape): %d clips x %d frames 128x128 per GPU, 11 slots, 2 Slot-Attention '
-                'iterations per frame with the slots carried through the TransformerPredictor (PyTorch), ResNet18-GN encoder '
+                'iterations per frame with the slots carried through the TransformerPredictor (B200 kernels, dropout 0.1), ResNet18-GN encoder '
                 'fwd+bwd, frozen VQ-VAE encoder, UNet fwd+bwd over all frames, gradient all-reduce, fused Adam; value = frames/s'
                 % (B, video))
     return {'metric': 'train_step_frames_per_sec' if video else 'train_step_samples_per_sec',

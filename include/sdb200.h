@@ -344,6 +344,22 @@ int sdb_lincomb(float* out, const float* x, const float* m0, const float* m1, fl
                 int64_t n, void* stream);
 
 
+/* ------------------------------------------------------------------ slot transition function (TransformerPredictor,
+ * video_based/models/predictor.py:20-44: nn.TransformerEncoder over the [B, S, D] slots between two video frames).
+ * Multi-head self-attention over S <= 32 slot tokens per sample on the fused in_proj rows qkv [B*S, ld >= 3 D]
+ * (q | k | v, head h at columns h*dh of each third; nn.MultiheadAttention), head dims 32 / 48 / 64, with dropout on the
+ * attention probabilities (counter-based mask: seed, element index, optional device-resident step counter); out [B*S, D].
+ * The backward recomputes the probabilities and the mask: dqkv [B*S, 3 D] (dense). */
+int sdb_token_attention_supported(int64_t S, int64_t dh);
+int sdb_token_attention(const float* qkv, int64_t ld, float* out, int64_t B, int64_t S, int heads, int dh, float scale,
+                        float drop_p, uint64_t seed, const uint64_t* seed_dev, void* stream);
+int sdb_token_attention_bwd(const float* qkv, int64_t ld, const float* dout, float* dqkv, int64_t B, int64_t S, int heads,
+                            int dh, float scale, float drop_p, uint64_t seed, const uint64_t* seed_dev, void* stream);
+/* out = (res ? res : 0) + dropout(x)  (nn.TransformerEncoderLayer dropout / dropout1 / dropout2 + residual add); the
+ * backward of the dropout is the same call on dy with res = NULL */
+int sdb_dropout_add(const float* x, const float* res, float* out, int64_t n, float drop_p, uint64_t seed,
+                    const uint64_t* seed_dev, void* stream);
+
 /* ================================================================== backward (training) entry points
  * Replace torch autograd of the forward lines cited above (LDM.loss_function, ldm.py:59-83 -> UNet backward;
  * SlotAttention backward through all iterations, slot_attention.py:78-102).  The contractions of the backward pass are

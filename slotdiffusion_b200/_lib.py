@@ -108,6 +108,12 @@ SIGNATURES = {
                                                c_int64, c_int64, c_float, c_float, c_void_p]),
     'sdb_slot_update_supported': (c_int, [c_int64, c_int64, c_int64, c_int64]),
     'sdb_slot_update': (c_int, [POINTER(SdbSlotUpdate), c_void_p]),
+    'sdb_token_attention_supported': (c_int, [c_int64, c_int64]),
+    'sdb_token_attention': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_float, c_float, c_uint64,
+                                    c_void_p, c_void_p]),
+    'sdb_token_attention_bwd': (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_float,
+                                        c_float, c_uint64, c_void_p, c_void_p]),
+    'sdb_dropout_add': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_uint64, c_void_p, c_void_p]),
     'sdb_slot_attention_resident_supported': (c_int, [c_int64, c_int64, c_int64, c_int64, c_int64]),
     'sdb_slot_attention_resident': (c_int, [POINTER(SdbSlotAttentionResident), c_void_p]),
     'sdb_slot_attention_resident_debug': (c_int, [c_void_p]),

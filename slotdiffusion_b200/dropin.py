@@ -19,6 +19,7 @@ training loop) keeps running as shipped:
   video_based/models/savi.py:17           SlotAttention            ...SlotAttention
   video_based/models/savi_diffusion.py:5,10 SlotAttention(WMask)   ...SlotAttention / SlotAttentionWMask
   {img,video}_based/models/ddpm/ddpm.py:24  UNetModel              slotdiffusion_b200.unet.UNetModel
+  video_based/models/savi.py:10            TransformerPredictor     slotdiffusion_b200.predictor.TransformerPredictor (fwd + bwd)
   video_based/models/vqvae/VQVAE.py:9      Encoder, Decoder         slotdiffusion_b200.vqvae.Encoder / Decoder (frozen, no-grad)
   img_based/models/slot_attention.py:8, video_based/models/savi.py:8  resnet18, resnet34   slotdiffusion_b200.resnet (fwd + bwd)
   {img,video}_based/models/ddpm/cond_ddpm.py:15  NoiseScheduleVP,  thin adapters (below) that route the one sampler
@@ -185,7 +186,7 @@ def _graphed_class(cls):
     return Graphed
 
 
-def install(tasks=_TASKS, sampler=True, boundary=True, vqvae=True, encoder=True, graph=False):
+def install(tasks=_TASKS, sampler=True, boundary=True, vqvae=True, encoder=True, graph=False, predictor=True):
     """Rebind the reference's hot-path names to the B200 implementations (idempotent).  The reference package
     `slotdiffusion` must be importable (on sys.path / installed).
     boundary: also route q_sample (DDPM._sample_xt_from_x0, ddpm.py:161-165), F.mse_loss of LDM / CondDDPM.loss_function
@@ -197,6 +198,7 @@ def install(tasks=_TASKS, sampler=True, boundary=True, vqvae=True, encoder=True,
     from .slot_attention import SlotAttention, SlotAttentionWMask
     from .unet import UNetModel
     from . import boundary as _bd
+    SlotAttentionEager, SlotAttentionWMaskEager = SlotAttention, SlotAttentionWMask
     if graph:
         # graph=True: the modules the reference constructs replay their training forward / backward schedules from CUDA
         # graphs (graphed.py) -- for the reference's eager nerv loop, where ~36 ms of Python per un-captured UNet step
@@ -216,11 +218,19 @@ def install(tasks=_TASKS, sampler=True, boundary=True, vqvae=True, encoder=True,
     for task in tasks:
         base = f'slotdiffusion.{task}.models.'
         sa_mod, wmask_mod = ('slot_attention', 'sa_diffusion') if task == 'img_based' else ('savi', 'savi_diffusion')
+        # video models call Slot Attention (and the predictor) once per FRAME before a single backward
+        # (savi_diffusion.py:183-196); a graphed callable cannot be replayed twice before its backward, so the recurrent
+        # modules of video_based stay launch-by-launch under graph=True (UNet / encoder, called once per step, are graphed)
+        sa_cls, sa_wm_cls = (SlotAttention, SlotAttentionWMask) if task == 'img_based' else \
+            (SlotAttentionEager, SlotAttentionWMaskEager)
         m = importlib.import_module(base + sa_mod)
-        _rebind(m, 'SlotAttention', SlotAttention)
+        _rebind(m, 'SlotAttention', sa_cls)
+        if predictor and hasattr(m, 'TransformerPredictor'):
+            from .predictor import TransformerPredictor
+            _rebind(m, 'TransformerPredictor', TransformerPredictor)      # savi.py:10, built at savi.py:331-336
         m = importlib.import_module(base + wmask_mod)
-        _rebind(m, 'SlotAttention', SlotAttention)
-        _rebind(m, 'SlotAttentionWMask', SlotAttentionWMask)
+        _rebind(m, 'SlotAttention', sa_cls)
+        _rebind(m, 'SlotAttentionWMask', sa_wm_cls)
         m = importlib.import_module(base + 'ddpm.ddpm')
         _rebind(m, 'UNetModel', UNetModel)
         if encoder:

@@ -667,6 +667,43 @@ def slot_attention_resident(w, x, slots_in, iterations, ln_in_eps, attn_eps, M, 
     return slots_out, mask
 
 
+def token_attention_supported(S, dh):
+    return bool(lib().sdb_token_attention_supported(S, dh))
+
+
+def token_attention(qkv, B, S, heads, drop_p=0.0, seed=0):
+    """Multi-head self-attention over S slot tokens per sample on the fused in_proj rows qkv [B*S, 3D] -> [B*S, D]."""
+    _f32(qkv)
+    D = qkv.shape[1] // 3
+    out = torch.empty(B * S, D, dtype=torch.float32, device=qkv.device)
+    dh = D // heads
+    check(lib().sdb_token_attention(_p(qkv), qkv.stride(0), _p(out), B, S, heads, dh, dh ** -0.5, float(drop_p), int(seed),
+                                    _p(dropout_step_counter(qkv.device)) if drop_p > 0 else None, _stream()),
+          'sdb_token_attention')
+    return out
+
+
+def token_attention_bwd(qkv, dout, B, S, heads, drop_p=0.0, seed=0):
+    D = qkv.shape[1] // 3
+    dqkv = torch.empty(B * S, 3 * D, dtype=torch.float32, device=qkv.device)
+    dh = D // heads
+    assert dout.is_contiguous()
+    check(lib().sdb_token_attention_bwd(_p(qkv), qkv.stride(0), _p(dout), _p(dqkv), B, S, heads, dh, dh ** -0.5,
+                                        float(drop_p), int(seed),
+                                        _p(dropout_step_counter(qkv.device)) if drop_p > 0 else None, _stream()),
+          'sdb_token_attention_bwd')
+    return dqkv
+
+
+def dropout_add(x, res, drop_p, seed):
+    """res + dropout(x) (res may be None); counter-based mask (seed, element index, device step counter)."""
+    assert x.is_contiguous() and (res is None or res.is_contiguous())
+    out = torch.empty_like(x)
+    check(lib().sdb_dropout_add(_p(x), _p(res), _p(out), x.numel(), float(drop_p), int(seed),
+                                _p(dropout_step_counter(x.device)), _stream()), 'sdb_dropout_add')
+    return out
+
+
 def gru_gates(gi, gh, h):
     R, D = h.shape
     out = torch.empty_like(h)

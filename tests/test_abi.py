@@ -75,7 +75,7 @@ def test_every_entry_point_rejects_null_and_zero_arguments():
     queries = {'sdb_version', 'sdb_last_error', 'sdb_launch_count', 'sdb_attention_tc_supported',
                'sdb_slot_attend_workspace', 'sdb_slot_attend_fused_supported', 'sdb_slot_attend_fused_debug',
                'sdb_slot_attend_fused_workspace', 'sdb_slot_attend_fused_chunks', 'sdb_slot_attend_fused_ascale',
-               'sdb_slot_update_supported', 'sdb_slot_attention_resident_supported', 'sdb_slot_attention_resident_debug', 'sdb_slot_attention_resident_wave',
+               'sdb_slot_update_supported', 'sdb_token_attention_supported', 'sdb_slot_attention_resident_supported', 'sdb_slot_attention_resident_debug', 'sdb_slot_attention_resident_wave',
                'sdb_set_pack_mode'}      # (fmt = 0, default stream) is a VALID call: a mode switch, no operands
     for name, (res, args) in _lib.SIGNATURES.items():
         if name in queries:

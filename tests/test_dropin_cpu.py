@@ -106,6 +106,9 @@ def test_install_swaps_hot_path_inside_unmodified_reference(dropin, task, rel):
     assert type(new_model.dm_decoder.vae.vqvae.encoder) is b200_vqvae.Encoder
     assert type(new_model.dm_decoder.vae.vqvae.decoder) is b200_vqvae.Decoder
     assert not any(p.requires_grad for p in new_model.dm_decoder.vae.parameters())      # frozen (VQVAE.py:172-176)
+    if task == 'video_based':      # the slot transition function between frames (savi.py:331-336)
+        from slotdiffusion_b200.predictor import TransformerPredictor
+        assert type(new_model.predictor) is TransformerPredictor and type(ref_model.predictor) is not TransformerPredictor
     # ... everything else is still the reference's own code
     assert type(new_model.dm_decoder) is type(ref_model.dm_decoder)
     assert type(new_model.dm_decoder.vae) is type(ref_model.dm_decoder.vae)

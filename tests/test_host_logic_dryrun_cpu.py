@@ -15,7 +15,7 @@ from oracle import slot_attention_ref as sa_ref
 
 QUERIES = {'sdb_version', 'sdb_last_error', 'sdb_launch_count', 'sdb_attention_tc_supported', 'sdb_slot_attend_workspace',
            'sdb_slot_attend_fused_supported', 'sdb_slot_attend_fused_workspace', 'sdb_slot_attend_fused_chunks',
-           'sdb_slot_attend_fused_ascale', 'sdb_slot_update_supported'}
+           'sdb_slot_attend_fused_ascale', 'sdb_slot_update_supported', 'sdb_token_attention_supported'}
 
 
 class DryLib:
@@ -214,3 +214,31 @@ def test_video_recurrence_chain_wires_up(dry):
     assert feats.grad.shape == feats.shape and init.grad is not None
     assert all(p.grad is not None for p in sa.parameters()) and all(p.grad is not None for p in predictor.parameters())
     assert dry.calls['sdb_slot_attend_bwd'] == T * 2            # iterations x frames
+
+
+@pytest.mark.parametrize('norm_first,train', [(True, False), (True, True), (False, True)])
+def test_predictor_schedules(dry, monkeypatch, norm_first, train):
+    """TransformerPredictor (predictor.py:20-44): inference, training (tape + backward) with and without dropout, pre-/post-LN;
+    T-1 calls of the same module before one backward (savi_diffusion.py:183-196) each own their gradient buffer."""
+    from slotdiffusion_b200 import predictor as pr
+    monkeypatch.setattr(pr, '_check', lambda mod, x: None)        # the CUDA-only guard; geometry support is a real query
+    B, S, D = 3, 11, 192
+    net = pr.TransformerPredictor(D, 2, 4, 4 * D, norm_first).train(train)
+    assert net._wcache is not None and pr.ops.token_attention_supported(S, D // 4)
+    with torch.no_grad():
+        y = net(torch.randn(B, S, D))
+    assert y.shape == (B, S, D)
+    n_attn = dry.calls['sdb_token_attention']
+    assert n_attn == 2 and dry.calls['sdb_gemm'] == 8
+    assert dry.calls['sdb_dropout_add'] == (6 if train else 0)
+    x = torch.randn(B, S, D, requires_grad=True)
+    a = net(x)
+    b = net(a)                                                      # second application before the backward
+    assert a.requires_grad and b.shape == (B, S, D)
+    (a.sum() + b.sum()).backward()
+    assert x.grad is not None and x.grad.shape == x.shape
+    missing = [n for n, q in net.named_parameters() if q.grad is None]
+    assert not missing, missing
+    assert all(q.grad.shape == q.shape for q in net.parameters())
+    assert dry.calls['sdb_token_attention_bwd'] == 4
+    assert dry.calls['sdb_dropout_add'] == (6 + 2 * 12 if train else 0)

@@ -150,3 +150,33 @@ def test_resnet_oracle_matches_reference_golden():
         assert rel_l2(sdg[k].grad, g['grad.' + k]) < 1e-5, k
     assert abs(checksum(sdg['layer1.0.conv1.weight'].grad)[1] - g['grad.layer1.0.conv1.weight'][1]) \
         / g['grad.layer1.0.conv1.weight'][1] < 1e-5
+
+
+PRED_CASES = {
+    'movid': (3, 15, 192, 2, 4, 768, True),
+    'clevrer': (2, 7, 128, 2, 4, 512, True),
+    'postln': (2, 11, 256, 1, 4, 512, False),
+}
+
+
+@pytest.mark.parametrize('name', sorted(PRED_CASES))
+def test_predictor_oracle_matches_reference_golden(name):
+    """oracle/predictor_ref.py pinned to the unmodified reference TransformerPredictor (predictor.py:20-44): outputs, input
+    gradient and parameter gradients of a fixed linear functional."""
+    from oracle import predictor_ref
+    g = golden('predictor')
+    B, S, D, L, Hh, F, nf = PRED_CASES[name]
+    sd = predictor_ref.random_state_dict(D, L, F, seed=900 + len(name))
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    x = seeded((B, S, D), 91).requires_grad_(True)
+    y = predictor_ref.predictor_forward(sdg, x, L, Hh, nf)
+    (y * seeded((B, S, D), 92)).sum().backward()
+    assert rel_l2(y, g[name + '.y']) < 2e-6
+    assert rel_l2(x.grad, g[name + '.dx']) < 1e-5
+    for k, v in sdg.items():
+        ref = g[name + '.grad.' + k]
+        if v.grad.dim() == 1:
+            assert rel_l2(v.grad, ref) < 2e-5, k
+        else:
+            got = checksum(v.grad)
+            assert abs(got[0] - ref[0]) <= 2e-4 * max(1.0, np.sqrt(ref[1])) and abs(got[1] - ref[1]) <= 1e-4 * ref[1], k

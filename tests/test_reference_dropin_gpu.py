@@ -34,7 +34,15 @@ def _build(task, rel, dropout=0.0):
     params.unet_dict['dropout'] = dropout            # mask streams differ (torch Philox vs counter-based): parity with p = 0
     with warnings.catch_warnings():
         warnings.simplefilter('ignore')
-        return mods.build_model(params)
+        model = mods.build_model(params)
+    pred = getattr(model, 'predictor', None)
+    if pred is not None:                             # nn.TransformerEncoderLayer(dropout=0.1): same reason, p = 0 on both sides
+        for m in pred.modules():
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0
+            if isinstance(m, torch.nn.MultiheadAttention):
+                m.dropout = 0.0
+    return model
 
 
 def _nonzero_init(model, seed=5):
@@ -164,8 +172,32 @@ def test_reference_savidiffusion_video_train_step_stock_vs_dropin(dropin):
     ref_model = ref_model.to(dev)
     img = torch.randn(B, T, 3, 128, 128, generator=torch.Generator().manual_seed(9)).clamp(-1, 1).to(dev)
     out_r, loss_r, g_r = _train_pass(ref_model, img, 321)
+    # Conditioning of the recurrence: the STOCK model again with the outputs of its predictor and Slot Attention perturbed by a relative 1e-6 (the size
+    # of the round-off difference between two correct fp32 implementations).  A ReLU of the Slot-Attention MLP that sits on
+    # its boundary flips under such a perturbation and moves the recurrent gradient groups by a fixed amount (measured:
+    # ~1e-3, the same for 1e-6 and 1e-5 -- tools/debug/video_grad_conditioning.py); that sensitivity is the floor of any
+    # stock-vs-drop-in comparison of those groups.
+    # Whether a given perturbation flips the unit is itself discrete, so the floor is the worst of a few draws.
+    def group_rel(ga, prefix):
+        d = sum((ga[k].double() - r.double()).norm().item() ** 2 for k, r in g_r.items() if k.startswith(prefix))
+        r = sum(r.double().norm().item() ** 2 for k, r in g_r.items() if k.startswith(prefix))
+        return (d / r) ** 0.5
+    gen = torch.Generator(device='cuda').manual_seed(1)
+
+    def jitter(t):
+        return t + 1e-6 * t.abs().mean() * torch.randn(t.shape, device=t.device, generator=gen)
+    hooks = [ref_model.predictor.register_forward_hook(lambda mod, inp, out: jitter(out)),
+             ref_model.slot_attention.register_forward_hook(lambda mod, inp, out: (jitter(out[0]), out[1]))]
+    floor_sa = floor_pr = 0.0
+    for _ in range(6):
+        _, _, g_p = _train_pass(ref_model, img, 321)
+        floor_sa, floor_pr = max(floor_sa, group_rel(g_p, 'slot_attention.')), max(floor_pr, group_rel(g_p, 'predictor.'))
+    for h in hooks:
+        h.remove()
     dropin.install()
     new_model = _build(*VCFG)
+    from slotdiffusion_b200.predictor import TransformerPredictor
+    assert type(new_model.predictor) is TransformerPredictor          # savi.py:331-336 built the B200 transition function
     new_model.load_state_dict(ref_model.state_dict(), strict=True)
     new_model = new_model.to(dev)
     out_n, loss_n, g_n = _train_pass(new_model, img, 321)
@@ -173,11 +205,12 @@ def test_reference_savidiffusion_video_train_step_stock_vs_dropin(dropin):
     assert abs(loss_n.item() - loss_r.item()) / abs(loss_r.item()) < 1e-3
     tot_d = sum((g_n[k].double() - r.double()).norm().item() ** 2 for k, r in g_r.items())
     tot_r = sum(r.double().norm().item() ** 2 for r in g_r.values())
-    sa_d = sum((g_n[k].double() - r.double()).norm().item() ** 2 for k, r in g_r.items() if k.startswith('slot_attention.'))
-    sa_r = sum(r.double().norm().item() ** 2 for k, r in g_r.items() if k.startswith('slot_attention.'))
-    print('video: global grad rel', (tot_d / tot_r) ** 0.5, 'slot_attention grad rel', (sa_d / sa_r) ** 0.5)
+    sa_rel, pr_rel = group_rel(g_n, 'slot_attention.'), group_rel(g_n, 'predictor.')
+    print('video: global grad rel', (tot_d / tot_r) ** 0.5, 'slot_attention grad rel', sa_rel, 'predictor grad rel', pr_rel,
+          'stock self-sensitivity (1e-6 perturbation)', floor_sa, floor_pr)
     assert (tot_d / tot_r) ** 0.5 < 1e-3
-    assert (sa_d / sa_r) ** 0.5 < 1e-3
+    assert sa_rel < max(1e-3, 1.5 * floor_sa)
+    assert pr_rel < max(1e-3, 1.5 * floor_pr)
 
 
 def test_reference_training_loop_with_graphed_dropin(dropin):

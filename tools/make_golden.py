@@ -267,6 +267,36 @@ def gen_resnet():
     print('resnet.npz', out['y128'].shape, out['y64'].shape, len(out))
 
 
+PRED_CASES = {
+    # name: (B, S, D, layers, heads, ffn, norm_first)
+    'movid': (3, 15, 192, 2, 4, 768, True),        # shipped MOVi-D / MOVi-E SAVi-diffusion predictor (head dim 48)
+    'clevrer': (2, 7, 128, 2, 4, 512, True),       # savi defaults (head dim 32)
+    'postln': (2, 11, 256, 1, 4, 512, False),      # post-LN variant, head dim 64
+}
+
+
+def gen_predictor():
+    """TransformerPredictor (video_based/models/predictor.py:20-44), eval mode (dropout off): outputs, input gradient and
+    parameter gradients of a fixed linear functional; weights: oracle.predictor_ref.random_state_dict."""
+    from slotdiffusion.video_based.models.predictor import TransformerPredictor
+    from oracle import predictor_ref
+    out = {}
+    for name, (B, S, D, L, Hh, F, nf) in PRED_CASES.items():
+        sd = predictor_ref.random_state_dict(D, L, F, seed=900 + len(name))
+        net = TransformerPredictor(d_model=D, num_layers=L, num_heads=Hh, ffn_dim=F, norm_first=nf).eval()
+        net.load_state_dict(sd, strict=True)
+        x = seeded((B, S, D), 91).requires_grad_(True)
+        y = net(x)
+        gw = seeded((B, S, D), 92)
+        (y * gw).sum().backward()
+        out[name + '.y'] = y.detach().numpy()
+        out[name + '.dx'] = x.grad.numpy()
+        for k, v in net.named_parameters():
+            out[name + '.grad.' + k] = v.grad.numpy() if v.grad.dim() == 1 else checksum(v.grad)
+    np.savez_compressed(os.path.join(OUT, 'predictor.npz'), **out)
+    print('predictor.npz', len(out))
+
+
 def gen_layout():
     """state_dict layout (ordered key -> shape) of the hot-path sub-modules inside the full reference models
     (build_model of the shipped configs): the checkpoint contract of the drop-in modules."""
@@ -319,7 +349,9 @@ def gen_layout():
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['sa', 'unet', 'dpm', 'layout', 'dpm_plan', 'vqvae', 'resnet']
+    which = sys.argv[1:] or ['sa', 'unet', 'dpm', 'layout', 'dpm_plan', 'vqvae', 'resnet', 'predictor']
+    if 'predictor' in which:
+        gen_predictor()
     if 'vqvae' in which:
         gen_vqvae()
     if 'resnet' in which:
