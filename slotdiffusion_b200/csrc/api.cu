@@ -27,6 +27,10 @@ int check_cuda(cudaError_t e, const char* what) {
   return SDB_ERR_CUDA;
 }
 
+static int g_host_pack_mode = SDB_FMT_F16X2;
+int host_pack_mode() { return g_host_pack_mode; }
+void set_host_pack_mode(int m) { g_host_pack_mode = m; }
+
 int num_sms() {
   static int n = 0;
   if (!n) {
@@ -50,5 +54,6 @@ extern "C" int sdb_set_pack_mode(int fmt, void* stream) {
   if (!rc) rc = sdb::set_pack_mode_gemm(fmt, sdb::as_stream(stream));
   if (!rc) rc = sdb::set_pack_mode_attention(fmt, sdb::as_stream(stream));
   if (!rc) rc = sdb::set_pack_mode_attention_tc(fmt, sdb::as_stream(stream));
+  if (!rc) sdb::set_host_pack_mode(fmt);
   return rc;
 }

@@ -17,6 +17,7 @@ __global__ void __launch_bounds__(ATT_THREADS)
 attention_pack_kernel(const float* __restrict__ q, int64_t ldq, const float* __restrict__ k, int64_t ldk,
                       const float* __restrict__ v, int64_t ldv, __half* __restrict__ out, int64_t Lq, int64_t Lk,
                       int heads, float scale, int64_t plane) {
+  const int pmode = g_pack_mode;   // operand format of the consumer GEMM: read once (common.cuh)
   __shared__ __align__(16) float sk[ATT_KV_TILE][D];
   __shared__ __align__(16) float sv[ATT_KV_TILE][D];
   const int h = blockIdx.y;
@@ -99,7 +100,7 @@ attention_pack_kernel(const float* __restrict__ q, int64_t ldq, const float* __r
     const int64_t o = (b * Lq + row) * C + h * D;
 #pragma unroll
     for (int i = 0; i < D; i += 4)     // operand format of the consumer GEMM follows the stream-ordered pack mode (common.cuh)
-      store_split4(out, out + plane, o + i, make_float4(acc[i] * inv, acc[i + 1] * inv, acc[i + 2] * inv, acc[i + 3] * inv));
+      store_split4(out, out + plane, o + i, make_float4(acc[i] * inv, acc[i + 1] * inv, acc[i + 2] * inv, acc[i + 3] * inv), pmode);
   }
 }
 

@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(AT_THREADS, 3)
 attention_tc_kernel(const float* __restrict__ q, int64_t ldq, const float* __restrict__ k, int64_t ldk,
                     const float* __restrict__ v, int64_t ldv, __half* __restrict__ out, int Lq, int Lk, int heads,
                     float scale, int64_t plane, int npairs) {
+  const int pmode = g_pack_mode;   // operand format of the consumer GEMM: read once (common.cuh)
   extern __shared__ uint8_t smem_raw[];
   AtSmem& sm = *reinterpret_cast<AtSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -292,10 +293,10 @@ attention_tc_kernel(const float* __restrict__ q, int64_t ldq, const float* __res
       const int h = G == 1 ? (int)blockIdx.y : pi - (int)b * heads;
       const float inv = 1.f / lrun;
       const int64_t ob = (b * Lq + lr) * C + h * AT_D;
-      if (g_pack_mode == SDB_FMT_F8C) {     // operand format of the consumer GEMM (to_out projection), common.cuh
+      if (pmode == SDB_FMT_F8C) {     // operand format of the consumer GEMM (to_out projection), common.cuh
 #pragma unroll
         for (int i = 0; i < AT_D; i += 4)
-          store_split4(out, out + plane, ob + i, make_float4(o[i] * inv, o[i + 1] * inv, o[i + 2] * inv, o[i + 3] * inv));
+          store_split4(out, out + plane, ob + i, make_float4(o[i] * inv, o[i + 1] * inv, o[i + 2] * inv, o[i + 3] * inv), pmode);
       } else {
 #pragma unroll
         for (int i = 0; i < AT_D; i += 8) {

@@ -53,8 +53,10 @@ __global__ void pack_weight_conv3_kernel(const float* __restrict__ w, __half* __
 }
 
 // ------------------------------------------------------------------ rows
+template <int PM>
 __global__ void pack_rows_kernel(const float* __restrict__ x, int64_t ldx, __half* __restrict__ out, int64_t M,
                                  int64_t K, int act) {
+  constexpr int pmode = PM;        // operand format of the consumer GEMM, chosen by the launcher (common.cuh)
   const int64_t k4 = K / 4;
   const int64_t total = M * k4;
   const int64_t plane = M * K;
@@ -66,14 +68,16 @@ __global__ void pack_rows_kernel(const float* __restrict__ x, int64_t ldx, __hal
     } else if (act == 2) {
       v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
     }
-    store_split4(out, out + plane, m * K + j * 4, v);
+    store_split4(out, out + plane, m * K + j * 4, v, pmode);
   }
 }
 
 // ------------------------------------------------------------------ LayerNorm (one warp per row)
-__global__ void layernorm_pack_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+template <int PM>
+__global__ void __launch_bounds__(256, 4) layernorm_pack_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                       const float* __restrict__ beta, float eps, __half* __restrict__ out,
                                       float* __restrict__ y, int64_t M, int C) {
+  constexpr int pmode = PM;        // operand format of the consumer GEMM, chosen by the launcher (common.cuh)
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const int64_t plane = M * (int64_t)C;
@@ -113,7 +117,7 @@ __global__ void layernorm_pack_kernel(const float* __restrict__ x, const float* 
         o.y = (v[j].y - mean) * rstd * gm.y + bt.y;
         o.z = (v[j].z - mean) * rstd * gm.z + bt.z;
         o.w = (v[j].w - mean) * rstd * gm.w + bt.w;
-        if (out) store_split4(out, out + plane, row * C + idx * 4, o);
+        if (out) store_split4(out, out + plane, row * C + idx * 4, o, pmode);
         if (y) reinterpret_cast<float4*>(y + row * C)[idx] = o;
       }
     }
@@ -169,10 +173,12 @@ __global__ void groupnorm_stats_kernel(const float* __restrict__ x1, int C1, con
   }
 }
 
+template <int PM>
 __global__ void groupnorm_apply_pack_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2,
                                             int C2, const float* __restrict__ stats,
                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                             __half* __restrict__ out, int64_t B, int64_t HW, int G, int silu) {
+  constexpr int pmode = PM;        // operand format of the consumer GEMM, chosen by the launcher (common.cuh)
   const int C = C1 + C2;
   const int c4n = C / 4;
   const int cpg = C / G;
@@ -196,7 +202,7 @@ __global__ void groupnorm_apply_pack_kernel(const float* __restrict__ x1, int C1
       float o = (r[j] - mean) * rstd * gmv[j] + btv[j];
       r[j] = silu == 1 ? silu_f(o) : (silu == 2 ? fmaxf(o, 0.f) : o);
     }
-    store_split4(out, out + plane, row * C + c, make_float4(r[0], r[1], r[2], r[3]));
+    store_split4(out, out + plane, row * C + c, make_float4(r[0], r[1], r[2], r[3]), pmode);
   }
 }
 
@@ -204,12 +210,14 @@ __global__ void groupnorm_apply_pack_kernel(const float* __restrict__ x1, int C1
 // (idn, stats_i == NULL), its normalised 1x1 projection (GN_i(idn), the `downsample` branch), or nothing (idn == NULL: the
 // stem conv1 -> bn1 -> relu, resnet.py:288-291).  Emits the fp32 rows (next block's identity) and / or the packed operand
 // of the next convolution in one pass.
+template <int PM>
 __global__ void groupnorm_add_relu_kernel(const float* __restrict__ h, const float* __restrict__ stats_h,
                                           const float* __restrict__ gamma_h, const float* __restrict__ beta_h,
                                           const float* __restrict__ idn, const float* __restrict__ stats_i,
                                           const float* __restrict__ gamma_i, const float* __restrict__ beta_i,
                                           float* __restrict__ out, __half* __restrict__ out_packed, int64_t B, int64_t HW,
                                           int C, int G) {
+  constexpr int pmode = PM;        // operand format of the consumer GEMM, chosen by the launcher (common.cuh)
   const int c4n = C / 4, cpg = C / G;
   const int64_t total = B * HW * c4n;
   const int64_t plane = B * HW * (int64_t)C;
@@ -245,20 +253,23 @@ __global__ void groupnorm_add_relu_kernel(const float* __restrict__ h, const flo
     }
     const float4 o = make_float4(r[0], r[1], r[2], r[3]);
     if (out) *reinterpret_cast<float4*>(out + row * C + c) = o;
-    if (out_packed) store_split4(out_packed, out_packed + plane, row * C + c, o);
+    if (out_packed) store_split4(out_packed, out_packed + plane, row * C + c, o, pmode);
   }
 }
 
 // GroupNorm apply (+SiLU) + pack, statistics either given ([B,G,2] mean/rstd) or derived on the fly from the
 // per-(sample, 4-channel block) partial sums that the producing GEMM epilogues accumulated (sdb_gemm `gsum`).
 // Grid (chunks, B); every thread owns 4 fixed channels (scale/shift live in registers) and strides over rows.
-__global__ void __launch_bounds__(256)
+// (256, 6): the launcher sizes the grid for six resident CTAs per SM; the inlined FP8C store path must not cost occupancy
+template <int PM>
+__global__ void __launch_bounds__(256, 6)
 groupnorm_apply_pack_fused_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ gsum1,
                                   const float* __restrict__ x2, int C2, const float* __restrict__ gsum2,
                                   const float* __restrict__ stats, const float* __restrict__ gamma,
                                   const float* __restrict__ beta, __half* __restrict__ out, int64_t B, int HW, int G,
                                   float eps, int silu, int rows_per_chunk, float drop_p, unsigned long long seed,
                                   const unsigned long long* __restrict__ seed_dev) {
+  constexpr int pmode = PM;        // operand format of the consumer GEMM, chosen by the launcher (common.cuh)
   if (seed_dev) seed += *seed_dev * 0x9E3779B97F4A7C15ull;   // per-step counter living in device memory (graph replays)
   __shared__ float s_mean[64], s_rstd[64];
   const int C = C1 + C2, c4n = C >> 2, cpg = C / G;
@@ -322,7 +333,7 @@ groupnorm_apply_pack_fused_kernel(const float* __restrict__ x1, int C1, const fl
       for (int j = 0; j < 4; ++j)
         o[j] *= dropout_scale(seed, (unsigned long long)(row * C + c + j), drop_p, inv_keep);
     }
-    store_split4(out, out + plane, row * C + c, make_float4(o[0], o[1], o[2], o[3]));
+    store_split4(out, out + plane, row * C + c, make_float4(o[0], o[1], o[2], o[3]), pmode);
   }
 }
 
@@ -399,14 +410,16 @@ __global__ void groupnorm_finalize_cb_kernel(const float* __restrict__ gsum, int
 }
 
 // GEGLU weight layout: output row r' (chunk j = r'/32) <- a-row 16j + r'%32 (r'%32 < 16) or g-row F + 16j + r'%32 - 16
+template <int PM>
 __global__ void pack_weight_geglu_kernel(const float* __restrict__ w, __half* __restrict__ out, int64_t F, int64_t K) {
+  constexpr int pmode = PM;        // operand format of the consumer GEMM, chosen by the launcher (common.cuh)
   const int64_t k4 = K / 4, total = 2 * F * k4, plane = 2 * F * K;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / k4, j = i % k4;
     const int64_t chunk = r / 32, within = r % 32;
     const int64_t srow = within < 16 ? chunk * 16 + within : F + chunk * 16 + within - 16;
     const float4 v = reinterpret_cast<const float4*>(w + srow * K)[j];
-    store_split4(out, out + plane, r * K + j * 4, v);
+    store_split4(out, out + plane, r * K + j * 4, v, pmode);
   }
 }
 __global__ void permute_geglu_bias_kernel(const float* __restrict__ bsrc, float* __restrict__ out, int64_t F) {
@@ -417,9 +430,11 @@ __global__ void permute_geglu_bias_kernel(const float* __restrict__ bsrc, float*
 }
 
 // ------------------------------------------------------------------ raw NHWC packing with layout transforms
-__global__ void pack_nhwc_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2, int C2,
+template <int PM>
+__global__ void __launch_bounds__(256, 8) pack_nhwc_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2, int C2,
                                  __half* __restrict__ out, float* __restrict__ ycat, int64_t B, int H, int W,
                                  int mode) {
+  constexpr int pmode = PM;        // operand format of the consumer GEMM, chosen by the launcher (common.cuh)
   const int C = C1 + C2;
   const int c4n = C / 4;
   const int Ho = (mode == SDB_PACK_UP2) ? 2 * H : H;
@@ -448,7 +463,7 @@ __global__ void pack_nhwc_kernel(const float* __restrict__ x1, int C1, const flo
       } else {
         dst = (((int64_t)bb * Ho + yo) * Wo + xo) * C + c;
       }
-      store_split4(out, out + plane, dst, v);
+      store_split4(out, out + plane, dst, v, pmode);
       if (ycat) *reinterpret_cast<float4*>(ycat + src * C + c) = v;
     }
     return;
@@ -472,13 +487,15 @@ __global__ void pack_nhwc_kernel(const float* __restrict__ x1, int C1, const flo
     } else {
       dst = ((b * Ho + yo) * Wo + xo) * C + c;
     }
-    store_split4(out, out + plane, dst, v);
+    store_split4(out, out + plane, dst, v, pmode);
     if (ycat) *reinterpret_cast<float4*>(ycat + src * C + c) = v;
   }
 }
 
 // ------------------------------------------------------------------ GEGLU
+template <int PM>
 __global__ void geglu_pack_kernel(const float* __restrict__ u, __half* __restrict__ out, int64_t M, int64_t F) {
+  constexpr int pmode = PM;        // operand format of the consumer GEMM, chosen by the launcher (common.cuh)
   const int64_t f4 = F / 4;
   const int64_t total = M * f4;
   const int64_t plane = M * F;
@@ -491,13 +508,15 @@ __global__ void geglu_pack_kernel(const float* __restrict__ u, __half* __restric
     o.y = a.y * gelu_erf_f(g.y);
     o.z = a.z * gelu_erf_f(g.z);
     o.w = a.w * gelu_erf_f(g.w);
-    store_split4(out, out + plane, m * F + j, o);
+    store_split4(out, out + plane, m * F + j, o, pmode);
   }
 }
 
 // ------------------------------------------------------------------ timestep embedding
+template <int PM>
 __global__ void timestep_embedding_pack_kernel(const float* __restrict__ t, __half* __restrict__ out, int64_t B,
                                                int dim) {
+  constexpr int pmode = PM;        // operand format of the consumer GEMM, chosen by the launcher (common.cuh)
   const int half = dim / 2;
   const int64_t total = B * dim;
   // four consecutive columns per thread (dim % 8 == 0: a group never straddles the cos | sin halves), written in the
@@ -515,14 +534,16 @@ __global__ void timestep_embedding_pack_kernel(const float* __restrict__ t, __ha
       const float arg = t[b] * freq;
       v[e] = j < half ? cosf(arg) : sinf(arg);
     }
-    store_split4(out, out + total, i, make_float4(v[0], v[1], v[2], v[3]));
+    store_split4(out, out + total, i, make_float4(v[0], v[1], v[2], v[3]), pmode);
   }
 }
 
 // ------------------------------------------------------------------ row softmax (+ scale) -> packed operand
 // one warp per row, N <= 4096: the row lives in registers (up to 32 float4 per lane)
+template <int PM>
 __global__ void softmax_pack_kernel(const float* __restrict__ x, int64_t ldx, float scale, float out_scale,
                                     __half* __restrict__ out, int64_t M, int N) {
+  constexpr int pmode = PM;        // operand format of the consumer GEMM, chosen by the launcher (common.cuh)
   const int lane = threadIdx.x & 31;
   const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -555,7 +576,7 @@ __global__ void softmax_pack_kernel(const float* __restrict__ x, int64_t ldx, fl
   for (int i = 0; i < 32; ++i) {
     const int j = i * 32 + lane;
     if (j < n4)
-      store_split4(out, out + plane, row * N + j * 4, make_float4(v[i].x * inv, v[i].y * inv, v[i].z * inv, v[i].w * inv));
+      store_split4(out, out + plane, row * N + j * 4, make_float4(v[i].x * inv, v[i].y * inv, v[i].z * inv, v[i].w * inv), pmode);
   }
 }
 
@@ -898,7 +919,7 @@ extern "C" int sdb_pack_weight_conv3(const float* w, void* out, int64_t Cout, in
 extern "C" int sdb_pack_rows(const float* x, int64_t ldx, void* out, int64_t M, int64_t K, int act, void* stream) {
   SDB_REQUIRE(x && out && M > 0 && K > 0 && K % 4 == 0 && ldx % 4 == 0, "sdb_pack_rows: bad args M=%lld K=%lld ldx=%lld",
               (long long)M, (long long)K, (long long)ldx);
-  pack_rows_kernel<<<grid_for(M * K / 4, 256), 256, 0, as_stream(stream)>>>(x, ldx, (__half*)out, M, K, act);
+  SDB_LAUNCH_PM(pack_rows_kernel, (grid_for(M * K / 4, 256)), (256), 0, as_stream(stream), x, ldx, (__half*)out, M, K, act);
   SDB_LAUNCH_CHECK();
   return 0;
 }
@@ -908,7 +929,7 @@ extern "C" int sdb_layernorm_pack(const float* x, const float* gamma, const floa
   SDB_REQUIRE(x && gamma && beta && (out || y) && M > 0, "sdb_layernorm_pack: null argument");
   SDB_REQUIRE(C % 4 == 0 && C <= 512, "sdb_layernorm_pack: C=%lld must be a multiple of 4 and <= 512", (long long)C);
   const int threads = 256;
-  layernorm_pack_kernel<<<grid_for(M, threads / 32), threads, 0, as_stream(stream)>>>(x, gamma, beta, eps,
+  SDB_LAUNCH_PM(layernorm_pack_kernel, (grid_for(M, threads / 32)), (threads), 0, as_stream(stream), x, gamma, beta, eps,
                                                                                       (__half*)out, y, M, (int)C);
   SDB_LAUNCH_CHECK();
   return 0;
@@ -929,7 +950,7 @@ extern "C" int sdb_groupnorm_apply_pack(const float* x1, int64_t C1, const float
                                         int G, int silu, void* stream) {
   SDB_REQUIRE(x1 && stats && gamma && beta && out, "sdb_groupnorm_apply_pack: null argument");
   SDB_REQUIRE(C1 % 4 == 0 && C2 % 4 == 0 && (C1 + C2) % G == 0, "sdb_groupnorm_apply_pack: bad channels");
-  groupnorm_apply_pack_kernel<<<grid_for(B * HW * (C1 + C2) / 4, 256), 256, 0, as_stream(stream)>>>(
+  SDB_LAUNCH_PM(groupnorm_apply_pack_kernel, (grid_for(B * HW * (C1 + C2) / 4, 256)), (256), 0, as_stream(stream), 
       x1, (int)C1, x2, (int)C2, stats, gamma, beta, (__half*)out, B, HW, G, silu);
   SDB_LAUNCH_CHECK();
   return 0;
@@ -943,7 +964,7 @@ extern "C" int sdb_pack_nhwc(const float* x1, int64_t C1, const float* x2, int64
   SDB_REQUIRE(mode != SDB_PACK_PHASE2 || (H % 2 == 0 && W % 2 == 0), "sdb_pack_nhwc: phase split needs even H, W");
   SDB_REQUIRE(!y_cat || mode != SDB_PACK_UP2, "sdb_pack_nhwc: y_cat unsupported with upsample");
   const int64_t mult = mode == SDB_PACK_UP2 ? 4 : 1;
-  pack_nhwc_kernel<<<grid_for(B * H * W * mult * (C1 + C2) / 4, 256), 256, 0, as_stream(stream)>>>(
+  SDB_LAUNCH_PM(pack_nhwc_kernel, (grid_for(B * H * W * mult * (C1 + C2) / 4, 256)), (256), 0, as_stream(stream), 
       x1, (int)C1, x2, (int)C2, (__half*)out, y_cat, B, (int)H, (int)W, mode);
   SDB_LAUNCH_CHECK();
   return 0;
@@ -951,7 +972,7 @@ extern "C" int sdb_pack_nhwc(const float* x1, int64_t C1, const float* x2, int64
 
 extern "C" int sdb_geglu_pack(const float* u, void* out, int64_t M, int64_t F, void* stream) {
   SDB_REQUIRE(u && out && M > 0 && F > 0 && F % 4 == 0, "sdb_geglu_pack: bad args");
-  geglu_pack_kernel<<<grid_for(M * F / 4, 256), 256, 0, as_stream(stream)>>>(u, (__half*)out, M, F);
+  SDB_LAUNCH_PM(geglu_pack_kernel, (grid_for(M * F / 4, 256)), (256), 0, as_stream(stream), u, (__half*)out, M, F);
   SDB_LAUNCH_CHECK();
   return 0;
 }
@@ -959,7 +980,7 @@ extern "C" int sdb_geglu_pack(const float* u, void* out, int64_t M, int64_t F, v
 extern "C" int sdb_timestep_embedding_pack(const float* t, void* out, int64_t B, int dim, void* stream) {
   SDB_REQUIRE(t && out && B > 0 && dim > 0 && dim % 2 == 0, "sdb_timestep_embedding_pack: bad args");
   SDB_REQUIRE(dim % 8 == 0, "sdb_timestep_embedding_pack: dim %% 8 == 0 required (got %d)", dim);
-  timestep_embedding_pack_kernel<<<grid_for(B * dim / 4, 128), 128, 0, as_stream(stream)>>>(t, (__half*)out, B, dim);
+  SDB_LAUNCH_PM(timestep_embedding_pack_kernel, (grid_for(B * dim / 4, 128)), (128), 0, as_stream(stream), t, (__half*)out, B, dim);
   SDB_LAUNCH_CHECK();
   return 0;
 }
@@ -981,7 +1002,7 @@ extern "C" int sdb_groupnorm_add_relu(const float* h, const float* stats_h, cons
   SDB_REQUIRE(B > 0 && HW > 0 && C > 0 && C % 4 == 0 && G > 0 && C % G == 0, "sdb_groupnorm_add_relu: bad shape C=%lld G=%d",
               (long long)C, G);
   SDB_REQUIRE(!stats_i || (idn && gamma_i && beta_i), "sdb_groupnorm_add_relu: stats_i needs idn, gamma_i, beta_i");
-  groupnorm_add_relu_kernel<<<grid_for(B * HW * C / 4, 256), 256, 0, as_stream(stream)>>>(
+  SDB_LAUNCH_PM(groupnorm_add_relu_kernel, (grid_for(B * HW * C / 4, 256)), (256), 0, as_stream(stream), 
       h, stats_h, gamma_h, beta_h, idn, stats_i, gamma_i, beta_i, out, (__half*)out_packed, B, HW, (int)C, G);
   SDB_LAUNCH_CHECK();
   return 0;
@@ -992,7 +1013,7 @@ extern "C" int sdb_softmax_pack(const float* x, int64_t ldx, float scale, float 
   SDB_REQUIRE(x && out && M > 0 && N > 0 && N % 4 == 0 && N <= 4096 && ldx % 4 == 0,
               "sdb_softmax_pack: bad args M=%lld N=%lld (N %% 4 == 0, N <= 4096)", (long long)M, (long long)N);
   const int wpb = 4;
-  softmax_pack_kernel<<<(unsigned)cdiv(M, wpb), wpb * 32, 0, as_stream(stream)>>>(x, ldx, scale, out_scale, (__half*)out, M,
+  SDB_LAUNCH_PM(softmax_pack_kernel, ((unsigned)cdiv(M, wpb)), (wpb * 32), 0, as_stream(stream), x, ldx, scale, out_scale, (__half*)out, M,
                                                                                   (int)N);
   SDB_LAUNCH_CHECK();
   return 0;
@@ -1119,7 +1140,7 @@ extern "C" int sdb_groupnorm_apply_pack_fused(const float* x1, int64_t C1, const
   const int rows_per_chunk = (int)cdiv(HW, chunks);
   chunks = cdiv(HW, rows_per_chunk);
   dim3 grid((unsigned)chunks, (unsigned)B);
-  groupnorm_apply_pack_fused_kernel<<<grid, threads, 0, as_stream(stream)>>>(
+  SDB_LAUNCH_PM(groupnorm_apply_pack_fused_kernel, (grid), (threads), 0, as_stream(stream), 
       x1, (int)C1, gsum1, x2, (int)C2, gsum2, stats, gamma, beta, (__half*)out, B, (int)HW, G, eps, silu, rows_per_chunk,
       g_drop_p, g_drop_seed, g_drop_seed_dev);
   SDB_LAUNCH_CHECK();
@@ -1173,7 +1194,7 @@ extern "C" int sdb_pack_weight_geglu(const float* w, const float* bias, void* ou
                                      void* stream) {
   SDB_REQUIRE(w && out && F > 0 && F % 16 == 0 && K > 0 && K % 4 == 0, "sdb_pack_weight_geglu: bad args F=%lld K=%lld",
               (long long)F, (long long)K);
-  pack_weight_geglu_kernel<<<grid_for(2 * F * K / 4, 256), 256, 0, as_stream(stream)>>>(w, (__half*)out, F, K);
+  SDB_LAUNCH_PM(pack_weight_geglu_kernel, (grid_for(2 * F * K / 4, 256)), (256), 0, as_stream(stream), w, (__half*)out, F, K);
   SDB_LAUNCH_CHECK();
   if (bias && bias_out) {
     permute_geglu_bias_kernel<<<grid_for(2 * F, 256), 256, 0, as_stream(stream)>>>(bias, bias_out, F);

@@ -105,12 +105,25 @@ struct GemmArgs {
 // per tile, tcgen05 cta_group::2 (UMMA 256 x bn): each CTA stages its own 128 rows of A and HALF of the W tile,
 // which halves the shared-memory fill and read traffic per flop -- with three MMA passes per product the single-CTA
 // form is shared-memory-bandwidth bound well below the tensor peak.
-template <int CG, int EPI>
+// VAR: compile-time feature set of an instance, so that the instance the UNet forward runs carries none of the code of the
+// rarer forms (measured on one B200, one evaluation at B=256: the runtime-flag version of these features cost the 144
+// pair-GEMM launches 15.4 -> 16.7 ms).  Bit 0 (VAR_F8C): FP8-corrected operands / packed outputs in the stream's pack mode
+// (passes == 2, D2 accumulator, one-stage accumulators); bit 1 (VAR_EXT): alpha != 1, 2-channel GroupNorm sums, block-
+// diagonal batching, WGRAD tap pairing.  The host picks the smallest instance that covers the call.
+constexpr int VAR_F8C = 1, VAR_EXT = 2;
+
+template <int CG, int EPI, int VAR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
             const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
             const __grid_constant__ CUtensorMap map_a_l8, const __grid_constant__ CUtensorMap map_b_l8,
             const GemmArgs g) {
+  constexpr bool kF8 = (VAR & VAR_F8C) != 0, kExt = (VAR & VAR_EXT) != 0;
+  const int pmode = kF8 ? g_pack_mode : SDB_FMT_F16X2;   // operand format of the consumer GEMM: read once (common.cuh)
+  const int acc_two = kF8 ? g.acc_two : 1;
+  const int gsum_cb = kExt ? g.gsum_cb : 4;
+  const int batch_rows = kExt ? g.batch_rows : 0;
+  const int tap_pair = kExt ? g.tap_pair : 0;
   extern __shared__ uint8_t smem_raw[];
   if (g.debug == 1) return;
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -122,7 +135,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
   const int num_items = g.n_tiles_m * g.n_tiles_n * g.splits;
   const int ksteps = g.kblocks * g.ntaps;   // k-blocks (stages) of a whole tile
   const bool three = g.passes >= 2;    // a second operand plane is staged (fp16 lo, or the two e4m3 half-planes)
-  const bool f8c = g.passes == 2;      // map_*_lo then address the h8 half-plane, map_*_l8 the l8 half-plane
+  const bool f8c = kF8 && g.passes == 2;      // map_*_lo then address the h8 half-plane, map_*_l8 the l8 half-plane
   const uint32_t b_tile_bytes = uint32_t(g.bnl) * BK * 2;
 
   if (warp == 0 && lane == 0) {
@@ -183,7 +196,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
           b0 = int(m0 / rows_per_img);
           y0 = int((m0 % rows_per_img) / g.W);
         }
-        const int bidx = g.batch_rows ? (int)(((long long)tm * g.tile_rows) / g.batch_rows) : 0;
+        const int bidx = batch_rows ? (int)(((long long)tm * g.tile_rows) / batch_rows) : 0;
         const int nrow = tn * g.bn + (int)rank * g.bnl + bidx * g.w_row_step;
         const int wk0 = bidx * g.w_k_step;
         for (int ks = ks_begin; ks < ks_end; ++ks) {
@@ -245,7 +258,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
               uint8_t* bp = pl ? b_lo : b_hi;
               for (int j = 0; j < na; ++j) {
                 int jc0 = c0 + j * 64, jcx = cx, jcy = cy, jc3 = c3;
-                if (g.tap_pair) {      // block j = tap 2 tm + j of the 64 channels (output row = tap * 64 + ci stays contiguous);
+                if (tap_pair) {      // block j = tap 2 tm + j of the 64 channels (output row = tap * 64 + ci stays contiguous);
                   const int tj = min(2 * tm + j, 8);     // the odd ninth tap repeats: its rows lie beyond M and are dropped
                   const int m0 = ks * BK, hw = g.H * g.W, bimg = m0 / hw;
                   const int yrow = (m0 - bimg * hw) / g.W, xoff = (m0 - bimg * hw) - yrow * g.W;
@@ -311,8 +324,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
         const int tile = item / g.splits, split = item - tile * g.splits;
         const int ks_begin = (int)((long long)ksteps * split / g.splits);
         const int ks_end = (int)((long long)ksteps * (split + 1) / g.splits);
-        const int as = g.acc_two ? (it & 1) : 0;
-        const uint32_t aphase = g.acc_two ? ((it >> 1) & 1) : (it & 1);
+        const int as = acc_two ? (it & 1) : 0;
+        const uint32_t aphase = acc_two ? ((it >> 1) & 1) : (it & 1);
 #if SDB_GEMM_TIMING
         const long long ta = clock64();
 #endif
@@ -408,8 +421,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
       const int tile = item / g.splits, split = item - tile * g.splits;
       const int tm = (tile / g.n_tiles_n) * CG + (int)rank, tn = tile % g.n_tiles_n;
       const bool first = split == 0;       // the split that also adds bias / rowvec / residual
-      const int as = g.acc_two ? (it & 1) : 0;
-      const uint32_t aphase = g.acc_two ? ((it >> 1) & 1) : (it & 1);
+      const int as = acc_two ? (it & 1) : 0;
+      const uint32_t aphase = acc_two ? ((it >> 1) & 1) : (it & 1);
       const long long row0l = (long long)tm * g.tile_rows + q * 32;   // first output row of this warp
       const int rows_valid = (int)min((long long)min(g.tile_rows - q * 32, 32), (long long)g.M - row0l);
       const int row0 = (int)min(row0l, (long long)g.M);
@@ -471,7 +484,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
           for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(fmaf(g.corr_scale, __uint_as_float(r2[k]), __uint_as_float(r[k])));
         }
         tmem_ld_wait();
-        if (g.alpha != 1.f) {
+        if (kExt && g.alpha != 1.f) {
 #pragma unroll
           for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(__uint_as_float(r[k]) * g.alpha);
         }
@@ -506,7 +519,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
               o.y = (a.y + ba.y) * gelu_erf_f(gg.y + bg.y);
               o.z = (a.z + ba.z) * gelu_erf_f(gg.z + bg.z);
               o.w = (a.w + ba.w) * gelu_erf_f(gg.w + bg.w);
-              store_split4(g.out_packed, g.out_packed + g.out_plane, (long long)(row0 + rr) * F + fo, o);
+              store_split4(g.out_packed, g.out_packed + g.out_plane, (long long)(row0 + rr) * F + fo, o, pmode);
             }
           }
         } else if (g.vec_ok) {
@@ -530,7 +543,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
                 else *reinterpret_cast<float4*>(dst) = v;
               }
               if (g.gsum) {
-                if (g.gsum_cb == 2) {
+                if (gsum_cb == 2) {
                   const float sa = v.x + v.y, qa = v.x * v.x + v.y * v.y, sb = v.z + v.w, qb = v.z * v.z + v.w * v.w;
                   if (i < 4) { s0 += sa; q0 += qa; s0b += sb; q0b += qb; } else { s1 += sa; q1 += qa; s1b += sb; q1b += qb; }
                 } else {
@@ -542,7 +555,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
               if (g.out_packed) {
                 if (g.out_act == 1) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
                 else if (g.out_act == 2) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-                store_split4(g.out_packed, g.out_packed + g.out_plane, m * g.N + n, v);
+                store_split4(g.out_packed, g.out_packed + g.out_plane, m * g.N + n, v, pmode);
               }
             }
           }
@@ -552,7 +565,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
             s1 += __shfl_xor_sync(0xffffffffu, s1, 8);  q1 += __shfl_xor_sync(0xffffffffu, q1, 8);
             s0 += __shfl_xor_sync(0xffffffffu, s0, 16); q0 += __shfl_xor_sync(0xffffffffu, q0, 16);
             s1 += __shfl_xor_sync(0xffffffffu, s1, 16); q1 += __shfl_xor_sync(0xffffffffu, q1, 16);
-            if (g.gsum_cb == 2) {
+            if (gsum_cb == 2) {
               s0b += __shfl_xor_sync(0xffffffffu, s0b, 8);  q0b += __shfl_xor_sync(0xffffffffu, q0b, 8);
               s1b += __shfl_xor_sync(0xffffffffu, s1b, 8);  q1b += __shfl_xor_sync(0xffffffffu, q1b, 8);
               s0b += __shfl_xor_sync(0xffffffffu, s0b, 16); q0b += __shfl_xor_sync(0xffffffffu, q0b, 16);
@@ -562,22 +575,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
               const unsigned b0 = (unsigned)row0 / g.rows_per_group;
               const unsigned b1 = (unsigned)(row0 + 16) / g.rows_per_group;
               // block index of this thread's first channel: n / cb; blocks per row: N / cb
-              const unsigned nb = g.gsum_cb == 2 ? ((unsigned)g.N >> 1) : n4;
-              const unsigned ib = g.gsum_cb == 2 ? ((unsigned)n >> 1) : ((unsigned)n >> 2);
+              const unsigned nb = gsum_cb == 2 ? ((unsigned)g.N >> 1) : n4;
+              const unsigned ib = gsum_cb == 2 ? ((unsigned)n >> 1) : ((unsigned)n >> 2);
               if (b1 == b0 || rows_valid <= 16) {
                 float* p = g.gsum + ((long long)b0 * nb + ib) * 2;
                 atomicAdd(p, s0 + s1);
                 atomicAdd(p + 1, q0 + q1);
-                if (g.gsum_cb == 2) { atomicAdd(p + 2, s0b + s1b); atomicAdd(p + 3, q0b + q1b); }
+                if (gsum_cb == 2) { atomicAdd(p + 2, s0b + s1b); atomicAdd(p + 3, q0b + q1b); }
               } else {
                 float* p = g.gsum + ((long long)b0 * nb + ib) * 2;
                 atomicAdd(p, s0);
                 atomicAdd(p + 1, q0);
-                if (g.gsum_cb == 2) { atomicAdd(p + 2, s0b); atomicAdd(p + 3, q0b); }
+                if (gsum_cb == 2) { atomicAdd(p + 2, s0b); atomicAdd(p + 3, q0b); }
                 p = g.gsum + ((long long)b1 * nb + ib) * 2;
                 atomicAdd(p, s1);
                 atomicAdd(p + 1, q1);
-                if (g.gsum_cb == 2) { atomicAdd(p + 2, s1b); atomicAdd(p + 3, q1b); }
+                if (gsum_cb == 2) { atomicAdd(p + 2, s1b); atomicAdd(p + 3, q1b); }
               }
             }
           }
@@ -683,13 +696,13 @@ static int env_int(const char* name, int dflt) {
   return (v && *v) ? atoi(v) : dflt;
 }
 
-template <int CG, int EPI>
+template <int CG, int EPI, int VAR>
 static int launch_gemm(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const CUtensorMap& mb_hi,
                        const CUtensorMap& mb_lo, const CUtensorMap& ma_l8, const CUtensorMap& mb_l8, const GemmArgs& g,
                        int groups, size_t smem, cudaStream_t st) {
   static size_t attr = 0;
   if (smem > attr) {
-    SDB_CHECK(cudaFuncSetAttribute(gemm_kernel<CG, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SDB_CHECK(cudaFuncSetAttribute(gemm_kernel<CG, EPI, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
   cudaLaunchConfig_t cfg{};
@@ -704,7 +717,7 @@ static int launch_gemm(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  SDB_CHECK(cudaLaunchKernelEx(&cfg, gemm_kernel<CG, EPI>, ma_hi, ma_lo, mb_hi, mb_lo, ma_l8, mb_l8, g));
+  SDB_CHECK(cudaLaunchKernelEx(&cfg, gemm_kernel<CG, EPI, VAR>, ma_hi, ma_lo, mb_hi, mb_lo, ma_l8, mb_l8, g));
   SDB_LAUNCH_CHECK();
   return 0;
 }
@@ -966,11 +979,21 @@ extern "C" int sdb_gemm(const SdbGemm* p, void* stream) {
   const size_t smem = (size_t)g.stages * g.stage_bytes + sizeof(GemmCtl) + 1024;
   const long long items = tiles * g.splits;
   const int groups = (int)(items < units ? items : units);
-  if (geglu)
-    return cg == 2 ? launch_gemm<2, EPI_GEGLU>(ma_hi, ma_lo, mb_hi, mb_lo, ma_l8, mb_l8, g, groups, smem, st)
-                   : launch_gemm<1, EPI_GEGLU>(ma_hi, ma_lo, mb_hi, mb_lo, ma_l8, mb_l8, g, groups, smem, st);
-  return cg == 2 ? launch_gemm<2, EPI_F32>(ma_hi, ma_lo, mb_hi, mb_lo, ma_l8, mb_l8, g, groups, smem, st)
-                 : launch_gemm<1, EPI_F32>(ma_hi, ma_lo, mb_hi, mb_lo, ma_l8, mb_l8, g, groups, smem, st);
+  // smallest instance that covers the call (see VAR_F8C / VAR_EXT at the kernel)
+  const bool v_f8 = f8c || (p->out_packed && host_pack_mode() == SDB_FMT_F8C);
+  const bool v_ext = g.alpha != 1.f || (p->gsum && g.gsum_cb == 2) || g.batch_rows != 0 || g.tap_pair != 0;
+#define SDB_GEMM_LAUNCH(CGv, EPIv, VARv) \
+  launch_gemm<CGv, EPIv, VARv>(ma_hi, ma_lo, mb_hi, mb_lo, ma_l8, mb_l8, g, groups, smem, st)
+  if (geglu) {
+    SDB_REQUIRE(!v_ext, "sdb_gemm: the GEGLU epilogue takes no alpha / 2-channel sums / batching");
+    if (v_f8) return cg == 2 ? SDB_GEMM_LAUNCH(2, EPI_GEGLU, VAR_F8C) : SDB_GEMM_LAUNCH(1, EPI_GEGLU, VAR_F8C);
+    return cg == 2 ? SDB_GEMM_LAUNCH(2, EPI_GEGLU, 0) : SDB_GEMM_LAUNCH(1, EPI_GEGLU, 0);
+  }
+  if (v_f8 && v_ext) return cg == 2 ? SDB_GEMM_LAUNCH(2, EPI_F32, VAR_F8C | VAR_EXT) : SDB_GEMM_LAUNCH(1, EPI_F32, VAR_F8C | VAR_EXT);
+  if (v_f8) return cg == 2 ? SDB_GEMM_LAUNCH(2, EPI_F32, VAR_F8C) : SDB_GEMM_LAUNCH(1, EPI_F32, VAR_F8C);
+  if (v_ext) return cg == 2 ? SDB_GEMM_LAUNCH(2, EPI_F32, VAR_EXT) : SDB_GEMM_LAUNCH(1, EPI_F32, VAR_EXT);
+  return cg == 2 ? SDB_GEMM_LAUNCH(2, EPI_F32, 0) : SDB_GEMM_LAUNCH(1, EPI_F32, 0);
+#undef SDB_GEMM_LAUNCH
 }
 
 /* issuer wait accounting of the SDB_GEMM_TIMING build: out4 = {cycles waiting for operands, cycles waiting for a free
