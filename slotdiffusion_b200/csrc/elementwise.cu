@@ -260,8 +260,9 @@ __global__ void groupnorm_add_relu_kernel(const float* __restrict__ h, const flo
 // GroupNorm apply (+SiLU) + pack, statistics either given ([B,G,2] mean/rstd) or derived on the fly from the
 // per-(sample, 4-channel block) partial sums that the producing GEMM epilogues accumulated (sdb_gemm `gsum`).
 // Grid (chunks, B); every thread owns 4 fixed channels (scale/shift live in registers) and strides over rows.
-// (256, 6): the launcher sizes the grid for six resident CTAs per SM; the inlined FP8C store path must not cost occupancy
-template <int PM>
+// (256, 6): the launcher sizes the grid for six resident CTAs per SM.  ACT (0 none / 1 SiLU / 2 ReLU) and DROP are
+// compile-time: the kernel is instruction-bound, and the UNet-inference instance <PM, 1, false> carries none of the other forms
+template <int PM, int ACT, bool DROP>
 __global__ void __launch_bounds__(256, 6)
 groupnorm_apply_pack_fused_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ gsum1,
                                   const float* __restrict__ x2, int C2, const float* __restrict__ gsum2,
@@ -320,14 +321,14 @@ groupnorm_apply_pack_fused_kernel(const float* __restrict__ x1, int C1, const fl
     const int64_t row = b * HW + r;
     const float4 v = *reinterpret_cast<const float4*>(src + row * ld);
     float o[4] = {v.x * sc[0] + sh[0], v.y * sc[1] + sh[1], v.z * sc[2] + sh[2], v.w * sc[3] + sh[3]};
-    if (silu == 1) {
+    if (ACT == 1) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) o[j] = silu_f(o[j]);
-    } else if (silu == 2) {        // ReLU (ResNet18-GN encoder: conv -> GN -> ReLU, resnet.py:76-78)
+    } else if (ACT == 2) {        // ReLU (ResNet18-GN encoder: conv -> GN -> ReLU, resnet.py:76-78)
 #pragma unroll
       for (int j = 0; j < 4; ++j) o[j] = fmaxf(o[j], 0.f);
     }
-    if (drop_p > 0.f) {
+    if (DROP) {
       const float inv_keep = 1.f / (1.f - drop_p);
 #pragma unroll
       for (int j = 0; j < 4; ++j)
@@ -431,7 +432,7 @@ __global__ void permute_geglu_bias_kernel(const float* __restrict__ bsrc, float*
 
 // ------------------------------------------------------------------ raw NHWC packing with layout transforms
 template <int PM>
-__global__ void __launch_bounds__(256, 8) pack_nhwc_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2, int C2,
+__global__ void __launch_bounds__(256) pack_nhwc_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2, int C2,
                                  __half* __restrict__ out, float* __restrict__ ycat, int64_t B, int H, int W,
                                  int mode) {
   constexpr int pmode = PM;        // operand format of the consumer GEMM, chosen by the launcher (common.cuh)
@@ -1140,9 +1141,30 @@ extern "C" int sdb_groupnorm_apply_pack_fused(const float* x1, int64_t C1, const
   const int rows_per_chunk = (int)cdiv(HW, chunks);
   chunks = cdiv(HW, rows_per_chunk);
   dim3 grid((unsigned)chunks, (unsigned)B);
-  SDB_LAUNCH_PM(groupnorm_apply_pack_fused_kernel, (grid), (threads), 0, as_stream(stream), 
-      x1, (int)C1, gsum1, x2, (int)C2, gsum2, stats, gamma, beta, (__half*)out, B, (int)HW, G, eps, silu, rows_per_chunk,
-      g_drop_p, g_drop_seed, g_drop_seed_dev);
+  {
+    cudaStream_t st = as_stream(stream);
+    const bool f8 = host_pack_mode() == SDB_FMT_F8C;
+    const bool drop = g_drop_p > 0.f;
+#define SDB_GN_LAUNCH(PMv, ACTv, DROPv)                                                                                    \
+    groupnorm_apply_pack_fused_kernel<PMv, ACTv, DROPv><<<grid, threads, 0, st>>>(                                          \
+        x1, (int)C1, gsum1, x2, (int)C2, gsum2, stats, gamma, beta, (__half*)out, B, (int)HW, G, eps, silu, rows_per_chunk, \
+        g_drop_p, g_drop_seed, g_drop_seed_dev)
+#define SDB_GN_ACT(PMv, DROPv)                          \
+    do {                                                \
+      if (silu == 1) SDB_GN_LAUNCH(PMv, 1, DROPv);      \
+      else if (silu == 2) SDB_GN_LAUNCH(PMv, 2, DROPv); \
+      else SDB_GN_LAUNCH(PMv, 0, DROPv);                \
+    } while (0)
+    if (f8) {
+      if (drop) SDB_GN_ACT(SDB_FMT_F8C, true);
+      else SDB_GN_ACT(SDB_FMT_F8C, false);
+    } else {
+      if (drop) SDB_GN_ACT(SDB_FMT_F16X2, true);
+      else SDB_GN_ACT(SDB_FMT_F16X2, false);
+    }
+#undef SDB_GN_ACT
+#undef SDB_GN_LAUNCH
+  }
   SDB_LAUNCH_CHECK();
   return 0;
 }
