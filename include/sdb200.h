@@ -205,6 +205,13 @@ int sdb_attention_pack(const float* q, int64_t ldq, const float* k, int64_t ldk,
 int sdb_attention_tc_supported(int64_t heads, int64_t d, int64_t ldq, int64_t ldk, int64_t ldv);
 int sdb_attention_tc(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv, void* out,
                      int64_t B, int64_t Lq, int64_t Lk, int heads, int d, float scale, void* stream);
+/* Few keys (Lk <= 32: the slot cross-attention, attention.py:188-205 with context = slots): fp32 CUDA-core kernel, one CTA per
+ * 32 query rows with all heads, coalesced tile loads / stores; head dim 32, heads <= 16, default operand format only
+ * (sdb_attention_fewkeys_supported) */
+int sdb_attention_fewkeys_supported(int64_t heads, int64_t d, int64_t Lk, int64_t ldq, int64_t ldk, int64_t ldv);
+int sdb_attention_fewkeys(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv, void* out,
+                          int64_t B, int64_t Lq, int64_t Lk, int heads, int d, float scale, void* stream);
+
 
 /* ------------------------------------------------------------------ small-channel convolutions
  * input conv (unet.py:408): x NCHW [B,Cin,H,W] (Cin small, e.g. 3) -> NHWC fp32 [B,H,W,Cout], 3x3 pad 1 */

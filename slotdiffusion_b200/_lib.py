@@ -88,6 +88,9 @@ SIGNATURES = {
     'sdb_attention_tc_supported': (c_int, [c_int64, c_int64, c_int64, c_int64, c_int64]),
     'sdb_attention_tc': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,
                                  c_int64, c_int64, c_int, c_int, c_float, c_void_p]),
+    'sdb_attention_fewkeys_supported': (c_int, [c_int64, c_int64, c_int64, c_int64, c_int64, c_int64]),
+    'sdb_attention_fewkeys': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,
+                                 c_int64, c_int64, c_int, c_int, c_float, c_void_p]),
     'sdb_conv3_in': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64,
                              c_void_p]),
     'sdb_conv3_out': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,

@@ -12,7 +12,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
-SOURCES = ['api.cu', 'gemm.cu', 'elementwise.cu', 'attention.cu', 'attention_tc.cu', 'slot_attention.cu', 'slot_attention_fused.cu', 'slot_attention_resident.cu', 'slot_update.cu', 'backward.cu', 'boundary.cu', 'predictor.cu']
+SOURCES = ['api.cu', 'gemm.cu', 'elementwise.cu', 'attention.cu', 'attention_tc.cu', 'attention_fewkeys.cu', 'slot_attention.cu', 'slot_attention_fused.cu', 'slot_attention_resident.cu', 'slot_update.cu', 'backward.cu', 'boundary.cu', 'predictor.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '--use_fast_math=false']
 # Build variants live next to the product library under their own names (they travel to the GPU box with it and are

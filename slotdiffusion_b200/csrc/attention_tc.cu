@@ -180,8 +180,13 @@ attention_tc_kernel(const float* __restrict__ q, int64_t ldq, const float* __res
 
   for (int j0 = 0; j0 < Lk; j0 += AT_KC) {
     const int jhi = jlo + min(KS, Lk - j0);          // valid key slots of this row: [jlo, jhi)
+#if SDB_AT_NO_PREFETCH
     if (j0 > 0) load_kv(j0);
     store_kv();
+#else
+    store_kv();
+    if (j0 + AT_KC < Lk) load_kv(j0 + AT_KC);   // next chunk's rows travel while this chunk is multiplied and normalised
+#endif
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();

@@ -515,10 +515,19 @@ def groupnorm_finalize_cb(gsum, C, B, HW, G, eps, cb):
 ATTENTION_TC = True   # tensor-core attention cores (csrc/attention_tc.cu) when the shape is supported
 
 
+ATTENTION_FEWKEYS = os.environ.get('SDB_ATTENTION_FEWKEYS', '1') == '1'
+
+
 def attention_pack(q, k, v, B, Lq, Lk, heads, d, scale, tc=None):
     """q/k/v: 2-D strided views [B*L, heads*d] (last dim contiguous) -> Packed [B*Lq, heads*d]."""
     out = Packed.empty(B * Lq, heads * d, q.device)
     use_tc = ATTENTION_TC if tc is None else tc
+    if tc is None and ATTENTION_FEWKEYS and _FMT == SDB_FMT_F16X2 and lib().sdb_attention_fewkeys_supported(
+            heads, d, Lk, q.stride(0), k.stride(0), v.stride(0)):
+        # slot cross-attention (Lk = num_slots): coalesced fp32 kernel, see csrc/attention_fewkeys.cu
+        check(lib().sdb_attention_fewkeys(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out.t), B, Lq, Lk,
+                                          heads, d, scale, _stream()), 'sdb_attention_fewkeys')
+        return out
     if use_tc and lib().sdb_attention_tc_supported(heads, d, q.stride(0), k.stride(0), v.stride(0)):
         check(lib().sdb_attention_tc(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out.t), B, Lq, Lk,
                                      heads, d, scale, _stream()), 'sdb_attention_tc')

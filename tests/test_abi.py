@@ -72,7 +72,7 @@ def test_every_entry_point_rejects_null_and_zero_arguments():
     pointers and zero sizes returns SDB_ERR_INVALID with a message (no CUDA call is reached, runs without a GPU)."""
     from slotdiffusion_b200 import _lib
     l = _lib.lib()
-    queries = {'sdb_version', 'sdb_last_error', 'sdb_launch_count', 'sdb_attention_tc_supported',
+    queries = {'sdb_version', 'sdb_last_error', 'sdb_launch_count', 'sdb_attention_tc_supported', 'sdb_attention_fewkeys_supported',
                'sdb_slot_attend_workspace', 'sdb_slot_attend_fused_supported', 'sdb_slot_attend_fused_debug',
                'sdb_slot_attend_fused_workspace', 'sdb_slot_attend_fused_chunks', 'sdb_slot_attend_fused_ascale',
                'sdb_slot_update_supported', 'sdb_token_attention_supported', 'sdb_slot_attention_resident_supported', 'sdb_slot_attention_resident_debug', 'sdb_slot_attention_resident_wave',

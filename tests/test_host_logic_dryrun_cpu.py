@@ -13,7 +13,7 @@ import torch
 from oracle import dpm_ref, unet_ref
 from oracle import slot_attention_ref as sa_ref
 
-QUERIES = {'sdb_version', 'sdb_last_error', 'sdb_launch_count', 'sdb_attention_tc_supported', 'sdb_slot_attend_workspace',
+QUERIES = {'sdb_version', 'sdb_last_error', 'sdb_launch_count', 'sdb_attention_tc_supported', 'sdb_attention_fewkeys_supported', 'sdb_slot_attend_workspace',
            'sdb_slot_attend_fused_supported', 'sdb_slot_attend_fused_workspace', 'sdb_slot_attend_fused_chunks',
            'sdb_slot_attend_fused_ascale', 'sdb_slot_update_supported', 'sdb_token_attention_supported'}
 

@@ -276,6 +276,30 @@ def test_attention(ops, Lq, Lk, heads, tc):
     assert rel_l2(out, ref) < 3e-6
 
 
+@pytest.mark.parametrize('Lq,Lk,heads,scale', [(256, 11, 8, 1.0), (64, 11, 12, 1.0), (16, 11, 16, 1.0), (256, 24, 8, 1.0),
+                                                (3136, 7, 4, 1.0), (100, 32, 1, 1.0), (45, 1, 16, 1.0), (256, 11, 8, 6.0)])
+def test_attention_fewkeys(ops, Lq, Lk, heads, scale):
+    """slot cross-attention (Lk = num_slots keys; csrc/attention_fewkeys.cu, the default route of attention_pack for Lk <= 32):
+    vs fp64 torch math, ragged row tiles, q as a column slice of a wider buffer, peaked logits; the other two kernels agree"""
+    B, d = 3, 32
+    C = heads * d
+    qkv = rnd(B * Lq, 3 * C, seed=26, scale=scale)
+    kv = rnd(B * Lk, 2 * C, seed=27, scale=scale)
+    q = qkv[:, C:2 * C]
+    k, v = kv[:, :C], kv[:, C:]
+    from slotdiffusion_b200._lib import lib
+    assert lib().sdb_attention_fewkeys_supported(heads, d, Lk, q.stride(0), k.stride(0), v.stride(0))
+    out = ops.attention_pack(q, k, v, B, Lq, Lk, heads, d, d ** -0.5).unpack()
+    qd = q.double().view(B, Lq, heads, d).transpose(1, 2)
+    kd = k.double().view(B, Lk, heads, d).transpose(1, 2)
+    vd = v.double().view(B, Lk, heads, d).transpose(1, 2)
+    ref = (torch.softmax(qd @ kd.transpose(-1, -2) * d ** -0.5, -1) @ vd).transpose(1, 2).reshape(B * Lq, C)
+    assert rel_l2(out, ref) < 2e-6
+    assert rel_l2(out, ops.attention_pack(q, k, v, B, Lq, Lk, heads, d, d ** -0.5, tc=True).unpack()) < 3e-6
+    assert not lib().sdb_attention_fewkeys_supported(heads, d, 33, q.stride(0), k.stride(0), v.stride(0))
+    assert not lib().sdb_attention_fewkeys_supported(heads, 64, Lk, q.stride(0), k.stride(0), v.stride(0))
+
+
 def test_attention_tc_peaked(ops):
     """large logits (peaked softmax) and a self-attention view of a fused q|k|v projection"""
     B, L, heads, d = 3, 256, 8, 32
