@@ -1,5 +1,6 @@
 // Error plumbing, device queries and bookkeeping shared by every entry point of libsdb200.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -25,6 +26,15 @@ int check_cuda(cudaError_t e, const char* what) {
   }
   set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
   return SDB_ERR_CUDA;
+}
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* v = getenv("SDB_PDL");
+    on = (v && *v == '0') ? 0 : 1;
+  }
+  return on != 0;
 }
 
 static int g_host_pack_mode = SDB_FMT_F16X2;

@@ -46,6 +46,8 @@ attention_fewkeys_kernel(const float* __restrict__ q, int64_t ldq, const float* 
   const int64_t b = blockIdx.y;
   const int r0 = blockIdx.x * FK_ROWS;
   const int rows = min(FK_ROWS, Lq - r0);
+  pdl_wait();        // PDL (common.cuh)
+  pdl_trigger();
 
   // all tile loads are asynchronous copies in flight together (a register-staged loop exposed one DRAM round trip per
   // trip: 11 per CTA, 80 us per launch instead of the ~25 us the bytes take)
@@ -173,11 +175,11 @@ extern "C" int sdb_attention_fewkeys(const float* q, int64_t ldq, const float* k
   }
   dim3 grid((unsigned)cdiv(Lq, FK_ROWS), (unsigned)B);
   if (Lk <= 16)
-    attention_fewkeys_kernel<16><<<grid, 32 * heads, smem, as_stream(stream)>>>(q, ldq, k, ldk, v, ldv, (__half*)out, (int)Lq,
-                                                                              (int)Lk, heads, scale, B * Lq * (int64_t)C);
+    (void)launch_k(attention_fewkeys_kernel<16>, grid, dim3(32 * heads), smem, as_stream(stream), q, ldq, k, ldk, v, ldv,
+                   (__half*)out, (int)Lq, (int)Lk, heads, scale, B * Lq * (int64_t)C);
   else
-    attention_fewkeys_kernel<32><<<grid, 32 * heads, smem, as_stream(stream)>>>(q, ldq, k, ldk, v, ldv, (__half*)out, (int)Lq,
-                                                                              (int)Lk, heads, scale, B * Lq * (int64_t)C);
+    (void)launch_k(attention_fewkeys_kernel<32>, grid, dim3(32 * heads), smem, as_stream(stream), q, ldq, k, ldk, v, ldv,
+                   (__half*)out, (int)Lq, (int)Lk, heads, scale, B * Lq * (int64_t)C);
   SDB_LAUNCH_CHECK();
   return 0;
 }

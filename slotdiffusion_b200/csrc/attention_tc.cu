@@ -73,7 +73,6 @@ __global__ void __launch_bounds__(AT_THREADS, 3)
 attention_tc_kernel(const float* __restrict__ q, int64_t ldq, const float* __restrict__ k, int64_t ldk,
                     const float* __restrict__ v, int64_t ldv, __half* __restrict__ out, int Lq, int Lk, int heads,
                     float scale, int64_t plane, int npairs) {
-  const int pmode = g_pack_mode;   // operand format of the consumer GEMM: read once (common.cuh)
   extern __shared__ uint8_t smem_raw[];
   AtSmem& sm = *reinterpret_cast<AtSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -94,6 +93,9 @@ attention_tc_kernel(const float* __restrict__ q, int64_t ldq, const float* __res
     tmem_alloc(&sm.tmem_base, AT_TMEM_COLS);
     tmem_relinquish();
   }
+  pdl_wait();        // PDL (common.cuh): barrier init and TMEM allocation above may overlap the previous kernel's tail
+  pdl_trigger();
+  const int pmode = g_pack_mode;   // operand format of the consumer GEMM: read once (common.cuh)
   // ---- loads of the Q tile and of the first K / V chunk are issued together (one exposed global latency)
   // K / V chunk staging: thread <-> 2 x (key, 8-channel quarter)
   float4 kreg[2][2], vreg[2][2];
@@ -355,14 +357,14 @@ extern "C" int sdb_attention_tc(const float* q, int64_t ldq, const float* k, int
   cudaStream_t st = as_stream(stream);
   __half* o = (__half*)out;
   if (Lq <= 32 && Lk <= 16)
-    attention_tc_kernel<4><<<(unsigned)cdiv(npairs, 4), AT_THREADS, smem, st>>>(q, ldq, k, ldk, v, ldv, o, (int)Lq,
-                                                                               (int)Lk, heads, scale, plane, npairs);
+    (void)launch_k(attention_tc_kernel<4>, dim3((unsigned)cdiv(npairs, 4)), dim3(AT_THREADS), smem, st, q, ldq, k, ldk, v, ldv,
+                   o, (int)Lq, (int)Lk, heads, scale, plane, npairs);
   else if (Lq <= 64 && Lk <= 32)
-    attention_tc_kernel<2><<<(unsigned)cdiv(npairs, 2), AT_THREADS, smem, st>>>(q, ldq, k, ldk, v, ldv, o, (int)Lq,
-                                                                               (int)Lk, heads, scale, plane, npairs);
+    (void)launch_k(attention_tc_kernel<2>, dim3((unsigned)cdiv(npairs, 2)), dim3(AT_THREADS), smem, st, q, ldq, k, ldk, v, ldv,
+                   o, (int)Lq, (int)Lk, heads, scale, plane, npairs);
   else
-    attention_tc_kernel<1><<<dim3((unsigned)cdiv(Lq, AT_M), (unsigned)heads, (unsigned)B), AT_THREADS, smem, st>>>(
-        q, ldq, k, ldk, v, ldv, o, (int)Lq, (int)Lk, heads, scale, plane, npairs);
+    (void)launch_k(attention_tc_kernel<1>, dim3((unsigned)cdiv(Lq, AT_M), (unsigned)heads, (unsigned)B), dim3(AT_THREADS), smem,
+                   st, q, ldq, k, ldk, v, ldv, o, (int)Lq, (int)Lk, heads, scale, plane, npairs);
   SDB_LAUNCH_CHECK();
   return 0;
 }

@@ -128,12 +128,41 @@ __device__ __forceinline__ void store_split4_w(__half* hi, __half* lo, long long
 // launchers pick the kernel INSTANCE for the current format (template <int PM>) instead of branching on the device flag --
 // the default-format instances then carry none of the FP8C code (registers / instructions of instruction-bound producers).
 // Kernels that are templates already (attention cores) read the device flag once per thread.
+// ---- programmatic dependent launch (PDL) --------------------------------------------------------------------------------
+// The kernels of an evaluation run back to back on one stream (430 launches per UNet evaluation, replayed from a CUDA graph);
+// between two of them the GPU drains, resolves the dependency and ramps the next grid up -- a few microseconds each.  Kernels
+// launched through launch_k() carry cudaLaunchAttributeProgrammaticStreamSerialization: their CTAs may become resident while
+// the previous kernel is still finishing (its last wave), run their prologue (barrier init, TMEM allocation, descriptor
+// prefetch, index arithmetic) and then block in pdl_wait() until the previous grid has COMPLETED and its writes are visible.
+// Rules: (1) every kernel launched this way calls pdl_wait() in every CTA before its first global access and before any
+// exit -- completion of a grid that skipped the wait would release its own dependents early; (2) pdl_trigger() right after
+// it lets the next grid start its prologue; (3) launches without the attribute (cudaMemsetAsync, torch kernels, everything not
+// converted) keep full stream-order semantics, so mixing is safe.  SDB_PDL=0 switches the attribute off.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+
+template <typename... P, typename... A>
+inline cudaError_t launch_k(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
+}
+
 int host_pack_mode();
 void set_host_pack_mode(int m);
-#define SDB_LAUNCH_PM(kernel, grid, block, smem, st, ...)                                                  \
-  do {                                                                                                     \
-    if (host_pack_mode() == SDB_FMT_F8C) kernel<SDB_FMT_F8C><<<grid, block, smem, st>>>(__VA_ARGS__);      \
-    else kernel<SDB_FMT_F16X2><<<grid, block, smem, st>>>(__VA_ARGS__);                                    \
+#define SDB_LAUNCH_PM(kernel, grid, block, smem, st, ...)                                                            \
+  do {                                                                                                               \
+    if (host_pack_mode() == SDB_FMT_F8C) (void)launch_k(kernel<SDB_FMT_F8C>, dim3 grid, dim3 block, smem, st, __VA_ARGS__); \
+    else (void)launch_k(kernel<SDB_FMT_F16X2>, dim3 grid, dim3 block, smem, st, __VA_ARGS__);                        \
   } while (0)
 int set_pack_mode_elementwise(int m, cudaStream_t st);
 int set_pack_mode_gemm(int m, cudaStream_t st);

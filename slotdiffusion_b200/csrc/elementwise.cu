@@ -57,6 +57,8 @@ template <int PM>
 __global__ void pack_rows_kernel(const float* __restrict__ x, int64_t ldx, __half* __restrict__ out, int64_t M,
                                  int64_t K, int act) {
   constexpr int pmode = PM;        // operand format of the consumer GEMM, chosen by the launcher (common.cuh)
+  pdl_wait();       // launched with the PDL attribute (common.cuh): nothing global before this line
+  pdl_trigger();
   const int64_t k4 = K / 4;
   const int64_t total = M * k4;
   const int64_t plane = M * K;
@@ -78,6 +80,8 @@ __global__ void __launch_bounds__(256, 4) layernorm_pack_kernel(const float* __r
                                       const float* __restrict__ beta, float eps, __half* __restrict__ out,
                                       float* __restrict__ y, int64_t M, int C) {
   constexpr int pmode = PM;        // operand format of the consumer GEMM, chosen by the launcher (common.cuh)
+  pdl_wait();       // launched with the PDL attribute (common.cuh): nothing global before this line
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const int64_t plane = M * (int64_t)C;
@@ -179,6 +183,8 @@ __global__ void groupnorm_apply_pack_kernel(const float* __restrict__ x1, int C1
                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                             __half* __restrict__ out, int64_t B, int64_t HW, int G, int silu) {
   constexpr int pmode = PM;        // operand format of the consumer GEMM, chosen by the launcher (common.cuh)
+  pdl_wait();       // launched with the PDL attribute (common.cuh): nothing global before this line
+  pdl_trigger();
   const int C = C1 + C2;
   const int c4n = C / 4;
   const int cpg = C / G;
@@ -218,6 +224,8 @@ __global__ void groupnorm_add_relu_kernel(const float* __restrict__ h, const flo
                                           float* __restrict__ out, __half* __restrict__ out_packed, int64_t B, int64_t HW,
                                           int C, int G) {
   constexpr int pmode = PM;        // operand format of the consumer GEMM, chosen by the launcher (common.cuh)
+  pdl_wait();       // launched with the PDL attribute (common.cuh): nothing global before this line
+  pdl_trigger();
   const int c4n = C / 4, cpg = C / G;
   const int64_t total = B * HW * c4n;
   const int64_t plane = B * HW * (int64_t)C;
@@ -271,6 +279,8 @@ groupnorm_apply_pack_fused_kernel(const float* __restrict__ x1, int C1, const fl
                                   float eps, int silu, int rows_per_chunk, float drop_p, unsigned long long seed,
                                   const unsigned long long* __restrict__ seed_dev) {
   constexpr int pmode = PM;        // operand format of the consumer GEMM, chosen by the launcher (common.cuh)
+  pdl_wait();       // launched with the PDL attribute (common.cuh): nothing global before this line
+  pdl_trigger();
   if (seed_dev) seed += *seed_dev * 0x9E3779B97F4A7C15ull;   // per-step counter living in device memory (graph replays)
   __shared__ float s_mean[64], s_rstd[64];
   const int C = C1 + C2, c4n = C >> 2, cpg = C / G;
@@ -414,6 +424,8 @@ __global__ void groupnorm_finalize_cb_kernel(const float* __restrict__ gsum, int
 template <int PM>
 __global__ void pack_weight_geglu_kernel(const float* __restrict__ w, __half* __restrict__ out, int64_t F, int64_t K) {
   constexpr int pmode = PM;        // operand format of the consumer GEMM, chosen by the launcher (common.cuh)
+  pdl_wait();       // launched with the PDL attribute (common.cuh): nothing global before this line
+  pdl_trigger();
   const int64_t k4 = K / 4, total = 2 * F * k4, plane = 2 * F * K;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / k4, j = i % k4;
@@ -436,6 +448,8 @@ __global__ void __launch_bounds__(256) pack_nhwc_kernel(const float* __restrict_
                                  __half* __restrict__ out, float* __restrict__ ycat, int64_t B, int H, int W,
                                  int mode) {
   constexpr int pmode = PM;        // operand format of the consumer GEMM, chosen by the launcher (common.cuh)
+  pdl_wait();       // launched with the PDL attribute (common.cuh): nothing global before this line
+  pdl_trigger();
   const int C = C1 + C2;
   const int c4n = C / 4;
   const int Ho = (mode == SDB_PACK_UP2) ? 2 * H : H;
@@ -497,6 +511,8 @@ __global__ void __launch_bounds__(256) pack_nhwc_kernel(const float* __restrict_
 template <int PM>
 __global__ void geglu_pack_kernel(const float* __restrict__ u, __half* __restrict__ out, int64_t M, int64_t F) {
   constexpr int pmode = PM;        // operand format of the consumer GEMM, chosen by the launcher (common.cuh)
+  pdl_wait();       // launched with the PDL attribute (common.cuh): nothing global before this line
+  pdl_trigger();
   const int64_t f4 = F / 4;
   const int64_t total = M * f4;
   const int64_t plane = M * F;
@@ -518,6 +534,8 @@ template <int PM>
 __global__ void timestep_embedding_pack_kernel(const float* __restrict__ t, __half* __restrict__ out, int64_t B,
                                                int dim) {
   constexpr int pmode = PM;        // operand format of the consumer GEMM, chosen by the launcher (common.cuh)
+  pdl_wait();       // launched with the PDL attribute (common.cuh): nothing global before this line
+  pdl_trigger();
   const int half = dim / 2;
   const int64_t total = B * dim;
   // four consecutive columns per thread (dim % 8 == 0: a group never straddles the cos | sin halves), written in the
@@ -545,6 +563,8 @@ template <int PM>
 __global__ void softmax_pack_kernel(const float* __restrict__ x, int64_t ldx, float scale, float out_scale,
                                     __half* __restrict__ out, int64_t M, int N) {
   constexpr int pmode = PM;        // operand format of the consumer GEMM, chosen by the launcher (common.cuh)
+  pdl_wait();       // launched with the PDL attribute (common.cuh): nothing global before this line
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -1146,7 +1166,7 @@ extern "C" int sdb_groupnorm_apply_pack_fused(const float* x1, int64_t C1, const
     const bool f8 = host_pack_mode() == SDB_FMT_F8C;
     const bool drop = g_drop_p > 0.f;
 #define SDB_GN_LAUNCH(PMv, ACTv, DROPv)                                                                                    \
-    groupnorm_apply_pack_fused_kernel<PMv, ACTv, DROPv><<<grid, threads, 0, st>>>(                                          \
+    (void)launch_k(groupnorm_apply_pack_fused_kernel<PMv, ACTv, DROPv>, grid, dim3(threads), 0, st,                         \
         x1, (int)C1, gsum1, x2, (int)C2, gsum2, stats, gamma, beta, (__half*)out, B, (int)HW, G, eps, silu, rows_per_chunk, \
         g_drop_p, g_drop_seed, g_drop_seed_dev)
 #define SDB_GN_ACT(PMv, DROPv)                          \

@@ -119,13 +119,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
             const __grid_constant__ CUtensorMap map_a_l8, const __grid_constant__ CUtensorMap map_b_l8,
             const GemmArgs g) {
   constexpr bool kF8 = (VAR & VAR_F8C) != 0, kExt = (VAR & VAR_EXT) != 0;
-  const int pmode = kF8 ? g_pack_mode : SDB_FMT_F16X2;   // operand format of the consumer GEMM: read once (common.cuh)
   const int acc_two = kF8 ? g.acc_two : 1;
   const int gsum_cb = kExt ? g.gsum_cb : 4;
   const int batch_rows = kExt ? g.batch_rows : 0;
   const int tap_pair = kExt ? g.tap_pair : 0;
   extern __shared__ uint8_t smem_raw[];
-  if (g.debug == 1) return;
+  if (g.debug == 1) { pdl_wait(); return; }
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   GemmCtl& ctl = *reinterpret_cast<GemmCtl*>(ring + (size_t)g.stages * g.stage_bytes);
   const int warp = threadIdx.x >> 5;
@@ -167,6 +166,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ctl.tmem_base;
+  // PDL (common.cuh): everything above -- descriptor prefetch, mbarrier init, TMEM allocation, the cluster barrier -- may
+  // overlap the tail of the previous kernel; nothing below may: operands, bias / residual, the pack-mode flag and C belong to it
+  pdl_wait();
+  pdl_trigger();
+  const int pmode = kF8 ? g_pack_mode : SDB_FMT_F16X2;   // operand format of the consumer GEMM: read once (common.cuh)
 
   if (g.debug == 2) {
     // skip the work
@@ -710,13 +714,15 @@ static int launch_gemm(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = CG;
   at[0].val.clusterDim.y = 1;
   at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // PDL, see common.cuh
+  at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   SDB_CHECK(cudaLaunchKernelEx(&cfg, gemm_kernel<CG, EPI, VAR>, ma_hi, ma_lo, mb_hi, mb_lo, ma_l8, mb_l8, g));
   SDB_LAUNCH_CHECK();
   return 0;
