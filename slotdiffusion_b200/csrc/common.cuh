@@ -211,6 +211,20 @@ __device__ __forceinline__ float warp_max(float v) {
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.f + __expf(-x)); }
 __device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+// erf-GELU for the GEGLU epilogue of the GEMM, where 64 evaluations per thread and tile compete with the tensor pipe for a
+// K = 256 main loop: Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7 ABSOLUTE, which is what 1 + erf needs; the result is then
+// stored as fp16 hi + lo = 22 bits anyway) -- one MUFU.RCP, one MUFU.EX2, 8 FMA-pipe instructions, no branch (erff: two
+// divergent polynomial branches, ~3x the instructions).
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float z = x * 0.70710678118654752440f, az = fabsf(z);
+  const float t = __fdividef(1.f, fmaf(0.3275911f, az, 1.f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float r = fmaf(-p * t, __expf(-az * az), 1.f);      // erf(|z|)
+  return 0.5f * x * (1.f + copysignf(r, z));
+}
 
 // counter-based dropout mask: keep-scale (1/(1-p)) or 0 for element `idx` of the tensor identified by `seed`
 __device__ __forceinline__ float dropout_scale(unsigned long long seed, unsigned long long idx, float p, float inv_keep) {

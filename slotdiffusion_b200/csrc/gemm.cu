@@ -519,10 +519,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
               const float4 a = *reinterpret_cast<const float4*>(stg + rr * 32 + ((cc ^ (rr & 7)) << 2));
               const float4 gg = *reinterpret_cast<const float4*>(stg + rr * 32 + (((cc + 4) ^ (rr & 7)) << 2));
               float4 o;
-              o.x = (a.x + ba.x) * gelu_erf_f(gg.x + bg.x);
-              o.y = (a.y + ba.y) * gelu_erf_f(gg.y + bg.y);
-              o.z = (a.z + ba.z) * gelu_erf_f(gg.z + bg.z);
-              o.w = (a.w + ba.w) * gelu_erf_f(gg.w + bg.w);
+              o.x = (a.x + ba.x) * gelu_erf_fast(gg.x + bg.x);
+              o.y = (a.y + ba.y) * gelu_erf_fast(gg.y + bg.y);
+              o.z = (a.z + ba.z) * gelu_erf_fast(gg.z + bg.z);
+              o.w = (a.w + ba.w) * gelu_erf_fast(gg.w + bg.w);
               store_split4(g.out_packed, g.out_packed + g.out_plane, (long long)(row0 + rr) * F + fo, o, pmode);
             }
           }

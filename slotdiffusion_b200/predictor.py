@@ -222,7 +222,8 @@ class TransformerPredictor(Predictor):
         super().__init__()
         transformer_enc_layer = nn.TransformerEncoderLayer(d_model=d_model, nhead=num_heads, dim_feedforward=ffn_dim,
                                                            norm_first=norm_first, batch_first=True)
-        self.transformer_encoder = nn.TransformerEncoder(encoder_layer=transformer_enc_layer, num_layers=num_layers)
+        self.transformer_encoder = nn.TransformerEncoder(encoder_layer=transformer_enc_layer, num_layers=num_layers,
+                                                         enable_nested_tensor=False)      # (no parameters; silences a warning)
         self._wcache = ops.WeightCache()
 
     def __getstate__(self):
