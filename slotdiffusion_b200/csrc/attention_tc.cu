@@ -52,6 +52,11 @@ __device__ __forceinline__ void split8(const float4& a, const float4& b, uint4& 
   sp(b.x, b.y, hi.z, lo.z);
   sp(b.z, b.w, hi.w, lo.w);
 }
+__device__ __forceinline__ float ex2_fast(float x) {     // bare MUFU.EX2 (2 ulp; flushes results below 2^-126 to 0)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 // 16-byte chunk `c` (0..7) of row `r` of a [rows][128 B] SWIZZLE_128B tile
 __device__ __forceinline__ uint4* sw_chunk(uint8_t* tile, int r, int c) {
   return reinterpret_cast<uint4*>(tile + r * 128 + ((c ^ (r & 7)) << 4));
@@ -150,8 +155,10 @@ attention_tc_kernel(const float* __restrict__ q, int64_t ldq, const float* __res
     for (int it = 0; it < 4; ++it) {
       const int item = tid + AT_THREADS * it, qr = item >> 2, qt = item & 3;
       float4 a = qreg[it][0], c = qreg[it][1];
-      a.x *= scale; a.y *= scale; a.z *= scale; a.w *= scale;
-      c.x *= scale; c.y *= scale; c.z *= scale; c.w *= scale;
+      // logits in units of log2: softmax(s) = 2^(s' - max s') with s' = s log2(e) -- the exponentials below are bare ex2
+      const float sc2 = scale * 1.4426950408889634f;
+      a.x *= sc2; a.y *= sc2; a.z *= sc2; a.w *= sc2;
+      c.x *= sc2; c.y *= sc2; c.z *= sc2; c.w *= sc2;
       uint4 hi, lo;
       split8(a, c, hi, lo);
       *sw_chunk(sm.q, qr, qt) = hi;
@@ -233,7 +240,7 @@ attention_tc_kernel(const float* __restrict__ q, int64_t ldq, const float* __res
         }
       }
       const float mnew = fmaxf(mrun, cmax);
-      const float corr = __expf(mrun - mnew);            // exp(-inf) = 0 on the first chunk
+      const float corr = ex2_fast(mrun - mnew);             // 2^(-inf) = 0 on the first chunk
       mrun = mnew;
       float psum = 0.f;
       auto probs = [&](auto fullc) {
@@ -244,8 +251,8 @@ attention_tc_kernel(const float* __restrict__ q, int64_t ldq, const float* __res
           for (int e = 0; e < 8; ++e) {
             const int j = c * 8 + e;
             const float sv = __uint_as_float(j < 32 ? s0[j] : s1[j - 32]);
-            if constexpr (decltype(fullc)::value) pv[e] = __expf(sv - mnew);
-            else pv[e] = (j >= jlo && j < jhi) ? __expf(sv - mnew) : 0.f;
+            if constexpr (decltype(fullc)::value) pv[e] = ex2_fast(sv - mnew);
+            else pv[e] = (j >= jlo && j < jhi) ? ex2_fast(sv - mnew) : 0.f;
           }
           psum += ((pv[0] + pv[1]) + (pv[2] + pv[3])) + ((pv[4] + pv[5]) + (pv[6] + pv[7]));
           uint4 hi, lo;
