@@ -627,30 +627,91 @@ __global__ void conv3_in_kernel(const float* __restrict__ x, const float* __rest
     sw[i] = w[o * Cin * 9 + r];
   }
   __syncthreads();
+  // A thread keeps its 4 output channels and walks over pixels (blockDim is a multiple of Cout / 4: sdb_conv3_in): the only
+  // divisions left are the two 32-bit ones of the pixel decomposition (the i / o4n form of this loop ran a 64-bit division per
+  // element -- most of the kernel's 134 M warp instructions, ncu: profiles/README.md section 23).  The bias and the 27
+  // weight float4 of the thread's channels are loop invariants read through shared memory.
   const int o4n = Cout / 4;
-  const int64_t total = B * H * W * o4n;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    // pixel / channel decomposition in 32-bit arithmetic (B*H*W < 2^31 is checked by the launcher)
-    const unsigned pq = (unsigned)(i / o4n);
-    const int o = int(i - (int64_t)pq * o4n) * 4;
+  const int o = int(threadIdx.x % o4n) * 4;
+  const unsigned ppb = blockDim.x / o4n;                      // pixels per CTA and trip
+  const unsigned npix = (unsigned)(B * H * W);
+  const float4 bias4 = *reinterpret_cast<const float4*>(bias + o);
+  for (unsigned pq = blockIdx.x * ppb + threadIdx.x / o4n; pq < npix; pq += gridDim.x * ppb) {
     const unsigned pr = pq / (unsigned)W;
     const int xo = int(pq - pr * (unsigned)W);
     const unsigned bb = pr / (unsigned)H;
     const int yo = int(pr - bb * (unsigned)H);
     const int64_t b = bb;
-    float4 acc = *reinterpret_cast<const float4*>(bias + o);
+    float4 acc = bias4;
     for (int c = 0; c < Cin; ++c) {
       const float* xc = x + (b * Cin + c) * (int64_t)H * W;
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap) {
+        // unconditional load from a clamped address, then select: the nine loads of a channel issue back to back (behind a
+        // per-tap branch they were serialised: long-scoreboard stall 8.4 per issue, ncu)
         const int yi = yo + tap / 3 - 1, xi = xo + tap % 3 - 1;
-        if (yi < 0 || yi >= H || xi < 0 || xi >= W) continue;
-        const float v = xc[yi * W + xi];
+        const bool inb = yi >= 0 && yi < H && xi >= 0 && xi < W;
+        const float ld = xc[min(max(yi, 0), H - 1) * W + min(max(xi, 0), W - 1)];
+        const float v = inb ? ld : 0.f;
         const float4 ww = *reinterpret_cast<const float4*>(sw + (c * 9 + tap) * Cout + o);
         acc.x += v * ww.x; acc.y += v * ww.y; acc.z += v * ww.z; acc.w += v * ww.w;
       }
     }
-    *reinterpret_cast<float4*>(y + ((b * H + yo) * W + xo) * Cout + o) = acc;
+    *reinterpret_cast<float4*>(y + (int64_t)pq * Cout + o) = acc;
+  }
+}
+
+// Same conv, four adjacent output pixels per thread (W % 4 == 0): the 3 x 6 input window of a channel is loaded once
+// (clamped addresses, zero select) and every weight float4 is reused by the four pixels -- 160 instead of 510 warp
+// instructions per pixel; the one-pixel form above was issue-bound (134 M warp instructions for 33.5 M outputs, ncu).
+__global__ void __launch_bounds__(256)
+conv3_in_px4_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                    float* __restrict__ y, int64_t B, int Cin, int H, int W, int Cout) {
+  extern __shared__ float sw[];   // [Cin*9][Cout]
+  for (int i = threadIdx.x; i < Cin * 9 * Cout; i += blockDim.x) {
+    const int o = i % Cout, r = i / Cout;    // r = c*9 + tap
+    sw[i] = w[o * Cin * 9 + r];
+  }
+  __syncthreads();
+  const int o4n = Cout / 4;
+  const int o = int(threadIdx.x % o4n) * 4;
+  const unsigned qpb = blockDim.x / o4n;                      // pixel quads per CTA and trip
+  const unsigned wq = (unsigned)W / 4, nquads = (unsigned)(B * H) * wq;
+  const float4 bias4 = *reinterpret_cast<const float4*>(bias + o);
+  for (unsigned qd = blockIdx.x * qpb + threadIdx.x / o4n; qd < nquads; qd += gridDim.x * qpb) {
+    const unsigned pr = qd / wq;                              // b * H + yo
+    const int x0 = int(qd - pr * wq) * 4;
+    const unsigned bb = pr / (unsigned)H;
+    const int yo = int(pr - bb * (unsigned)H);
+    float4 acc[4] = {bias4, bias4, bias4, bias4};
+    for (int c = 0; c < Cin; ++c) {
+      const float* xc = x + ((int64_t)bb * Cin + c) * (int64_t)H * W;
+      float win[3][6];
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int yi = yo + ky - 1;
+        const bool yin = yi >= 0 && yi < H;
+        const float* row = xc + min(max(yi, 0), H - 1) * W;
+#pragma unroll
+        for (int kx = 0; kx < 6; ++kx) {
+          const int xi = x0 + kx - 1;
+          const float ld = row[min(max(xi, 0), W - 1)];
+          win[ky][kx] = (yin && xi >= 0 && xi < W) ? ld : 0.f;
+        }
+      }
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const float4 ww = *reinterpret_cast<const float4*>(sw + (c * 9 + tap) * Cout + o);
+#pragma unroll
+        for (int px = 0; px < 4; ++px) {
+          const float v = win[tap / 3][px + tap % 3];
+          acc[px].x += v * ww.x; acc[px].y += v * ww.y; acc[px].z += v * ww.z; acc[px].w += v * ww.w;
+        }
+      }
+    }
+    float* dst = y + ((int64_t)pr * W + x0) * Cout + o;
+#pragma unroll
+    for (int px = 0; px < 4; ++px) *reinterpret_cast<float4*>(dst + (int64_t)px * Cout) = acc[px];
   }
 }
 
@@ -713,29 +774,55 @@ conv3_out_tile_kernel(const float* __restrict__ h, const float* __restrict__ sta
   float* sa = smem_f + Cout * 9 * C;          // [R + 2][W + 2][C]
   const int64_t b = blockIdx.y;
   const int y0 = blockIdx.x * R;
-  const int Wp = W + 2, c4n = C / 4, cpg = C / G;
-  for (int i = threadIdx.x; i < Cout * 9 * C; i += blockDim.x) {
-    const int c = i % C, tap = (i / C) % 9, o = i / (9 * C);
-    sw[i] = w[(o * C + c) * 9 + tap];
+  const int Wp = W + 2, cpg = C / G;
+  // Stage 1: raw tile and weights as asynchronous copies, all in flight together
+  auto cp4 = [](void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+  };
+  auto cp16 = [](void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+  };
+  // Index arithmetic: a warp owns (output channel, tap) rows of the weights and pixels of the tile, lanes run over the
+  // channels -- no per-element division (the i % c4n, (i / c4n) % Wp, i / (c4n Wp) form of these loops was 60 % of the
+  // kernel's 279 M warp instructions: ncu, profiles/README.md section 23).
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int ot = warp; ot < Cout * 9; ot += nwarps) {
+    const int o = ot / 9, tap = ot - o * 9;
+    for (int c = lane; c < C; c += 32) cp4(sw + ot * C + c, w + (o * C + c) * 9 + tap);
   }
-  for (int i = threadIdx.x; i < (R + 2) * Wp * c4n; i += blockDim.x) {
-    const int c = (i % c4n) * 4, xp = (i / c4n) % Wp, rr = i / (c4n * Wp);
+  const int npix = (R + 2) * Wp;
+  for (int pix = warp; pix < npix; pix += nwarps) {
+    const int rr = pix / Wp, xp = pix - rr * Wp;
     const int yi = y0 - 1 + rr, xi = xp - 1;
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (yi >= 0 && yi < H && xi >= 0 && xi < W) {
-      const float4 v = *reinterpret_cast<const float4*>(h + ((b * H + yi) * W + xi) * C + c);
-      const float4 ga = *reinterpret_cast<const float4*>(gamma + c), be = *reinterpret_cast<const float4*>(beta + c);
-      const int g = c / cpg;                  // C / G is a multiple of 4: the four channels share a group
-      const float mean = stats[(b * G + g) * 2], rstd = stats[(b * G + g) * 2 + 1];
-      a.x = silu_f((v.x - mean) * rstd * ga.x + be.x);
-      a.y = silu_f((v.y - mean) * rstd * ga.y + be.y);
-      a.z = silu_f((v.z - mean) * rstd * ga.z + be.z);
-      a.w = silu_f((v.w - mean) * rstd * ga.w + be.w);
+    const bool inb = yi >= 0 && yi < H && xi >= 0 && xi < W;
+    float* dst = sa + pix * C;
+    const float* src = h + ((b * H + yi) * W + xi) * C;
+    for (int c = lane * 4; c < C; c += 128) {
+      if (inb) cp16(dst + c, src + c);
+      else *reinterpret_cast<float4*>(dst + c) = make_float4(0.f, 0.f, 0.f, 0.f);      // zero border = the conv padding
     }
-    *reinterpret_cast<float4*>(sa + (rr * Wp + xp) * C + c) = a;
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
+  // Stage 2: SiLU(GN(.)) in place, once per input pixel; a lane keeps its channels, so scale / shift are loop invariants
+  for (int c = lane * 4; c < C; c += 128) {
+    const float4 ga = *reinterpret_cast<const float4*>(gamma + c), be = *reinterpret_cast<const float4*>(beta + c);
+    const int g = c / cpg;                  // C / G is a multiple of 4: the four channels share a group
+    const float mean = stats[(b * G + g) * 2], rstd = stats[(b * G + g) * 2 + 1];
+    const float4 sc = make_float4(rstd * ga.x, rstd * ga.y, rstd * ga.z, rstd * ga.w);
+    const float4 sh = make_float4(be.x - mean * sc.x, be.y - mean * sc.y, be.z - mean * sc.z, be.w - mean * sc.w);
+    for (int pix = warp; pix < npix; pix += nwarps) {
+      const int rr = pix / Wp, xp = pix - rr * Wp;
+      const int yi = y0 - 1 + rr, xi = xp - 1;
+      if (yi >= 0 && yi < H && xi >= 0 && xi < W) {
+        float4* pa = reinterpret_cast<float4*>(sa + pix * C + c);
+        const float4 v = *pa;
+        *pa = make_float4(silu_f(fmaf(v.x, sc.x, sh.x)), silu_f(fmaf(v.y, sc.y, sh.y)), silu_f(fmaf(v.z, sc.z, sh.z)),
+                          silu_f(fmaf(v.w, sc.w, sh.w)));
+      }
+    }
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int rows = min(R, H - y0);
   const int quads = rows * (W / 4);
   for (int qd = warp; qd < quads; qd += nwarps) {
@@ -824,6 +911,7 @@ __global__ void dpm_x0_kernel(const float* __restrict__ x, const float* __restri
 // minimum.  Same expanded distance |z|^2 + |e|^2 - 2 z.e as the reference, with the contraction order pinned by fmaf.
 constexpr int VQ_PX = 4;
 constexpr int VQ_THREADS = 128;
+constexpr int VQ_G = 8;          // codes per comparison group
 __global__ void __launch_bounds__(VQ_THREADS)
 dpm_x0_vq3_kernel(const float* __restrict__ x, const float* __restrict__ eps, float alpha, float sigma,
                   const float* __restrict__ codebook, int ncodes, float* __restrict__ x0, int* __restrict__ idx,
@@ -861,13 +949,42 @@ dpm_x0_vq3_kernel(const float* __restrict__ x, const float* __restrict__ eps, fl
     best[i] = INFINITY;
     bi[i] = 0;
   }
-#pragma unroll 4
-  for (int j = 0; j < ncodes; ++j) {
+  // Codes in groups of VQ_G: per pixel only the group minimum is compared with the running best (strict '<', groups in
+  // increasing order: the FIRST group that holds the global minimum wins); the winning group is rescored afterwards to
+  // find its first code at that distance -- the same expression, so bit-identical.  3 instead of 3 * VQ_G compare / select
+  // instructions per group and pixel (the per-code form spent 48 % of its issue slots on them: ncu, profiles/README 23).
+  auto dist = [&](const float4& e, int i) {
+    const float dot = fmaf(z2[i], e.z, fmaf(z1[i], e.y, z0[i] * e.x));
+    return fmaf(-2.f, dot, zz[i] + e.w);
+  };
+  const int ngroups = ncodes / VQ_G;
+  for (int g = 0; g < ngroups; ++g) {
+    float m[VQ_PX];
+#pragma unroll
+    for (int i = 0; i < VQ_PX; ++i) m[i] = INFINITY;
+#pragma unroll
+    for (int jj = 0; jj < VQ_G; ++jj) {
+      const float4 e = scb4[g * VQ_G + jj];
+#pragma unroll
+      for (int i = 0; i < VQ_PX; ++i) m[i] = fminf(m[i], dist(e, i));
+    }
+#pragma unroll
+    for (int i = 0; i < VQ_PX; ++i)
+      if (m[i] < best[i]) { best[i] = m[i]; bi[i] = g; }
+  }
+#pragma unroll
+  for (int i = 0; i < VQ_PX; ++i) {                 // first code of the winning group at the best distance
+    const int g = bi[i];
+    int first = g * VQ_G;
+    for (int jj = VQ_G - 1; jj >= 0; --jj)
+      if (dist(scb4[g * VQ_G + jj], i) == best[i]) first = g * VQ_G + jj;
+    bi[i] = ngroups > 0 ? first : 0;
+  }
+  for (int j = ngroups * VQ_G; j < ncodes; ++j) {   // codebook sizes that are not a multiple of VQ_G
     const float4 e = scb4[j];
 #pragma unroll
     for (int i = 0; i < VQ_PX; ++i) {
-      const float dot = fmaf(z2[i], e.z, fmaf(z1[i], e.y, z0[i] * e.x));
-      const float d = fmaf(-2.f, dot, zz[i] + e.w);
+      const float d = dist(e, i);
       if (d < best[i]) { best[i] = d; bi[i] = j; }
     }
   }
@@ -1060,8 +1177,17 @@ extern "C" int sdb_conv3_in(const float* x, const float* w, const float* bias, f
     SDB_CHECK(cudaFuncSetAttribute(conv3_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
-  conv3_in_kernel<<<grid_for(B * H * W * Cout / 4, 256, 4), 256, smem, as_stream(stream)>>>(x, w, bias, y, B, (int)Cin,
+  const int o4n = (int)(Cout / 4);
+  SDB_REQUIRE(o4n <= 256, "sdb_conv3_in: Cout=%lld too large", (long long)Cout);
+  const int threads = (256 / o4n) * o4n;          // a thread keeps its 4 output channels: blockDim is a multiple of Cout / 4
+  if (W % 4 == 0) {
+    if (smem > 48 * 1024) SDB_CHECK(cudaFuncSetAttribute(conv3_in_px4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv3_in_px4_kernel<<<grid_for(B * H * (W / 4) * o4n, threads, 4), threads, smem, as_stream(stream)>>>(
+        x, w, bias, y, B, (int)Cin, (int)H, (int)W, (int)Cout);
+  } else {
+    conv3_in_kernel<<<grid_for(B * H * W * o4n, threads, 4), threads, smem, as_stream(stream)>>>(x, w, bias, y, B, (int)Cin,
                                                                                           (int)H, (int)W, (int)Cout);
+  }
   SDB_LAUNCH_CHECK();
   return 0;
 }
