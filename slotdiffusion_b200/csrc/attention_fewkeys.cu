@@ -32,8 +32,10 @@ __device__ __forceinline__ int fk_chunk(int r, int c, int chunks_per_row, int ma
   return r * chunks_per_row + (c ^ (r & mask));
 }
 
-template <int MAXK>
-__global__ void __launch_bounds__(512)
+// MAXT: block-size class (256: up to 8 heads, three CTAs resident -- the kernel is issue / latency bound, 24 % active warps
+// with two: 66 -> 55 us; 384: up to 12 heads, two CTAs; 512: up to 16 heads)
+template <int MAXK, int MAXT>
+__global__ void __launch_bounds__(MAXT, MAXT == 256 ? 3 : (MAXT == 384 ? 2 : 1))
 attention_fewkeys_kernel(const float* __restrict__ q, int64_t ldq, const float* __restrict__ k, int64_t ldk,
                          const float* __restrict__ v, int64_t ldv, __half* __restrict__ out, int Lq, int Lk, int heads,
                          float scale, int64_t plane) {
@@ -169,17 +171,24 @@ extern "C" int sdb_attention_fewkeys(const float* q, int64_t ldq, const float* k
   const size_t smem = (size_t)(FK_ROWS + 2 * Lk) * C * sizeof(float);
   static size_t attr = 0;
   if (smem > attr) {
-    SDB_CHECK(cudaFuncSetAttribute(attention_fewkeys_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SDB_CHECK(cudaFuncSetAttribute(attention_fewkeys_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SDB_CHECK(cudaFuncSetAttribute(attention_fewkeys_kernel<16, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SDB_CHECK(cudaFuncSetAttribute(attention_fewkeys_kernel<32, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SDB_CHECK(cudaFuncSetAttribute(attention_fewkeys_kernel<16, 384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SDB_CHECK(cudaFuncSetAttribute(attention_fewkeys_kernel<32, 384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SDB_CHECK(cudaFuncSetAttribute(attention_fewkeys_kernel<16, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SDB_CHECK(cudaFuncSetAttribute(attention_fewkeys_kernel<32, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
   dim3 grid((unsigned)cdiv(Lq, FK_ROWS), (unsigned)B);
-  if (Lk <= 16)
-    (void)launch_k(attention_fewkeys_kernel<16>, grid, dim3(32 * heads), smem, as_stream(stream), q, ldq, k, ldk, v, ldv,
-                   (__half*)out, (int)Lq, (int)Lk, heads, scale, B * Lq * (int64_t)C);
-  else
-    (void)launch_k(attention_fewkeys_kernel<32>, grid, dim3(32 * heads), smem, as_stream(stream), q, ldq, k, ldk, v, ldv,
-                   (__half*)out, (int)Lq, (int)Lk, heads, scale, B * Lq * (int64_t)C);
+  const dim3 block(32 * heads);
+  cudaStream_t st = as_stream(stream);
+  const int64_t plane = B * Lq * (int64_t)C;
+#define SDB_FK_LAUNCH(K, T) \
+  (void)launch_k(attention_fewkeys_kernel<K, T>, grid, block, smem, st, q, ldq, k, ldk, v, ldv, (__half*)out, (int)Lq, (int)Lk, heads, scale, plane)
+  if (heads <= 8) { if (Lk <= 16) SDB_FK_LAUNCH(16, 256); else SDB_FK_LAUNCH(32, 256); }
+  else if (heads <= 12) { if (Lk <= 16) SDB_FK_LAUNCH(16, 384); else SDB_FK_LAUNCH(32, 384); }
+  else { if (Lk <= 16) SDB_FK_LAUNCH(16, 512); else SDB_FK_LAUNCH(32, 512); }
+#undef SDB_FK_LAUNCH
   SDB_LAUNCH_CHECK();
   return 0;
 }
