@@ -1203,7 +1203,7 @@ extern "C" int sdb_conv3_out(const float* h, const float* stats, const float* ga
   const int R = 2;
   const size_t smem_t = smem + (size_t)(R + 2) * (W + 2) * C * 4;
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-  if (W % 4 == 0 && C % 4 == 0 && (C / G) % 4 == 0 && smem_t <= 110 * 1024 && B <= 65535 && al16(h) && al16(gamma) &&
+  if (W % 4 == 0 && C % 4 == 0 && (C / G) % 4 == 0 && smem_t <= 200 * 1024 && B <= 65535 && al16(h) && al16(gamma) &&
       al16(beta)) {
     static size_t attr = 0;
     if (smem_t > attr) {
