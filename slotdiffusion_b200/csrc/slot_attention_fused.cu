@@ -117,14 +117,14 @@ __device__ __forceinline__ void tmem_ld_folded(uint32_t taddr, float (&out)[SP])
   }
 }
 
-// Two changes derived offline from the ncu source page of this kernel (profiles/README.md section 12) were made after the
-// round's GPU budget was spent.  They are compiled in only with -DSDB_SF_EXPERIMENTAL=1 (SDB_SF_EXPERIMENTAL=1 python -m
-// slotdiffusion_b200.build) until tools/gpu_round2_first.sh has run the parity tests and timed both builds:
+// Two changes derived offline from the ncu source page of this kernel (profiles/README.md section 12).  Run on the B200 in
+// round 2 (profiles/README.md section 13: parity tests green, attend 38.9 -> 36.9 us at B=64, 96.3 -> 92.2 us at B=256) and
+// the default since; -DSDB_SF_EXPERIMENTAL=0 builds the earlier form:
 //   * bounded-wait loops read the clock once per 256 / 4096 polls instead of on each one (poll loops were 40 % of the
 //     executed warp instructions: 18 -> 8 instructions per poll);
 //   * the converters zero rows beyond the end of a sample only in the partial last group (48 FSELs of 611 instructions).
 #ifndef SDB_SF_EXPERIMENTAL
-#define SDB_SF_EXPERIMENTAL 0
+#define SDB_SF_EXPERIMENTAL 1
 #endif
 #if SDB_SF_EXPERIMENTAL
 constexpr uint32_t SF_SPIN_CLOCK_MASK = 0xfffu;   // read the clock when (polls & mask) == 0
