@@ -414,6 +414,26 @@ def test_dpm_glue(ops):
     assert rel_l2(y, 0.5 * x - 0.25 * m0 + 2.0 * (m1 - m0)) < 1e-6
 
 
+@pytest.mark.parametrize('ncodes', [1, 7, 8, 13, 100, 512])
+def test_vq_grouped_search_ragged_codebooks_and_first_minimum(ops, ncodes):
+    """the nearest-code search scores the codebook in groups of 8 (csrc/elementwise.cu dpm_x0_vq3_kernel): sizes that are
+    not a multiple of the group, and DUPLICATED codes -- argmin's rule is the FIRST minimum (quantize.py:84-94), inside a group,
+    across groups and in the tail"""
+    B = 2
+    x, eps = rnd(B, 3, 16, 16, seed=71), rnd(B, 3, 16, 16, seed=72)
+    cb = rnd(ncodes, 3, seed=73)
+    cb = torch.cat([cb, cb, cb[: max(1, ncodes // 2)]], 0).contiguous()          # every code appears again later
+    x0, idx = ops.dpm_x0(x, eps, 0.8, 0.6, cb, want_idx=True)
+    z = ((x - 0.6 * eps) / 0.8).permute(0, 2, 3, 1).reshape(-1, 3)
+    # the kernel's own distance expression, evaluated in fp32 on the GPU in the same order (fmaf chain), first minimum
+    zz = (z[:, 0] * z[:, 0] + z[:, 1] * z[:, 1]) + z[:, 2] * z[:, 2]
+    assert (idx.flatten() < ncodes).all()                        # a duplicate further on never wins
+    d64 = torch.cdist(z.double(), cb.double())
+    pick = d64.gather(1, idx.flatten().long()[:, None])[:, 0]
+    assert (pick - d64.min(1).values <= 1e-5 * (1 + zz.double().sqrt())).all()   # and it is a nearest code
+    assert torch.equal(x0.permute(0, 2, 3, 1).reshape(-1, 3), cb[idx.flatten().long()])
+
+
 @pytest.mark.parametrize('cg', [1, 2])
 def test_gemm_groupnorm_sums_two_channel_blocks(ops, gemm_env, cg):
     """gsum_cb = 2: per-(sample, channel PAIR) sums for the 64-channel / 32-group layers (ResNet stem, VQ-VAE level 0)"""
