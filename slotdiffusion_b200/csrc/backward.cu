@@ -254,7 +254,9 @@ struct GnBwdArgs {
   float drop_p; unsigned long long seed; const unsigned long long* seed_dev;
 };
 
-template <bool APPLY>
+// ACT (0 none / 1 SiLU / 2 ReLU) and DROP are compile-time (instances, not flags: DESIGN.md section 4); the row loop is
+// unrolled so that the loads of several rows are in flight together (one row per trip left the kernel latency bound).
+template <bool APPLY, int ACT, bool DROP>
 __global__ void __launch_bounds__(256) groupnorm_bwd_kernel(const GnBwdArgs a) {
   __shared__ float s_mean[64], s_rstd[64], s_s1[64], s_s2[64];
   const int C = a.C1 + a.C2, c4n = C >> 2, cpg = C / a.G;
@@ -290,11 +292,12 @@ __global__ void __launch_bounds__(256) groupnorm_bwd_kernel(const GnBwdArgs a) {
   const int ld = from1 ? a.C1 : a.C2;
   float* dst = from1 ? a.dx1 + c : (a.dx2 ? a.dx2 + (c - a.C1) : nullptr);
   const float* add = from1 ? (a.add1 ? a.add1 + c : nullptr) : (a.add2 ? a.add2 + (c - a.C1) : nullptr);
-  const float inv_keep = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
-  const unsigned long long seed = a.seed + (a.seed_dev ? *a.seed_dev * 0x9E3779B97F4A7C15ull : 0ull);
+  const float inv_keep = DROP ? 1.f / (1.f - a.drop_p) : 1.f;
+  const unsigned long long seed = a.seed + ((DROP && a.seed_dev) ? *a.seed_dev * 0x9E3779B97F4A7C15ull : 0ull);
   float accA[4] = {0.f, 0.f, 0.f, 0.f}, accB[4] = {0.f, 0.f, 0.f, 0.f};
   const int r_begin = blockIdx.x * a.rows_per_chunk;
   const int r_end = min(a.HW, r_begin + a.rows_per_chunk);
+#pragma unroll 4
   for (int r = r_begin + ty; r < r_end; r += rpb) {
     const int64_t row = b * a.HW + r;
     const float4 xv = *reinterpret_cast<const float4*>(src + row * ld);
@@ -306,9 +309,9 @@ __global__ void __launch_bounds__(256) groupnorm_bwd_kernel(const GnBwdArgs a) {
     for (int j = 0; j < 4; ++j) {
       const float xh = (x[j] - mu[j]) * rs[j];
       float dz = d[j];
-      if (a.drop_p > 0.f) dz *= dropout_scale(seed, (unsigned long long)(row * C + c + j), a.drop_p, inv_keep);
-      if (a.silu == 1) dz *= silu_grad_f(xh * gm[j] + bt[j]);
-      else if (a.silu == 2) {
+      if (DROP) dz *= dropout_scale(seed, (unsigned long long)(row * C + c + j), a.drop_p, inv_keep);
+      if (ACT == 1) dz *= silu_grad_f(xh * gm[j] + bt[j]);
+      else if (ACT == 2) {
         // ReLU (ResNet18-GN encoder, resnet.py:76-78).  The mask must be the FORWARD's: the same expression as the operand
         // producer (elementwise.cu: v * (rstd gamma) + (beta - mean rstd gamma)), not an algebraically equal one -- an
         // input within round-off of zero would otherwise pass in one direction and be blocked in the other
@@ -916,10 +919,20 @@ extern "C" int sdb_groupnorm_bwd(const float* x1, int64_t C1, const float* x2, i
   cudaStream_t st = as_stream(stream);
   SDB_CHECK(cudaMemsetAsync(sums_work, 0, (size_t)B * C * 2 * sizeof(float), st));
   dim3 grid((unsigned)chunks, (unsigned)B);
-  groupnorm_bwd_kernel<false><<<grid, threads, 0, st>>>(a);
+  const bool drop = drop_p > 0.f;
+#define SDB_GNB_LAUNCH(APPLYv, ACTv, DROPv) groupnorm_bwd_kernel<APPLYv, ACTv, DROPv><<<grid, threads, 0, st>>>(a)
+#define SDB_GNB(APPLYv)                                                                             \
+  do {                                                                                              \
+    if (silu == 1) { if (drop) SDB_GNB_LAUNCH(APPLYv, 1, true); else SDB_GNB_LAUNCH(APPLYv, 1, false); }       \
+    else if (silu == 2) { if (drop) SDB_GNB_LAUNCH(APPLYv, 2, true); else SDB_GNB_LAUNCH(APPLYv, 2, false); }  \
+    else { if (drop) SDB_GNB_LAUNCH(APPLYv, 0, true); else SDB_GNB_LAUNCH(APPLYv, 0, false); }                 \
+  } while (0)
+  SDB_GNB(false);
   SDB_LAUNCH_CHECK();
-  groupnorm_bwd_kernel<true><<<grid, threads, 0, st>>>(a);
+  SDB_GNB(true);
   SDB_LAUNCH_CHECK();
+#undef SDB_GNB
+#undef SDB_GNB_LAUNCH
   groupnorm_bwd_param_kernel<<<(unsigned)cdiv(C, 128), 128, 0, st>>>(sums_work, dgamma, dbeta, B, (int)C);
   SDB_LAUNCH_CHECK();
   return 0;
