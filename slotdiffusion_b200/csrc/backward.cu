@@ -911,7 +911,9 @@ extern "C" int sdb_groupnorm_bwd(const float* x1, int64_t C1, const float* x2, i
   const int rpb = 256 / c4n > 0 ? 256 / c4n : 1;
   int threads = c4n * rpb;
   if (threads < 64) threads = 64;
-  int64_t chunks = cdiv((int64_t)num_sms() * 4, B);
+  // ONE wave: chunks * B CTAs must not exceed the resident slots (4 CTAs per SM) -- rounding UP left a second wave of a few
+  // CTAs that ran alone at a fraction of the bandwidth (ncu: 1.08 waves, SMs active 70 % of the kernel, profiles/README 23)
+  int64_t chunks = ((int64_t)num_sms() * 4) / B;
   if (chunks > cdiv(HW, rpb)) chunks = cdiv(HW, rpb);
   if (chunks < 1) chunks = 1;
   a.rows_per_chunk = (int)cdiv(HW, chunks);

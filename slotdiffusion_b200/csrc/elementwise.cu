@@ -1281,7 +1281,9 @@ extern "C" int sdb_groupnorm_apply_pack_fused(const float* x1, int64_t C1, const
   int threads = c4n * rpb;
   if (threads < 64) threads = 64;       // the first G threads also derive the statistics (G <= 64)
   // note: threads % c4n may be != 0 only in the clamp case; extra threads then map to ty >= rpb rows, still valid rows
-  int64_t chunks = cdiv((int64_t)num_sms() * 6, B);
+  // ONE wave: chunks * B CTAs must not exceed the resident slots (6 CTAs per SM) -- rounding UP left a second wave of a few
+  // CTAs that ran alone at a fraction of the bandwidth (ncu: 1.08 waves, SMs active 70 % of the kernel, profiles/README 23)
+  int64_t chunks = ((int64_t)num_sms() * 6) / B;
   if (chunks > cdiv(HW, rpb)) chunks = cdiv(HW, rpb);
   if (chunks < 1) chunks = 1;
   const int rows_per_chunk = (int)cdiv(HW, chunks);
@@ -1337,7 +1339,9 @@ extern "C" int sdb_channel_block_sums(const float* x, int64_t C, float* gsum, in
               "sdb_channel_block_sums: C=%lld unsupported", (long long)C);
   const int c4n = (int)(C / 4);
   const int rpb = 256 / c4n > 0 ? 256 / c4n : 1;
-  int64_t chunks = cdiv((int64_t)num_sms() * 4, B);
+  // ONE wave: chunks * B CTAs must not exceed the resident slots (4 CTAs per SM) -- rounding UP left a second wave of a few
+  // CTAs that ran alone at a fraction of the bandwidth (ncu: 1.08 waves, SMs active 70 % of the kernel, profiles/README 23)
+  int64_t chunks = ((int64_t)num_sms() * 4) / B;
   if (chunks > cdiv(HW, rpb)) chunks = cdiv(HW, rpb);
   if (chunks < 1) chunks = 1;
   const int rows_per_chunk = (int)cdiv(HW, chunks);
