@@ -909,7 +909,7 @@ __global__ void dpm_x0_kernel(const float* __restrict__ x, const float* __restri
 // the codebook as (e0, e1, e2, |e|^2) float4 rows in shared memory once; every thread scores PX pixels against each
 // broadcast row (one LDS.128 feeds PX * 5 FMA-pipe operations), strict '<' in increasing code order = argmin's first
 // minimum.  Same expanded distance |z|^2 + |e|^2 - 2 z.e as the reference, with the contraction order pinned by fmaf.
-constexpr int VQ_PX = 4;
+constexpr int VQ_PX = 5;          // 262 144 latent pixels (B = 256): 410 CTAs for the 444 resident slots = one wave (4: 512 CTAs, 1.15 waves)
 constexpr int VQ_THREADS = 128;
 constexpr int VQ_G = 8;          // codes per comparison group
 __global__ void __launch_bounds__(VQ_THREADS)
