@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(256, 4) layernorm_pack_kernel(const float* __r
 // a shifted single pass (Welford-free: subtract the first element as pivot) followed by an exact second pass
 // from L2 for the variance -- the activation of one sample-group (<= 128 KB) stays L2/L1 resident.
 __global__ void groupnorm_stats_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2, int C2,
-                                       float* __restrict__ stats, int64_t HW, int G, float eps) {
+                                       float* __restrict__ stats, int64_t HW, int G, float eps, int vec) {
   const int b = blockIdx.x / G, g = blockIdx.x % G;
   const int C = C1 + C2;
   const int cpg = C / G;
@@ -146,8 +146,27 @@ __global__ void groupnorm_stats_kernel(const float* __restrict__ x1, int C1, con
     const int c = c_begin + int(i % cpg);
     return (c < C1) ? x1[(b * HW + p) * C1 + c] : x2[(b * HW + p) * C2 + (c - C1)];
   };
+  // vec (launcher): groups of a multiple of 4 channels that do not straddle x1 | x2, 16-byte aligned rows, HW * cpg / 4 < 2^31
+  // -- float4 loads and 32-bit index arithmetic (the scalar form runs a 64-bit division and a modulo per ELEMENT)
+  const int q4 = cpg >> 2;
+  const unsigned n4 = vec ? (unsigned)(HW * q4) : 0u;
+  const bool in1 = c_begin < C1;
+  const float* vbase = (in1 ? x1 + c_begin : x2 + (c_begin - C1)) + (int64_t)b * HW * (in1 ? C1 : C2);
+  const int vld = in1 ? C1 : C2;
+  auto load4 = [&](unsigned i) -> float4 {
+    const unsigned p = i / (unsigned)q4, q = i - p * (unsigned)q4;
+    return *reinterpret_cast<const float4*>(vbase + (int64_t)p * vld + q * 4);
+  };
   float s = 0.f;
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += load(i);
+  if (vec) {
+#pragma unroll 4
+    for (unsigned i = threadIdx.x; i < n4; i += blockDim.x) {
+      const float4 v = load4(i);
+      s += (v.x + v.y) + (v.z + v.w);
+    }
+  } else {
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += load(i);
+  }
   s = warp_sum(s);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
   __syncthreads();
@@ -159,9 +178,18 @@ __global__ void groupnorm_stats_kernel(const float* __restrict__ x1, int C1, con
   __syncthreads();
   const float mean = s_mean;
   float ss = 0.f;
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-    const float d = load(i) - mean;
-    ss += d * d;
+  if (vec) {
+#pragma unroll 4
+    for (unsigned i = threadIdx.x; i < n4; i += blockDim.x) {
+      const float4 v = load4(i);
+      const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
+      ss += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+    }
+  } else {
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+      const float d = load(i) - mean;
+      ss += d * d;
+    }
   }
   ss = warp_sum(ss);
   __syncthreads();
@@ -1078,7 +1106,10 @@ extern "C" int sdb_groupnorm_stats(const float* x1, int64_t C1, const float* x2,
   SDB_REQUIRE(x1 && stats && B > 0 && HW > 0 && G > 0, "sdb_groupnorm_stats: bad args");
   SDB_REQUIRE((C1 + C2) % G == 0 && (C2 == 0 || x2), "sdb_groupnorm_stats: C=%lld not divisible by G=%d",
               (long long)(C1 + C2), G);
-  groupnorm_stats_kernel<<<(int)(B * G), 256, 0, as_stream(stream)>>>(x1, (int)C1, x2, (int)C2, stats, HW, G, eps);
+  const int64_t cpg = (C1 + C2) / G;
+  const bool vec = cpg % 4 == 0 && C1 % 4 == 0 && C2 % 4 == 0 && C1 % cpg == 0 && HW * (cpg / 4) < (1ll << 31) &&
+                   (reinterpret_cast<uintptr_t>(x1) & 15) == 0 && (!x2 || (reinterpret_cast<uintptr_t>(x2) & 15) == 0);
+  groupnorm_stats_kernel<<<(int)(B * G), 256, 0, as_stream(stream)>>>(x1, (int)C1, x2, (int)C2, stats, HW, G, eps, vec ? 1 : 0);
   SDB_LAUNCH_CHECK();
   return 0;
 }
